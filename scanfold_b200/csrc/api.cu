@@ -1,0 +1,709 @@
+// C-ABI of libscanfold_b200.so (include/scanfold_b200.h).  Host-side orchestration only: every fold,
+// shuffle and accumulation runs in the CUDA kernels of mfe.cu / pf.cu / shuffle.cu.  No CPU fallback.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <dlfcn.h>
+#include <memory>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/scanfold_b200.h"
+#include "device_common.cuh"
+
+namespace {
+
+using namespace sfb;
+
+struct Context {
+    bool ready = false;
+    int device = -1, n_sm = 0;
+    HostParams hp;
+    double pf_temperature = -1e9;
+    MfeTables *d_mfe = nullptr;
+    PfTables *d_pf = nullptr;
+    cudaStream_t stream = nullptr;
+};
+
+Context g_ctx;
+std::mutex g_mu;
+thread_local std::string g_err;
+
+int fail(int code, const std::string &msg) {
+    g_err = msg;
+    return code;
+}
+
+struct CudaError : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+#define CK(expr)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e__ = (expr);                                                                        \
+        if (e__ != cudaSuccess)                                                                          \
+            throw CudaError(std::string(#expr) + ": " + cudaGetErrorString(e__));                        \
+    } while (0)
+
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    ~DevBuf() { release(); }
+    void alloc(size_t count) {
+        release();
+        n = count;
+        if (count) CK(cudaMalloc(&p, count * sizeof(T)));
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+};
+
+std::string default_par_path() {
+    Dl_info info;
+    if (dladdr((void *)&sfb_version, &info) && info.dli_fname) {
+        std::string so = info.dli_fname;
+        size_t k = so.find_last_of('/');
+        std::string dir = k == std::string::npos ? "." : so.substr(0, k);
+        return dir + "/params/rna_turner2004_besteffort.par";
+    }
+    return "rna_turner2004_besteffort.par";
+}
+
+void ensure_pf_tables(double temperature) {
+    if (g_ctx.d_pf && g_ctx.pf_temperature == temperature) return;
+    static PfTables host_pf;
+    make_pf_tables(g_ctx.hp, temperature, host_pf);
+    if (!g_ctx.d_pf) CK(cudaMalloc(&g_ctx.d_pf, sizeof(PfTables)));
+    CK(cudaMemcpy(g_ctx.d_pf, &host_pf, sizeof(PfTables), cudaMemcpyHostToDevice));
+    g_ctx.pf_temperature = temperature;
+}
+
+int check_model(const sfb_model *m) {
+    if (!g_ctx.ready) return fail(SFB_E_STATE, "sfb_init has not been called");
+    if (m && std::fabs(m->temperature - 37.0) > 1e-9)
+        return fail(SFB_E_PARAMS,
+                    "temperature != 37 needs enthalpy rescaling of every table, which this build does not do "
+                    "(SURVEY 8f row f3)");
+    return 0;
+}
+
+void encode_host(const uint8_t *ascii, size_t n, std::vector<uint8_t> &codes) {
+    codes.resize(n);
+    for (size_t k = 0; k < n; k++) codes[k] = (uint8_t)encode_nt(ascii[k]);
+}
+
+// ---------------------------------------------------------------------------------------------
+struct FoldWork {  // device scratch for one MFE launch
+    DevBuf<int32_t> scratch;
+    int mode = 0;
+    size_t per_cta = 0;
+    void prepare(int W, int n_fold) {
+        per_cta = mfe_scratch_ints_per_cta(W, &mode);
+        size_t need = per_cta * (size_t)mfe_grid_size(W, g_ctx.n_sm, n_fold);
+        if (need > scratch.n) scratch.alloc(need);
+    }
+    void fill(MfeLaunch &L) const {
+        L.gscratch = scratch.p;
+        L.gscratch_per_cta = (long long)per_cta;
+        L.mats_in_gmem = mode;
+    }
+};
+
+struct PfWork {
+    DevBuf<double> scratch;
+    size_t per_cta = 0;
+    void prepare(int W, int n_fold) {
+        per_cta = pf_scratch_doubles_per_cta(W);
+        size_t need = per_cta * (size_t)pf_grid_size(W, g_ctx.n_sm, n_fold);
+        if (need > scratch.n) scratch.alloc(need);
+    }
+};
+
+}  // namespace
+
+// =================================================================================================
+struct sfb_scan_plan {
+    sfb_scan_args a;
+    int n_slots = 0;        // n_windows + final
+    int chunk = 0;          // windows per chunk
+    bool constrained = false;
+    std::vector<uint8_t> parity_host;  // not owned copy avoided: pointer kept in a.parity_shuffles
+    DevBuf<uint8_t> seq, hc, nat, shuf, hc_win, parity_ascii;
+    DevBuf<int32_t> es1, sc_win;
+    DevBuf<int32_t> mfe, nat_unc, shuf_e, e_tmp;
+    DevBuf<int16_t> pair_tbl, centroid;
+    DevBuf<double> ed, dG;
+    DevBuf<uint8_t> shuf_all;  // only when shuffles_out requested at fetch time (kept per chunk -> full)
+    FoldWork fw;
+    PfWork pw;
+    bool keep_shuffles = false;
+};
+
+extern "C" {
+
+int sfb_version(void) { return SFB_VERSION; }
+
+const char *sfb_last_error(void) { return g_err.c_str(); }
+
+int sfb_params_besteffort(void) { return g_ctx.ready && g_ctx.hp.besteffort ? 1 : 0; }
+
+int sfb_init(int device_ordinal, const char *par_file_or_null) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    try {
+        std::string path = par_file_or_null && *par_file_or_null ? par_file_or_null : default_par_path();
+        try {
+            load_params(path, g_ctx.hp);
+        } catch (const std::exception &e) {
+            return fail(SFB_E_PARAMS, e.what());
+        }
+        int n_dev = 0;
+        cudaError_t e = cudaGetDeviceCount(&n_dev);
+        if (e != cudaSuccess || n_dev == 0)
+            return fail(SFB_E_CUDA, std::string("no CUDA device available: ") + cudaGetErrorString(e) +
+                                        " (this library has no CPU fallback)");
+        if (device_ordinal < 0 || device_ordinal >= n_dev) return fail(SFB_E_ARG, "device ordinal out of range");
+        CK(cudaSetDevice(device_ordinal));
+        cudaDeviceProp prop;
+        CK(cudaGetDeviceProperties(&prop, device_ordinal));
+        g_ctx.device = device_ordinal;
+        g_ctx.n_sm = prop.multiProcessorCount;
+        if (!g_ctx.stream) CK(cudaStreamCreateWithFlags(&g_ctx.stream, cudaStreamNonBlocking));
+        if (!g_ctx.d_mfe) CK(cudaMalloc(&g_ctx.d_mfe, sizeof(MfeTables)));
+        CK(cudaMemcpy(g_ctx.d_mfe, &g_ctx.hp.mfe, sizeof(MfeTables), cudaMemcpyHostToDevice));
+        g_ctx.pf_temperature = -1e9;
+        g_ctx.ready = true;
+        ensure_pf_tables(37.0);
+        return 0;
+    } catch (const CudaError &e) {
+        return fail(SFB_E_CUDA, e.what());
+    }
+}
+
+void sfb_shutdown(void) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_ctx.d_mfe) cudaFree(g_ctx.d_mfe);
+    if (g_ctx.d_pf) cudaFree(g_ctx.d_pf);
+    if (g_ctx.stream) cudaStreamDestroy(g_ctx.stream);
+    g_ctx = Context();
+}
+
+int sfb_deigan(const double *react1, int n, double m, double b, int32_t *es1) {
+    if (!react1 || !es1 || n < 0) return fail(SFB_E_ARG, "sfb_deigan: bad argument");
+    es1[0] = 0;
+    for (int i = 1; i <= n; i++) {
+        double v = react1[i] < 0 ? 0. : m * std::log(react1[i] + 1) + b;
+        es1[i] = (int32_t)roundf((float)(v * 100.));
+    }
+    return 0;
+}
+
+int sfb_fold_batch(const uint8_t *seqs, int n_seq, int len, const sfb_model *model, const uint8_t *hc,
+                   const int32_t *sc, int32_t *e_dcal, int16_t *pair_tbl) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (int rc = check_model(model)) return rc;
+    if (!seqs || !e_dcal || n_seq < 0 || len < 1) return fail(SFB_E_ARG, "sfb_fold_batch: bad argument");
+    if (len > MAX_W) return fail(SFB_E_RANGE, "fold length exceeds MAX_W");
+    if (n_seq == 0) return 0;
+    try {
+        CK(cudaSetDevice(g_ctx.device));
+        std::vector<uint8_t> codes;
+        encode_host(seqs, (size_t)n_seq * len, codes);
+        DevBuf<uint8_t> d_seq, d_hc;
+        DevBuf<int32_t> d_sc, d_e;
+        DevBuf<int16_t> d_pt;
+        d_seq.alloc(codes.size());
+        CK(cudaMemcpyAsync(d_seq.p, codes.data(), codes.size(), cudaMemcpyHostToDevice, g_ctx.stream));
+        if (hc) {
+            d_hc.alloc((size_t)n_seq * len);
+            CK(cudaMemcpyAsync(d_hc.p, hc, (size_t)n_seq * len, cudaMemcpyHostToDevice, g_ctx.stream));
+        }
+        if (sc) {
+            d_sc.alloc((size_t)n_seq * (len + 1));
+            CK(cudaMemcpyAsync(d_sc.p, sc, sizeof(int32_t) * (size_t)n_seq * (len + 1), cudaMemcpyHostToDevice,
+                               g_ctx.stream));
+        }
+        d_e.alloc(n_seq);
+        if (pair_tbl) d_pt.alloc((size_t)n_seq * len);
+        FoldWork fw;
+        fw.prepare(len, n_seq);
+        MfeLaunch L{};
+        L.seqs = d_seq.p;
+        L.hc = d_hc.p;
+        L.sc = d_sc.p;
+        L.n_fold = n_seq;
+        L.W = len;
+        L.max_span = model ? model->max_bp_span : 0;
+        L.e_out = d_e.p;
+        L.pair_tbl = d_pt.p;
+        fw.fill(L);
+        launch_mfe(L, g_ctx.d_mfe, g_ctx.n_sm, g_ctx.stream, nullptr);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(e_dcal, d_e.p, sizeof(int32_t) * n_seq, cudaMemcpyDeviceToHost, g_ctx.stream));
+        if (pair_tbl)
+            CK(cudaMemcpyAsync(pair_tbl, d_pt.p, sizeof(int16_t) * (size_t)n_seq * len, cudaMemcpyDeviceToHost,
+                               g_ctx.stream));
+        CK(cudaStreamSynchronize(g_ctx.stream));
+        for (int k = 0; k < n_seq; k++)
+            if (e_dcal[k] >= SFB_INF) return fail(SFB_E_CUDA, "traceback failed for fold " + std::to_string(k));
+        return 0;
+    } catch (const CudaError &e) {
+        return fail(SFB_E_CUDA, e.what());
+    }
+}
+
+int sfb_pf_batch(const uint8_t *seqs, int n_seq, int len, const sfb_model *model, const uint8_t *hc,
+                 const int32_t *sc, double *ensemble_dG, double *ed, int16_t *centroid_tbl, double *bpp) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (int rc = check_model(model)) return rc;
+    if (!seqs || !ed || !ensemble_dG || !centroid_tbl || n_seq < 0 || len < 1)
+        return fail(SFB_E_ARG, "sfb_pf_batch: bad argument");
+    if (len > MAX_W) return fail(SFB_E_RANGE, "fold length exceeds MAX_W");
+    if (n_seq == 0) return 0;
+    try {
+        CK(cudaSetDevice(g_ctx.device));
+        ensure_pf_tables(model ? model->temperature : 37.0);
+        std::vector<uint8_t> codes;
+        encode_host(seqs, (size_t)n_seq * len, codes);
+        DevBuf<uint8_t> d_seq, d_hc;
+        DevBuf<int32_t> d_sc;
+        DevBuf<double> d_dG, d_ed, d_bpp;
+        DevBuf<int16_t> d_cen;
+        d_seq.alloc(codes.size());
+        CK(cudaMemcpyAsync(d_seq.p, codes.data(), codes.size(), cudaMemcpyHostToDevice, g_ctx.stream));
+        if (hc) {
+            d_hc.alloc((size_t)n_seq * len);
+            CK(cudaMemcpyAsync(d_hc.p, hc, (size_t)n_seq * len, cudaMemcpyHostToDevice, g_ctx.stream));
+        }
+        if (sc) {
+            d_sc.alloc((size_t)n_seq * (len + 1));
+            CK(cudaMemcpyAsync(d_sc.p, sc, sizeof(int32_t) * (size_t)n_seq * (len + 1), cudaMemcpyHostToDevice,
+                               g_ctx.stream));
+        }
+        d_dG.alloc(n_seq);
+        d_ed.alloc(n_seq);
+        d_cen.alloc((size_t)n_seq * len);
+        if (bpp) {
+            d_bpp.alloc((size_t)n_seq * len * len);
+            CK(cudaMemsetAsync(d_bpp.p, 0, sizeof(double) * d_bpp.n, g_ctx.stream));
+        }
+        PfWork pw;
+        pw.prepare(len, n_seq);
+        PfLaunch L{};
+        L.seqs = d_seq.p;
+        L.hc = d_hc.p;
+        L.sc = d_sc.p;
+        L.n_fold = n_seq;
+        L.W = len;
+        L.max_span = model ? model->max_bp_span : 0;
+        L.dG = d_dG.p;
+        L.ed = d_ed.p;
+        L.centroid = d_cen.p;
+        L.bpp = d_bpp.p;
+        L.gscratch = pw.scratch.p;
+        L.gscratch_per_cta = (long long)pw.per_cta;
+        launch_pf(L, g_ctx.d_mfe, g_ctx.d_pf, g_ctx.n_sm, g_ctx.stream, nullptr);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(ensemble_dG, d_dG.p, sizeof(double) * n_seq, cudaMemcpyDeviceToHost, g_ctx.stream));
+        CK(cudaMemcpyAsync(ed, d_ed.p, sizeof(double) * n_seq, cudaMemcpyDeviceToHost, g_ctx.stream));
+        CK(cudaMemcpyAsync(centroid_tbl, d_cen.p, sizeof(int16_t) * (size_t)n_seq * len, cudaMemcpyDeviceToHost,
+                           g_ctx.stream));
+        if (bpp)
+            CK(cudaMemcpyAsync(bpp, d_bpp.p, sizeof(double) * d_bpp.n, cudaMemcpyDeviceToHost, g_ctx.stream));
+        CK(cudaStreamSynchronize(g_ctx.stream));
+        return 0;
+    } catch (const CudaError &e) {
+        return fail(SFB_E_CUDA, e.what());
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+int sfb_scan_plan_create(const sfb_scan_args *args, sfb_scan_plan **plan_out) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!args || !plan_out) return fail(SFB_E_ARG, "sfb_scan_plan_create: null argument");
+    if (int rc = check_model(&args->model)) return rc;
+    const sfb_scan_args &a = *args;
+    if (!a.seq || a.L < 1 || a.W < 1 || a.W > a.L || a.step < 1 || a.r < 0 || a.n_windows < 0 || a.first_window < 0)
+        return fail(SFB_E_ARG, "sfb_scan_plan_create: bad geometry");
+    if (a.W > MAX_W) return fail(SFB_E_RANGE, "window exceeds MAX_W");
+    const int total_windows = (a.L - a.W) / a.step + 1;
+    if (a.first_window + a.n_windows > total_windows) return fail(SFB_E_ARG, "window range exceeds the record");
+    if (a.final_window && (a.n_windows == 0 || a.first_window + a.n_windows != total_windows))
+        return fail(SFB_E_ARG, "final_window requires the shard that holds the last regular window");
+    if (a.shuffle_type != SFB_SHUFFLE_MONO && a.shuffle_type != SFB_SHUFFLE_DI)
+        return fail(SFB_E_ARG, "unknown shuffle type");
+    try {
+        CK(cudaSetDevice(g_ctx.device));
+        ensure_pf_tables(a.model.temperature);
+        auto *P = new sfb_scan_plan();
+        std::unique_ptr<sfb_scan_plan> guard(P);
+        P->a = a;
+        P->n_slots = a.n_windows + (a.final_window ? 1 : 0);
+        P->constrained = a.hc || a.react;
+        const int n = P->n_slots;
+        long long per_win = (long long)std::max(a.r, 1) * a.W;
+        long long chunk = (768ll << 20) / std::max(per_win, 1ll);
+        chunk = std::max(1ll, std::min<long long>(chunk, 65536));
+        P->chunk = (int)std::min<long long>(chunk, std::max(n, 1));
+        const size_t cap = (size_t)P->chunk + 1;  // the final-window slot may ride on the last chunk
+
+        std::vector<uint8_t> codes;
+        encode_host(a.seq, a.L, codes);
+        P->seq.alloc(a.L);
+        CK(cudaMemcpyAsync(P->seq.p, codes.data(), a.L, cudaMemcpyHostToDevice, g_ctx.stream));
+        if (a.hc) {
+            P->hc.alloc(a.L);
+            CK(cudaMemcpyAsync(P->hc.p, a.hc, a.L, cudaMemcpyHostToDevice, g_ctx.stream));
+            P->hc_win.alloc(cap * a.W);
+        }
+        if (a.react) {
+            std::vector<int32_t> es(a.L + 1);
+            sfb_deigan(a.react, a.L, a.shape_m, a.shape_b, es.data());
+            P->es1.alloc(a.L + 1);
+            CK(cudaMemcpyAsync(P->es1.p, es.data(), sizeof(int32_t) * (a.L + 1), cudaMemcpyHostToDevice, g_ctx.stream));
+            CK(cudaStreamSynchronize(g_ctx.stream));
+            P->sc_win.alloc(cap * (a.W + 1));
+        }
+        CK(cudaStreamSynchronize(g_ctx.stream));
+        P->nat.alloc(cap * a.W);
+        P->shuf.alloc(cap * std::max(a.r, 1) * a.W);
+        if (a.parity_shuffles) P->parity_ascii.alloc(cap * std::max(a.r, 1) * a.W);
+        P->mfe.alloc(std::max(n, 1));
+        P->nat_unc.alloc(std::max(n, 1));
+        P->shuf_e.alloc((size_t)std::max(n, 1) * std::max(a.r, 1));
+        P->pair_tbl.alloc((size_t)std::max(n, 1) * a.W);
+        P->centroid.alloc((size_t)std::max(n, 1) * a.W);
+        P->ed.alloc(std::max(n, 1));
+        P->dG.alloc(std::max(n, 1));
+        CK(cudaMemset(P->centroid.p, 0, sizeof(int16_t) * P->centroid.n));
+        CK(cudaMemset(P->ed.p, 0, sizeof(double) * P->ed.n));
+        CK(cudaMemset(P->dG.p, 0, sizeof(double) * P->dG.n));
+        P->fw.prepare(a.W, (int)cap * std::max(a.r, 1));
+        if (a.want_pf) P->pw.prepare(a.W, (int)cap);
+        *plan_out = guard.release();
+        return 0;
+    } catch (const CudaError &e) {
+        return fail(SFB_E_CUDA, e.what());
+    } catch (const std::bad_alloc &) {
+        return fail(SFB_E_CUDA, "out of host memory");
+    }
+}
+
+void sfb_scan_plan_keep_shuffles(sfb_scan_plan *plan) {
+    if (!plan || plan->keep_shuffles) return;
+    plan->keep_shuffles = true;
+    plan->shuf_all.alloc((size_t)std::max(plan->n_slots, 1) * std::max(plan->a.r, 1) * plan->a.W);
+}
+
+__global__ void encode_ascii_kernel(const uint8_t *in, uint8_t *out, long long n) {
+    long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    uint8_t c = in[k];
+    out[k] = (c == 'A' || c == 'a') ? 1 : (c == 'C' || c == 'c') ? 2 : (c == 'G' || c == 'g') ? 3
+           : (c == 'U' || c == 'u' || c == 'T' || c == 't') ? 4 : 0;
+}
+
+__global__ void copy_last_slot_kernel(int32_t *mfe, int16_t *pair_tbl, int16_t *centroid, double *ed, double *dG,
+                                      int last, int fin, int W, int copy_pf) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k == 0) {
+        mfe[fin] = mfe[last];
+        if (copy_pf) {
+            ed[fin] = ed[last];
+            dG[fin] = dG[last];
+        }
+    }
+    if (k < W) {
+        pair_tbl[(long long)fin * W + k] = pair_tbl[(long long)last * W + k];
+        if (copy_pf) centroid[(long long)fin * W + k] = centroid[(long long)last * W + k];
+    }
+}
+
+int sfb_scan_plan_run(sfb_scan_plan *P, float *ms_total, float *ms_mfe, int32_t *n_launches_out) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!P) return fail(SFB_E_ARG, "null plan");
+    if (!g_ctx.ready) return fail(SFB_E_STATE, "sfb_init has not been called");
+    const sfb_scan_args &a = P->a;
+    cudaStream_t st = g_ctx.stream;
+    int n_launch = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, em0 = nullptr, em1 = nullptr;
+    try {
+        CK(cudaSetDevice(g_ctx.device));
+        CK(cudaEventCreate(&ev0));
+        CK(cudaEventCreate(&ev1));
+        CK(cudaEventCreate(&em0));
+        CK(cudaEventCreate(&em1));
+        float mfe_ms = 0.f;
+        CK(cudaEventRecord(ev0, st));
+        const int n = P->n_slots, r = a.r, W = a.W;
+        for (int c0 = 0, cn = 0; c0 < n; c0 += cn) {
+            cn = std::min(P->chunk, n - c0);
+            if (a.final_window && n - (c0 + cn) == 1) cn++;  // never leave the final-window slot alone
+            const bool has_final = a.final_window && (c0 + cn == n);
+            const int cn_regular = cn - (has_final ? 1 : 0);
+            // natives (final slot = seq[L-W:L])
+            launch_gather_windows(P->seq.p, a.L, W, a.step, a.first_window + c0, cn, has_final, P->nat.p, st, &n_launch);
+            // background sequences
+            if (r > 0) {
+                if (a.parity_shuffles) {
+                    size_t bytes = (size_t)cn * r * W;
+                    CK(cudaMemcpyAsync(P->parity_ascii.p, a.parity_shuffles + (size_t)c0 * r * W, bytes,
+                                       cudaMemcpyHostToDevice, st));
+                    encode_ascii_kernel<<<(unsigned)((bytes + 255) / 256), 256, 0, st>>>(P->parity_ascii.p, P->shuf.p,
+                                                                                       (long long)bytes);
+                    n_launch++;
+                } else {
+                    ShuffleLaunch S{};
+                    S.seq_codes = P->seq.p;
+                    S.L = a.L;
+                    S.W = W;
+                    S.step = a.step;
+                    S.r = r;
+                    S.type = a.shuffle_type;
+                    S.seed = a.seed;
+                    S.first_window = a.first_window + c0;
+                    S.n_windows = cn;
+                    S.final_slot = has_final;
+                    S.global_window_base = a.first_window + c0;
+                    S.out = P->shuf.p;
+                    launch_shuffle(S, st, &n_launch);
+                }
+                if (P->keep_shuffles)
+                    CK(cudaMemcpyAsync(P->shuf_all.p + (size_t)c0 * r * W, P->shuf.p, (size_t)cn * r * W,
+                                       cudaMemcpyDeviceToDevice, st));
+            }
+            CK(cudaEventRecord(em0, st));
+            // r background folds per window, energy only (ScanFoldFunctions.py:805-814)
+            if (r > 0) {
+                MfeLaunch L{};
+                L.seqs = P->shuf.p;
+                L.n_fold = cn * r;
+                L.W = W;
+                L.max_span = 0;
+                L.e_out = P->shuf_e.p + (size_t)c0 * r;
+                P->fw.fill(L);
+                launch_mfe(L, g_ctx.d_mfe, g_ctx.n_sm, st, &n_launch);
+            }
+            // energy_list[0]: native without constraints / span (ScanFoldFunctions.py:774-789)
+            const bool need_unc = P->constrained || a.model.max_bp_span > 0;
+            {
+                MfeLaunch L{};
+                L.seqs = P->nat.p;
+                L.n_fold = cn;
+                L.W = W;
+                L.max_span = 0;
+                L.e_out = P->nat_unc.p + c0;
+                L.pair_tbl = need_unc ? nullptr : P->pair_tbl.p + (size_t)c0 * W;
+                P->fw.fill(L);
+                launch_mfe(L, g_ctx.d_mfe, g_ctx.n_sm, st, &n_launch);
+            }
+            // native fold with md / hc / sc and structure (ScanFold.py:494-497,512-513,534-541)
+            if (need_unc && cn_regular > 0) {
+                if (a.hc) launch_slice_hc(P->hc.p, a.L, W, a.step, a.first_window + c0, cn_regular, 0, P->hc_win.p, st, &n_launch);
+                if (a.react)
+                    launch_slice_sc(P->es1.p, a.L, W, a.step, a.first_window + c0, cn_regular, 0, P->sc_win.p, st, &n_launch);
+                MfeLaunch L{};
+                L.seqs = P->nat.p;
+                L.hc = a.hc ? P->hc_win.p : nullptr;
+                L.sc = a.react ? P->sc_win.p : nullptr;
+                L.n_fold = cn_regular;
+                L.W = W;
+                L.max_span = a.model.max_bp_span;
+                L.e_out = P->mfe.p + c0;
+                L.pair_tbl = P->pair_tbl.p + (size_t)c0 * W;
+                P->fw.fill(L);
+                launch_mfe(L, g_ctx.d_mfe, g_ctx.n_sm, st, &n_launch);
+            } else if (!need_unc) {
+                CK(cudaMemcpyAsync(P->mfe.p + c0, P->nat_unc.p + c0, sizeof(int32_t) * cn, cudaMemcpyDeviceToDevice, st));
+            }
+            CK(cudaEventRecord(em1, st));
+            // partition function of the native window: sees hc (ScanFold.py:512-514) but not sc (:525)
+            if (a.want_pf && cn_regular > 0) {
+                PfLaunch L{};
+                L.seqs = P->nat.p;
+                L.hc = a.hc ? P->hc_win.p : nullptr;
+                L.n_fold = cn_regular;
+                L.W = W;
+                L.max_span = a.model.max_bp_span;
+                L.dG = P->dG.p + c0;
+                L.ed = P->ed.p + c0;
+                L.centroid = P->centroid.p + (size_t)c0 * W;
+                L.gscratch = P->pw.scratch.p;
+                L.gscratch_per_cta = (long long)P->pw.per_cta;
+                launch_pf(L, g_ctx.d_mfe, g_ctx.d_pf, g_ctx.n_sm, st, &n_launch);
+            }
+            if (has_final) {
+                // Q5: the final-window block re-evaluates the STALE fold compound of the last regular window
+                const int last = n - 2, fin = n - 1;
+                int copy_pf = 1;
+                if (a.want_pf && a.react) {  // stale fc now carries the soft constraints: pf() sees them
+                    PfLaunch L{};
+                    L.seqs = P->nat.p + (size_t)(cn_regular - 1) * W;
+                    L.sc = P->sc_win.p + (size_t)(cn_regular - 1) * (W + 1);
+                    L.n_fold = 1;
+                    L.W = W;
+                    L.max_span = a.model.max_bp_span;
+                    L.dG = P->dG.p + fin;
+                    L.ed = P->ed.p + fin;
+                    L.centroid = P->centroid.p + (size_t)fin * W;
+                    L.gscratch = P->pw.scratch.p;
+                    L.gscratch_per_cta = (long long)P->pw.per_cta;
+                    launch_pf(L, g_ctx.d_mfe, g_ctx.d_pf, g_ctx.n_sm, st, &n_launch);
+                    copy_pf = 0;
+                }
+                copy_last_slot_kernel<<<(W + 127) / 128, 128, 0, st>>>(P->mfe.p, P->pair_tbl.p, P->centroid.p, P->ed.p,
+                                                                       P->dG.p, last, fin, W, copy_pf);
+                n_launch++;
+            }
+            CK(cudaEventSynchronize(em1));
+            float ms = 0.f;
+            CK(cudaEventElapsedTime(&ms, em0, em1));
+            mfe_ms += ms;
+        }
+        CK(cudaEventRecord(ev1, st));
+        CK(cudaEventSynchronize(ev1));
+        CK(cudaGetLastError());
+        float tot = 0.f;
+        CK(cudaEventElapsedTime(&tot, ev0, ev1));
+        if (ms_total) *ms_total = tot;
+        if (ms_mfe) *ms_mfe = mfe_ms;
+        if (n_launches_out) *n_launches_out = n_launch;
+        cudaEventDestroy(ev0);
+        cudaEventDestroy(ev1);
+        cudaEventDestroy(em0);
+        cudaEventDestroy(em1);
+        return 0;
+    } catch (const CudaError &e) {
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
+        if (em0) cudaEventDestroy(em0);
+        if (em1) cudaEventDestroy(em1);
+        return fail(SFB_E_CUDA, e.what());
+    }
+}
+
+int sfb_scan_plan_fetch(sfb_scan_plan *P, sfb_scan_out *out) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!P || !out) return fail(SFB_E_ARG, "null argument");
+    try {
+        CK(cudaSetDevice(g_ctx.device));
+        const int n = P->n_slots, W = P->a.W, r = P->a.r;
+        cudaStream_t st = g_ctx.stream;
+        auto d2h = [&](void *dst, const void *src, size_t bytes) {
+            if (dst && bytes) CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st));
+        };
+        d2h(out->mfe_dcal, P->mfe.p, sizeof(int32_t) * n);
+        d2h(out->native_unconstrained_dcal, P->nat_unc.p, sizeof(int32_t) * n);
+        d2h(out->shuffle_dcal, P->shuf_e.p, sizeof(int32_t) * (size_t)n * r);
+        d2h(out->pair_tbl, P->pair_tbl.p, sizeof(int16_t) * (size_t)n * W);
+        d2h(out->centroid_tbl, P->centroid.p, sizeof(int16_t) * (size_t)n * W);
+        d2h(out->ed, P->ed.p, sizeof(double) * n);
+        d2h(out->ensemble_dG, P->dG.p, sizeof(double) * n);
+        if (out->shuffles_out) {
+            if (!P->keep_shuffles) return fail(SFB_E_STATE, "shuffles were not kept: call sfb_scan_plan_keep_shuffles before run");
+            d2h(out->shuffles_out, P->shuf_all.p, (size_t)n * r * W);
+        }
+        CK(cudaStreamSynchronize(st));
+        if (out->shuffles_out) {
+            static const char dec[5] = {'N', 'A', 'C', 'G', 'U'};
+            size_t m = (size_t)n * r * W;
+            for (size_t k = 0; k < m; k++) out->shuffles_out[k] = (uint8_t)dec[out->shuffles_out[k] % 5];
+        }
+        if (out->mfe_dcal)
+            for (int k = 0; k < n; k++)
+                if (out->mfe_dcal[k] >= SFB_INF) return fail(SFB_E_CUDA, "traceback failed in window slot " + std::to_string(k));
+        return 0;
+    } catch (const CudaError &e) {
+        return fail(SFB_E_CUDA, e.what());
+    }
+}
+
+void sfb_scan_plan_destroy(sfb_scan_plan *plan) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    delete plan;
+}
+
+int sfb_scan(const sfb_scan_args *args, sfb_scan_out *out) {
+    sfb_scan_plan *P = nullptr;
+    int rc = sfb_scan_plan_create(args, &P);
+    if (rc) return rc;
+    if (out && out->shuffles_out) sfb_scan_plan_keep_shuffles(P);
+    rc = sfb_scan_plan_run(P, nullptr, nullptr, nullptr);
+    if (!rc) rc = sfb_scan_plan_fetch(P, out);
+    sfb_scan_plan_destroy(P);
+    return rc;
+}
+
+int sfb_accumulate(const sfb_accum_args *args, int64_t *count, int64_t *sum_z100, int64_t *sum_mfe,
+                   int64_t *sum_ed100, int32_t *first_seen) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!g_ctx.ready) return fail(SFB_E_STATE, "sfb_init has not been called");
+    if (!args || !count || !sum_z100 || !sum_mfe || !sum_ed100 || !first_seen) return fail(SFB_E_ARG, "null argument");
+    const sfb_accum_args &a = *args;
+    if (a.L < 1 || a.W < 1 || a.step < 1 || a.n_windows < 0) return fail(SFB_E_ARG, "bad geometry");
+    try {
+        CK(cudaSetDevice(g_ctx.device));
+        cudaStream_t st = g_ctx.stream;
+        const size_t cells = (size_t)a.L * (2 * a.W - 1);
+        DevBuf<long long> d_cnt, d_z, d_m, d_e;
+        DevBuf<int32_t> d_fs, d_z100, d_mfe, d_ed100;
+        DevBuf<int16_t> d_pt;
+        d_cnt.alloc(cells);
+        d_z.alloc(cells);
+        d_m.alloc(cells);
+        d_e.alloc(cells);
+        d_fs.alloc(cells);
+        CK(cudaMemsetAsync(d_cnt.p, 0, cells * 8, st));
+        CK(cudaMemsetAsync(d_z.p, 0, cells * 8, st));
+        CK(cudaMemsetAsync(d_m.p, 0, cells * 8, st));
+        CK(cudaMemsetAsync(d_e.p, 0, cells * 8, st));
+        CK(cudaMemsetAsync(d_fs.p, 0x7F, cells * 4, st));
+        const size_t nw = std::max(a.n_windows, 1);
+        d_pt.alloc(nw * a.W);
+        d_z100.alloc(nw);
+        d_mfe.alloc(nw);
+        d_ed100.alloc(nw);
+        if (a.n_windows) {
+            CK(cudaMemcpyAsync(d_pt.p, a.pair_tbl, sizeof(int16_t) * (size_t)a.n_windows * a.W, cudaMemcpyHostToDevice, st));
+            CK(cudaMemcpyAsync(d_z100.p, a.z100, sizeof(int32_t) * a.n_windows, cudaMemcpyHostToDevice, st));
+            CK(cudaMemcpyAsync(d_mfe.p, a.mfe_dcal, sizeof(int32_t) * a.n_windows, cudaMemcpyHostToDevice, st));
+            CK(cudaMemcpyAsync(d_ed100.p, a.ed100, sizeof(int32_t) * a.n_windows, cudaMemcpyHostToDevice, st));
+            AccumLaunch A{};
+            A.L = a.L;
+            A.W = a.W;
+            A.step = a.step;
+            A.first_window = a.first_window;
+            A.n_windows = a.n_windows;
+            A.pair_tbl = d_pt.p;
+            A.z100 = d_z100.p;
+            A.mfe = d_mfe.p;
+            A.ed100 = d_ed100.p;
+            A.count = d_cnt.p;
+            A.sum_z = d_z.p;
+            A.sum_mfe = d_m.p;
+            A.sum_ed = d_e.p;
+            A.first_seen = d_fs.p;
+            launch_accumulate(A, st, nullptr);
+            CK(cudaGetLastError());
+        }
+        CK(cudaMemcpyAsync(count, d_cnt.p, cells * 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(sum_z100, d_z.p, cells * 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(sum_mfe, d_m.p, cells * 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(sum_ed100, d_e.p, cells * 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(first_seen, d_fs.p, cells * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        return 0;
+    } catch (const CudaError &e) {
+        return fail(SFB_E_CUDA, e.what());
+    }
+}
+
+}  // extern "C"

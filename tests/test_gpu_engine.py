@@ -1,0 +1,307 @@
+"""GPU parity tests: CUDA engine (through the C-ABI) vs the CPU oracle on the same seeded inputs.
+
+Bit-exact for integer work (MFE energies, structures, accumulators); 1e-6 relative for the fp64 partition
+function (north_star tolerance).  The oracle itself is unpinned against ViennaRNA (see oracle/sf_oracle.h).
+"""
+import random
+
+import numpy as np
+import pytest
+
+from util import db_from_pt, rand_seqs
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("W,n_seq", [(5, 20), (12, 50), (40, 200), (120, 300), (200, 24), (300, 4), (600, 2)])
+def test_mfe_energy_and_structure(engine, oracle, W, n_seq):
+    seqs = rand_seqs(1000 + W, n_seq, W, gc_rich=True)
+    e, pt = engine.fold_batch(seqs, structure=True)
+    e2, _ = engine.fold_batch(seqs, structure=False)
+    assert np.array_equal(e, e2)
+    for k, s in enumerate(seqs):
+        eo, so = oracle.mfe(s)
+        assert e[k] == eo, (W, k, s)
+        assert db_from_pt(pt[k]) == so, (W, k, s)
+
+
+def test_mfe_adversarial(engine, oracle):
+    seqs = ["G" * 60 + "C" * 60, "GC" * 60, "A" * 120, "GGGGAAAACCCC" * 10, "AU" * 60, "GU" * 60,
+            "CUUCGG" * 20, "GCAACGC" * 17 + "A"]
+    e, pt = engine.fold_batch(seqs, structure=True)
+    for k, s in enumerate(seqs):
+        eo, so = oracle.mfe(s)
+        assert e[k] == eo and db_from_pt(pt[k]) == so, s
+
+
+def _rand_hc(rng, n, with_brackets):
+    hc = ["."] * n
+    for k in range(n):
+        r = rng.random()
+        if r < 0.08:
+            hc[k] = "x"
+        elif r < 0.11:
+            hc[k] = "<"
+        elif r < 0.14:
+            hc[k] = ">"
+        elif r < 0.16:
+            hc[k] = "|"
+    if with_brackets:
+        for _ in range(3):
+            i = rng.randrange(0, n - 10)
+            j = rng.randrange(i + 5, n)
+            inside = hc[i:j + 1]
+            if "(" in inside or ")" in inside:
+                continue
+            # keep brackets nested: only place if no bracket lies between
+            hc[i], hc[j] = "(", ")"
+    return "".join(hc)
+
+
+@pytest.mark.parametrize("brackets", [False, True])
+def test_mfe_hard_constraints(engine, oracle, brackets):
+    rng = random.Random(7 + brackets)
+    W = 80
+    seqs = rand_seqs(77, 60, W)
+    hcs = [_rand_hc(rng, W, brackets) for _ in seqs]
+    if brackets:
+        hcs[0] = "((((" + "." * (W - 8) + "))))"
+        hcs[1] = ")" + "." * (W - 2) + "("      # unbalanced: ignored
+        hcs[2] = "((" + "." * (W - 3) + ")"     # one unmatched '('
+    e, pt = engine.fold_batch(seqs, hc=hcs, structure=True)
+    for k, s in enumerate(seqs):
+        eo, so = oracle.mfe(s, hc=hcs[k])
+        assert e[k] == eo, (k, s, hcs[k])
+        assert db_from_pt(pt[k]) == so, (k, s, hcs[k])
+
+
+def test_mfe_soft_constraints_and_span(engine, oracle):
+    rng = np.random.default_rng(5)
+    W = 100
+    seqs = rand_seqs(55, 40, W)
+    sc = rng.integers(-150, 150, size=(len(seqs), W + 1)).astype(np.int32)
+    sc[:, 0] = 0
+    e, pt = engine.fold_batch(seqs, sc=sc, structure=True)
+    for k, s in enumerate(seqs):
+        eo, so = oracle.mfe(s, sc_stack=sc[k])
+        assert e[k] == eo and db_from_pt(pt[k]) == so, (k, s)
+    e, pt = engine.fold_batch(seqs, structure=True, max_span=30)
+    for k, s in enumerate(seqs):
+        eo, so = oracle.mfe(s, max_span=30)
+        assert e[k] == eo and db_from_pt(pt[k]) == so, (k, s)
+
+
+def test_deigan_conversion(engine, oracle):
+    rng = np.random.default_rng(9)
+    r = np.concatenate([[-999.0], rng.exponential(0.4, size=300)])
+    r[rng.random(301) < 0.05] = -999.0
+    assert np.array_equal(engine.deigan(r, 0.8, -0.2), oracle.deigan(r, 0.8, -0.2))
+
+
+@pytest.mark.parametrize("W,n_seq", [(30, 20), (120, 24), (200, 4)])
+def test_partition_function(engine, oracle, W, n_seq):
+    seqs = rand_seqs(2000 + W, n_seq, W, gc_rich=True)
+    res = engine.pf_batch(seqs, want_bpp=True)
+    for k, s in enumerate(seqs):
+        o = oracle.pf(s, want_bpp=True)
+        assert abs(res["dG"][k] - o["dG"]) <= 1e-6 * max(1.0, abs(o["dG"])), (k, s)
+        assert abs(res["ed"][k] - o["ed"]) <= 1e-6 * max(1.0, abs(o["ed"])), (k, s)
+        assert np.abs(res["bpp"][k] - o["bpp"]).max() < 1e-9
+        assert db_from_pt(res["centroid"][k]) == o["centroid"]
+
+
+def test_partition_function_constraints(engine, oracle):
+    rng = random.Random(3)
+    W = 90
+    seqs = rand_seqs(31, 12, W)
+    hcs = [_rand_hc(rng, W, k % 2 == 0) for k in range(len(seqs))]
+    sc = np.random.default_rng(1).integers(-100, 100, size=(len(seqs), W + 1)).astype(np.int32)
+    res = engine.pf_batch(seqs, hc=hcs, sc=sc, max_span=50)
+    for k, s in enumerate(seqs):
+        o = oracle.pf(s, hc=hcs[k], sc_stack=sc[k], max_span=50)
+        assert abs(res["dG"][k] - o["dG"]) <= 1e-6 * max(1.0, abs(o["dG"]))
+        assert abs(res["ed"][k] - o["ed"]) <= 1e-6 * max(1.0, abs(o["ed"]))
+        assert db_from_pt(res["centroid"][k]) == o["centroid"]
+
+
+def test_random_parameter_file(engine, oracle, tmp_path):
+    """A randomised table set catches any index-order disagreement between the two table loaders / kernels."""
+    import os
+    from scanfold_b200 import engine as E
+    src = open(os.path.join(os.path.dirname(E.LIB_PATH), "params", "rna_turner2004_besteffort.par")).read().split("\n")
+    rng = random.Random(11)
+    out, in_block, name = [], False, ""
+    for line in src:
+        if line.startswith("# "):
+            name = line[2:].strip()
+            out.append(line)
+            continue
+        toks = line.split()
+        numeric = toks and all(t.lstrip("-").isdigit() or t == "INF" for t in toks)
+        if numeric and name not in ("hairpin", "bulge", "interior", "ML_params", "NINIO", "Misc") and not name.endswith("_enthalpies"):
+            out.append(" ".join(str(rng.randrange(-300, 300)) for _ in toks))
+        else:
+            out.append(line)
+    par = tmp_path / "random.par"
+    par.write_text("\n".join(out))
+    try:
+        E.init(0, str(par))
+        oracle.load_params(str(par))
+        seqs = rand_seqs(99, 80, 70)
+        e, pt = E.fold_batch(seqs, structure=True)
+        for k, s in enumerate(seqs):
+            eo, so = oracle.mfe(s)
+            assert e[k] == eo and db_from_pt(pt[k]) == so, (k, s)
+        res = E.pf_batch(seqs[:10])
+        for k in range(10):
+            o = oracle.pf(seqs[k])
+            assert abs(res["ed"][k] - o["ed"]) <= 1e-6 * max(1.0, abs(o["ed"]))
+    finally:
+        E.init(0, None)
+        oracle.load_params(oracle.DEFAULT_PAR)
+
+
+def _dinuc_counts(s):
+    c = {}
+    for a, b in zip(s[:-1], s[1:]):
+        c[a + b] = c.get(a + b, 0) + 1
+    return c
+
+
+@pytest.mark.parametrize("stype", ["mono", "di"])
+def test_device_shuffles_invariants(engine, stype):
+    seq = rand_seqs(4242, 1, 400)[0]
+    W, r = 60, 25
+    plan = engine.ScanPlan(seq, W, 7, r, shuffle_type=stype, seed=123, want_pf=False, keep_shuffles=True)
+    res = plan.run().fetch()
+    plan.close()
+    n_reg = res.n - 1
+    distinct = set()
+    for w in range(res.n):
+        start = w * 7 if w < n_reg else len(seq) - W
+        frag = seq[start:start + W]
+        for k in range(r):
+            sh = bytes(res.shuffles[w, k]).decode()
+            distinct.add(sh)
+            assert sorted(sh) == sorted(frag)
+            if stype == "di":
+                assert sh[0] == frag[0] and sh[-1] == frag[-1]
+                assert _dinuc_counts(sh) == _dinuc_counts(frag)
+    assert len(distinct) > 0.95 * res.n * r
+    # same seed -> same shuffles regardless of sharding (Philox counter = absolute window index)
+    plan2 = engine.ScanPlan(seq, W, 7, r, shuffle_type=stype, seed=123, want_pf=False, keep_shuffles=True,
+                            first_window=10, n_windows=5, final_window=False)
+    res2 = plan2.run().fetch()
+    plan2.close()
+    assert np.array_equal(res2.shuffles, res.shuffles[10:15])
+    assert np.array_equal(res2.shuffle_dcal, res.shuffle_dcal[10:15])
+
+
+def test_mono_shuffle_uniformity(engine):
+    """position of the first nucleotide after shuffling is uniform (chi-square, generous bound)"""
+    W, r = 24, 100
+    seq = "A" + "C" * (W - 1)
+    counts = np.zeros(W)
+    for seed in range(40):
+        p = engine.ScanPlan(seq[:W], W, 1, r, seed=seed, want_pf=False, keep_shuffles=True, final_window=False)
+        sh = p.run().fetch().shuffles[0]
+        p.close()
+        for k in range(r):
+            counts[bytes(sh[k]).index(b"A")] += 1
+    exp = counts.sum() / W
+    chi2 = ((counts - exp) ** 2 / exp).sum()
+    assert chi2 < 60, chi2   # 23 dof: P(chi2 > 60) ~ 3e-5
+
+
+def test_scan_parity_mode(engine, oracle):
+    """sfb_scan with host-provided shuffles vs the oracle, all outputs (the scan loop ScanFold.py:429-757)."""
+    rng = random.Random(17)
+    seq = rand_seqs(808, 1, 230)[0]
+    W, step, r = 50, 3, 12
+    nwin = (len(seq) - W) // step + 1
+    shuf = np.zeros((nwin + 1, r, W), dtype=np.uint8)
+    for w in range(nwin + 1):
+        start = w * step if w < nwin else len(seq) - W
+        frag = seq[start:start + W]
+        for k in range(r):
+            shuf[w, k] = np.frombuffer("".join(rng.sample(frag, W)).encode(), dtype=np.uint8)
+    hc = "".join(rng.choice("....x") for _ in seq)
+    res = engine.scan(seq, W, step, r, parity_shuffles=shuf, hc=hc)
+    assert res.n == nwin + 1
+    for w in range(nwin + 1):
+        start = w * step if w < nwin else len(seq) - W
+        frag = seq[start:start + W]
+        src = min(w, nwin - 1)          # final slot: stale fold compound of the last regular window (Q5)
+        sfrag = seq[src * step:src * step + W]
+        shc = hc[src * step:src * step + W]
+        eo, so = oracle.mfe(sfrag, hc=shc)
+        assert res.mfe_dcal[w] == eo
+        assert db_from_pt(res.pair_tbl[w]) == so
+        assert res.native_unconstrained_dcal[w] == oracle.mfe(frag, structure=False)[0]
+        for k in range(r):
+            assert res.shuffle_dcal[w, k] == oracle.mfe(bytes(shuf[w, k]).decode(), structure=False)[0]
+        o = oracle.pf(sfrag, hc=shc)
+        assert abs(res.ed[w] - o["ed"]) <= 1e-6 * max(1, abs(o["ed"]))
+        assert db_from_pt(res.centroid_tbl[w]) == o["centroid"]
+
+
+def test_scan_shape_mode(engine, oracle):
+    rng = np.random.default_rng(21)
+    seq = rand_seqs(909, 1, 160)[0]
+    L, W, step, r = len(seq), 40, 1, 3
+    react = np.concatenate([[-999.0], np.clip(rng.exponential(0.4, L), 0, 4)])
+    react[rng.random(L + 1) < 0.05] = -999.0
+    res = engine.scan(seq, W, step, r, react=react, shape_m=0.8, shape_b=-0.2)
+    es = oracle.deigan(react, 0.8, -0.2)
+    nwin = L - W + 1
+    for w in range(nwin):
+        frag = seq[w:w + W]
+        scw = np.zeros(W + 1, dtype=np.int32)
+        for p in range(1, W):                       # Q7: +1 shift, position W reads past the slice
+            g = w + 1 + p
+            scw[p] = es[g] if g <= L else 0
+        eo, so = oracle.mfe(frag, sc_stack=scw)
+        assert res.mfe_dcal[w] == eo and db_from_pt(res.pair_tbl[w]) == so
+        o = oracle.pf(frag)                          # Q6: PF before sc is added
+        assert abs(res.ed[w] - o["ed"]) <= 1e-6 * max(1, abs(o["ed"]))
+        if w == nwin - 1:                            # Q5: final slot re-runs pf() on the stale fc WITH sc
+            o2 = oracle.pf(frag, sc_stack=scw)
+            assert abs(res.ed[nwin] - o2["ed"]) <= 1e-6 * max(1, abs(o2["ed"]))
+            assert res.mfe_dcal[nwin] == eo
+
+
+def test_accumulate(engine):
+    rng = np.random.default_rng(2)
+    L, W, step = 300, 40, 3
+    nwin = (L - W) // step + 1
+    pt = np.zeros((nwin, W), dtype=np.int16)
+    for w in range(nwin):
+        for _ in range(6):
+            i = int(rng.integers(0, W - 5))
+            j = int(rng.integers(i + 4, W))
+            if pt[w, i] == 0 and pt[w, j] == 0:
+                pt[w, i], pt[w, j] = j + 1, i + 1
+    z = rng.integers(-400, 300, nwin).astype(np.int32)
+    m = rng.integers(-3000, 0, nwin).astype(np.int32)
+    e = rng.integers(0, 4000, nwin).astype(np.int32)
+    out = engine.accumulate(L, W, step, 0, pt, z, m, e)
+    cnt = np.zeros((L, 2 * W - 1), dtype=np.int64)
+    sz = np.zeros_like(cnt)
+    fs = np.full((L, 2 * W - 1), 0x7F7F7F7F, dtype=np.int64)
+    for w in range(nwin):
+        for p in range(W):
+            k = w * step + p
+            off = (w * step + pt[w, p] - 1 - k) if pt[w, p] else 0
+            cnt[k, off + W - 1] += 1
+            sz[k, off + W - 1] += z[w]
+            fs[k, off + W - 1] = min(fs[k, off + W - 1], w)
+    assert np.array_equal(out["count"], cnt)
+    assert np.array_equal(out["sum_z100"], sz)
+    assert np.array_equal(out["first_seen"].astype(np.int64), fs)
+    # two shards add up to the whole (multi-GPU reduce property)
+    h = nwin // 2
+    a = engine.accumulate(L, W, step, 0, pt[:h], z[:h], m[:h], e[:h])
+    b = engine.accumulate(L, W, step, h, pt[h:], z[h:], m[h:], e[h:])
+    for key in ("count", "sum_z100", "sum_mfe", "sum_ed100"):
+        assert np.array_equal(a[key] + b[key], out[key])
+    assert np.array_equal(np.minimum(a["first_seen"], b["first_seen"]), out["first_seen"])
