@@ -19,7 +19,7 @@ namespace {
 
 constexpr int NT = 256;        // threads per CTA
 constexpr int NCAND = 496;     // (u1,u2), u1+u2 <= 30
-constexpr int ROLL = 32;       // rolling diagonals (MAXLOOP + 2)
+constexpr int ROLL = 33;       // rolling diagonals: reads reach back to d - 32 while diagonal d is written
 
 enum { CLS_GENERIC = 0, CLS_1N = 1, CLS_BULGE = 2, CLS_TABLE = 3 };
 
@@ -392,7 +392,7 @@ __global__ void __launch_bounds__(NT) mfe_fold_kernel(MfeLaunch L, const MfeTabl
         for (int d = TURN + 1; d < W; d++) {
             const int ncells = W - d;
             const int tri_d = tri_off(d, W);
-            const int rrow = (d & (ROLL - 1)) * W;
+            const int rrow = (d % ROLL) * W;
             if (tid == 0) misc[0] = 0;
             __syncthreads();
             // phase 1a: pair permission per cell, compact the pairable ones
@@ -438,7 +438,7 @@ __global__ void __launch_bounds__(NT) mfe_fold_kernel(MfeLaunch L, const MfeTabl
                             int v;
                             if (cls != CLS_TABLE) {
                                 const int outer = cls == CLS_GENERIC ? outer0 : (cls == CLS_1N ? outer1 : outer2);
-                                v = roll[cls * ROLL * W + (dd & (ROLL - 1)) * W + p] + (cd >> 16) + outer;
+                                v = roll[cls * ROLL * W + (dd % ROLL) * W + p] + (cd >> 16) + outer;
                             } else {
                                 const int q = j - 1 - u2;
                                 const int cpq = Cm[tri_off(dd, W) + p];
