@@ -1,0 +1,325 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the ScanFold scanning hot path on B200 (contract: see DESIGN.md "Measurement").
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload C2]
+
+One "step" = one pass of the hot path over one record shard: for every window the native MFE fold
+(+ structure), the partition function / ensemble diversity / centroid, r shuffles generated on the
+device and their MFE folds, the z-score / p-value, and the ScanFold-Fold per-base-pair accumulation.
+The workload is BASELINE.json configs[1] (C2): 29,903-nt synthetic SARS-CoV-2-like genome, 120-nt
+window, step 1, 100 mono-nucleotide shuffles.  With N GPUs every rank scans its own contiguous range
+of ~29.8 k windows of an N x 29,903-nt record (weak scaling).
+
+`value`   windows/s with the record resident in HBM (sfb_scan_plan_run; CUDA events on the launch stream)
+`e2e`     windows/s through the public host-buffer API scanfold_b200.scan.scan_record + fold accumulate
+          (H2D of the record, D2H of every per-window result, host z/p, accumulate H2D/D2H) -- the headline
+`--impl reference`  the reference's CPU path.  ViennaRNA is not installable here (no network, not in the
+          image), so this arm times oracle/ (the CPU restatement of the same algorithms) on all host
+          cores over a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (L, W, step, r, shuffle, composition ACGU, seed)   -- SURVEY.md 8d
+    "C1": (1000, 120, 1, 100, "mono", (0.25, 0.25, 0.25, 0.25), 1001),
+    "C2": (29903, 120, 1, 100, "mono", (0.299, 0.184, 0.196, 0.321), 1002),
+}
+
+
+def synth_record(name, copies=1):
+    L, W, step, r, stype, comp, seed = WORKLOADS[name]
+    rng = np.random.Generator(np.random.PCG64(seed))
+    idx = rng.choice(4, size=L * copies, p=np.array(comp) / sum(comp))
+    return "".join("ACGU"[k] for k in idx), W, step, r, stype
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)"""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, power, reasons = [], [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+                power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def cpu_sample(seq, W, step, r, n_windows, rng_seed=7):
+    """one bounded sample of the workload for the CPU arm: the first n_windows windows"""
+    import random
+    rnd = random.Random(rng_seed)
+    natives = [seq[w * step:w * step + W] for w in range(n_windows)]
+    folds = []
+    for frag in natives:
+        folds.append(frag)
+        folds.extend("".join(rnd.sample(frag, W)) for _ in range(r))
+    a = np.frombuffer("".join(folds).encode(), dtype=np.uint8).reshape(len(folds), W)
+    n = np.frombuffer("".join(natives).encode(), dtype=np.uint8).reshape(len(natives), W)
+    return a, n
+
+
+def cpu_step(O, folds, natives, threads):
+    """what the reference does per window on the CPU: r+1 MFE folds (ScanFoldFunctions.py:805-814), the
+    native MFE with structure and one partition function with bpp / centroid / ED (ScanFold.py:494-504)"""
+    O.fold_batch(folds, n_threads=threads)
+    O.fold_batch(natives, n_threads=threads)
+    O.pf_batch(natives, n_threads=threads)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as O
+    O.lib()
+    seq, W, step, r, stype = synth_record(args.workload)
+    threads = host_threads()
+    nwin = args.cpu_windows
+    folds, natives = cpu_sample(seq, W, step, r, nwin)
+    for _ in range(max(args.warmup, 0) and 1):
+        cpu_step(O, folds[:threads * (r + 1)], natives[:threads], threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_step(O, folds, natives, threads)
+    dt = time.perf_counter() - t0
+    wps = nwin * args.steps / dt
+    sample = "first %d windows of %s per step (%d MFE folds + %d native folds + %d partition functions)" % (
+        nwin, args.workload, len(folds), nwin, nwin)
+    line = {"impl": "reference", "metric": "windows/sec (MFE+%d shuffles+ED)" % r, "value": wps, "unit": "windows/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+            "config": workload_config(args.workload, 1),
+            "cpu_baseline": {"value": wps, "unit": "windows/s", "cores": threads, "kind": "port", "sample": sample,
+                             "note": "ViennaRNA (the reference's fold engine) is not installable offline; "
+                                     "oracle/ is the CPU restatement of the same algorithms"},
+            "e2e": {"value": wps, "unit": "windows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def workload_config(name, n_gpus):
+    L, W, step, r, stype, comp, seed = WORKLOADS[name]
+    return {"workload": "%s: %d-nt synthetic record per GPU, window %d, step %d, %d %s shuffles, PF/ED on, "
+                        "ScanFold-Fold accumulation" % (name, L, W, step, r, stype),
+            "record_nt": L * n_gpus, "window": W, "step": step, "shuffles": r, "shuffle_type": stype,
+            "seed": seed, "l2": "flushed between steps (256 MiB write)", "parallelism": "windows sharded by range"}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from scanfold_b200 import engine, scan, stats, workcount
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    engine.init(local)
+    stream = torch.cuda.current_stream()
+    engine.set_stream(stream.cuda_stream)
+
+    seq, W, step, r, stype = synth_record(args.workload, copies=world)
+    L = len(seq)
+    total = scan.n_windows_of(L, W, step)
+    if args.windows:
+        total = min(total, args.windows * world)
+    w0 = total * rank // world
+    w1 = total * (rank + 1) // world
+    nwin = w1 - w0
+    final = (w1 == scan.n_windows_of(L, W, step))
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident arm: `value`
+    plan = engine.ScanPlan(seq, W, step, r, shuffle_type=stype, seed=42, first_window=w0, n_windows=nwin,
+                           final_window=final, want_pf=True)
+    for _ in range(args.warmup):
+        plan.run()
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ms_mfe = 0.0
+    launches = 0
+    ev0.record(stream)
+    for _ in range(args.steps):
+        flush.zero_()
+        plan.run()
+        ms_mfe += plan.ms_mfe
+        launches += plan.n_launches
+    ev1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    ms_dev = ev0.elapsed_time(ev1)
+    res = plan.fetch()
+    plan.close()
+
+    # ---------------- end-to-end arm through the public API with host buffers: `e2e`
+    def e2e_step():
+        t = scan.scan_record(seq, W, step, r, shuffle_type=stype, seed=42, first_window=w0, n_windows=nwin,
+                             final_window=final)
+        z100 = np.rint(t.z * 100).astype(np.int32)
+        ed100 = np.rint(t.ed * 100).astype(np.int32)
+        acc = engine.accumulate(L, W, step, w0, t.pair_tbl, z100, t.mfe_dcal, ed100)
+        return t, acc
+
+    e2e_steps = args.e2e_steps if args.e2e_steps else args.steps
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        flush.zero_()
+        t, acc = e2e_step()
+    barrier()
+    ms_e2e = (time.perf_counter() - t0) * 1e3
+    n_slots = nwin + (1 if final else 0)
+    h2d = L + nwin * W * 2 + nwin * 12
+    d2h = n_slots * (4 + 4 + 4 * r + 2 * W + 2 * W + 8 + 8) + L * (2 * W - 1) * 36
+
+    # ---------------- max over ranks
+    tt = torch.tensor([ms_dev, ms_e2e, ms_mfe], dtype=torch.float64, device="cuda")
+    cnt = torch.tensor([float(nwin), float(launches)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    ms_dev, ms_e2e, ms_mfe_max = tt.tolist()
+    total_windows, total_launches = cnt.tolist()
+
+    if rank == 0:
+        folds_per_window = r + 1
+        n_folds = (nwin + (1 if final else 0)) * folds_per_window
+        cells = workcount.cells(W)
+        dense = workcount.dense_relaxations(W)
+        rs = np.random.default_rng(5)
+        sample_w = rs.integers(0, L - W, size=24)
+        useful = float(np.mean([workcount.useful_relaxations(seq[s:s + W]) for s in sample_w[:12]] +
+                               [workcount.useful_relaxations("".join(rs.permutation(list(seq[s:s + W]))))
+                                for s in sample_w[12:]]))
+        peak_addmin = engine.microbench(0)
+        peak_lds = engine.microbench(1)
+        mfe_s = ms_mfe / args.steps * 1e-3          # MFE kernels of one step on this rank (library CUDA events)
+        achieved = useful * n_folds / mfe_s
+        value = total_windows * args.steps / (ms_dev * 1e-3)
+        e2e = total_windows * e2e_steps / (ms_e2e * 1e-3)
+        line = {
+            "metric": "windows/sec (MFE+%d shuffles+ED)" % r, "value": value, "unit": "windows/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+            "config": workload_config(args.workload, world),
+            "folds_per_s": value * folds_per_window, "dp_cells_per_s": value * folds_per_window * cells,
+            "e2e": {"value": e2e, "unit": "windows/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps},
+            "gpu_launches": int(total_launches),
+            "roofline": {"bound": "int_alu", "kernel": "mfe_fold_kernel", "achieved": achieved / 1e9,
+                         "peak": peak_addmin / 1e9, "unit": "G add-min/s", "frac": achieved / peak_addmin,
+                         "peak_source": "sfb_microbench VIADDMNMX rate measured in this run (MEASURED_PEAKS.json "
+                                        "has no integer peak; HBM is not the bound)",
+                         "algorithmic_ops_per_fold": useful, "dense_ops_per_fold": dense,
+                         "achieved_dense": dense * n_folds / mfe_s / 1e9,
+                         "smem_ld32_peak_per_s": peak_lds, "kernel_ms_per_step": mfe_s * 1e3,
+                         "kernel_share_of_step": ms_mfe / ms_dev if world == 1 else None,
+                         "hbm_algorithmic_bytes_per_fold": W + 4, "traffic": None},
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            from oracle import oracle as O
+            O.lib()
+            threads = host_threads()
+            cw = args.cpu_windows
+            folds, natives = cpu_sample(seq, W, step, r, cw)
+            t0 = time.perf_counter()
+            cpu_step(O, folds, natives, threads)
+            dt = time.perf_counter() - t0
+            line["cpu_baseline"] = {"value": cw / dt, "unit": "windows/s", "cores": threads, "kind": "port",
+                                    "sample": "first %d windows of %s, once (%d MFE folds + %d partition functions)"
+                                              % (cw, args.workload, len(folds) + cw, cw)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
+    ap.add_argument("--windows", type=int, default=0, help="debug: cap the windows per GPU")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="end-to-end steps (default: --steps)")
+    ap.add_argument("--cpu-windows", type=int, default=96, help="windows per CPU sample step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -44,6 +44,9 @@ int sfb_version(void);
 int sfb_init(int device_ordinal, const char *par_file_or_null);
 void sfb_shutdown(void);
 const char *sfb_last_error(void);
+/* Launch everything on the caller's CUDA stream (a cudaStream_t, e.g. torch.cuda.current_stream().cuda_stream)
+ * so that the caller's events bracket the library's work; NULL = back to the library's own stream. */
+int sfb_set_stream(void *cuda_stream_or_null);
 /* 1 if the loaded table is the built-in best-effort stand-in (parity with ViennaRNA unpinned) */
 int sfb_params_besteffort(void);
 
@@ -125,6 +128,13 @@ typedef struct sfb_accum_args {
 } sfb_accum_args;
 int sfb_accumulate(const sfb_accum_args *args, int64_t *count, int64_t *sum_z100, int64_t *sum_mfe,
                    int64_t *sum_ed100, int32_t *first_seen);
+
+/* Roofline denominators measured on the current device (bench.py): SFB_MICROBENCH_ADDMIN = int32
+ * add-min (VIADDMNMX) operations per second over all SMs; SFB_MICROBENCH_SMEM_LD32 = conflict-free
+ * 32-bit shared-memory loads per second (x4 = bytes/s).  No reference counterpart. */
+#define SFB_MICROBENCH_ADDMIN 0
+#define SFB_MICROBENCH_SMEM_LD32 1
+int sfb_microbench(int which, double *ops_per_s);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

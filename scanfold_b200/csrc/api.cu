@@ -25,7 +25,8 @@ struct Context {
     double pf_temperature = -1e9;
     MfeTables *d_mfe = nullptr;
     PfTables *d_pf = nullptr;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;      // stream every launch / copy goes to (own_stream unless sfb_set_stream)
+    cudaStream_t own_stream = nullptr;
 };
 
 Context g_ctx;
@@ -176,7 +177,8 @@ int sfb_init(int device_ordinal, const char *par_file_or_null) {
         CK(cudaGetDeviceProperties(&prop, device_ordinal));
         g_ctx.device = device_ordinal;
         g_ctx.n_sm = prop.multiProcessorCount;
-        if (!g_ctx.stream) CK(cudaStreamCreateWithFlags(&g_ctx.stream, cudaStreamNonBlocking));
+        if (!g_ctx.own_stream) CK(cudaStreamCreateWithFlags(&g_ctx.own_stream, cudaStreamNonBlocking));
+        if (!g_ctx.stream) g_ctx.stream = g_ctx.own_stream;
         if (!g_ctx.d_mfe) CK(cudaMalloc(&g_ctx.d_mfe, sizeof(MfeTables)));
         CK(cudaMemcpy(g_ctx.d_mfe, &g_ctx.hp.mfe, sizeof(MfeTables), cudaMemcpyHostToDevice));
         g_ctx.pf_temperature = -1e9;
@@ -192,8 +194,15 @@ void sfb_shutdown(void) {
     std::lock_guard<std::mutex> lk(g_mu);
     if (g_ctx.d_mfe) cudaFree(g_ctx.d_mfe);
     if (g_ctx.d_pf) cudaFree(g_ctx.d_pf);
-    if (g_ctx.stream) cudaStreamDestroy(g_ctx.stream);
+    if (g_ctx.own_stream) cudaStreamDestroy(g_ctx.own_stream);
     g_ctx = Context();
+}
+
+int sfb_set_stream(void *cuda_stream_or_null) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!g_ctx.ready) return fail(SFB_E_STATE, "sfb_init has not been called");
+    g_ctx.stream = cuda_stream_or_null ? (cudaStream_t)cuda_stream_or_null : g_ctx.own_stream;
+    return 0;
 }
 
 int sfb_deigan(const double *react1, int n, double m, double b, int32_t *es1) {

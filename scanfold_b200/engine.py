@@ -20,7 +20,7 @@ SHUFFLE_MONO, SHUFFLE_DI = 0, 1
 
 EXPORTS = ["sfb_version", "sfb_init", "sfb_shutdown", "sfb_last_error", "sfb_params_besteffort", "sfb_fold_batch",
            "sfb_pf_batch", "sfb_deigan", "sfb_scan", "sfb_scan_plan_create", "sfb_scan_plan_keep_shuffles",
-           "sfb_scan_plan_run", "sfb_scan_plan_fetch", "sfb_scan_plan_destroy", "sfb_accumulate"]
+           "sfb_scan_plan_run", "sfb_scan_plan_fetch", "sfb_scan_plan_destroy", "sfb_accumulate", "sfb_microbench", "sfb_set_stream"]
 
 
 class EngineError(RuntimeError):
@@ -82,6 +82,8 @@ def load_library():
         L.sfb_scan_plan_destroy.restype = None
         L.sfb_accumulate.argtypes = [C.POINTER(AccumArgs), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.sfb_shutdown.restype = None
+        L.sfb_set_stream.argtypes = [C.c_void_p]
+        L.sfb_microbench.argtypes = [C.c_int, C.POINTER(C.c_double)]
         _lib = L
     return _lib
 
@@ -312,3 +314,17 @@ def accumulate(L, W, step, first_window, pair_tbl, z100, mfe_dcal, ed100):
                                          out["sum_mfe"].ctypes.data, out["sum_ed100"].ctypes.data,
                                          out["first_seen"].ctypes.data))
     return out
+
+
+def microbench(which):
+    """Measured device peak: which=0 int32 add-min ops/s, which=1 32-bit shared-memory loads/s."""
+    ensure_init()
+    v = C.c_double()
+    _check(load_library().sfb_microbench(int(which), C.byref(v)))
+    return v.value
+
+
+def set_stream(cuda_stream):
+    """Route every launch and copy of the library to `cuda_stream` (int handle, e.g. torch's current stream)."""
+    ensure_init()
+    _check(load_library().sfb_set_stream(C.c_void_p(int(cuda_stream)) if cuda_stream else None))
