@@ -1,0 +1,160 @@
+#!/usr/bin/env python
+"""Generates tests/golden/<case>/ by running the UNMODIFIED reference /root/reference/ScanFold.py.
+
+The reference's fold engine (ViennaRNA) is absent, so `import RNA` resolves to tests/golden/stubs/RNA.py,
+i.e. the Level-1 shim backed by the CPU oracle; Biopython is replaced by a 40-line FASTA reader and the
+per-window process pools by an in-process map with a seeded `random` (stubs/sitecustomize.py).  Everything
+else -- shuffling, z/p, pair records, aggregation, competition, every writer -- is the reference's own code.
+
+Each case directory holds:
+  case.json      command line, window geometry
+  input.fa       (+ constraints.dbn / react.shape)
+  trace.npz      per-window engine inputs/outputs recovered from the fold trace: the shuffled sequences the
+                 reference drew (parity shuffles), energies, structures, ED, centroids
+  expected/      every output file the reference wrote (motif .ps placeholders dropped)
+
+Run here (needs /root/reference):  python tests/golden/make_golden.py
+The fixtures are oracle-derived, NOT ViennaRNA-derived (parity unpinned, see oracle/sf_oracle.h).
+"""
+import json
+import os
+import random
+import shutil
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = "/root/reference"
+
+
+def rand_seq(rng, n, alpha="ACGU"):
+    return "".join(rng.choice(alpha) for _ in range(n))
+
+
+def pt_from_db(s):
+    pt = np.zeros(len(s), dtype=np.int16)
+    stk = []
+    for k, ch in enumerate(s):
+        if ch == "(":
+            stk.append(k)
+        elif ch == ")":
+            a = stk.pop()
+            pt[a], pt[k] = k + 1, a + 1
+    return pt
+
+
+CASES = {
+    # name: (L, seq seed, args, extras)
+    "mono_w40": dict(L=150, seed=11, args=["-w", "40", "-r", "10"]),
+    "mono_w60_gc": dict(L=260, seed=12, alpha="GGCCAU", args=["-w", "60", "-r", "12"]),
+    "di_w40": dict(L=140, seed=13, args=["-w", "40", "-r", "10", "--type", "di"]),
+    "step7_w40": dict(L=150, seed=14, args=["-w", "40", "-r", "10", "-s", "7"]),
+    "hc_w40": dict(L=150, seed=15, args=["-w", "40", "-r", "10"], hc=True),
+    "shape_w40": dict(L=150, seed=16, args=["-w", "40", "-r", "10", "--shapeD"], react=True),
+    "dna_name_w30": dict(L=100, seed=17, alpha="ACGT", args=["-w", "30", "-r", "8", "--name", "chrTest"],
+                         header="rec17|extra|fields"),
+}
+
+
+def make_case(name, spec):
+    rng = random.Random(spec["seed"])
+    seq = rand_seq(rng, spec["L"], spec.get("alpha", "ACGU"))
+    header = spec.get("header", name)
+    work = tempfile.mkdtemp(prefix="golden_")
+    fasta = os.path.join(work, "input.fa")
+    with open(fasta, "w") as f:
+        f.write(">%s\n%s\n" % (header, seq))
+    args = list(spec["args"])
+    aux = {}
+    if spec.get("hc"):
+        hc = "".join(rng.choice("......x") for _ in seq)
+        path = os.path.join(work, "constraints.dbn")
+        with open(path, "w") as f:
+            f.write(">%s\n%s\n%s\n" % (name, seq, hc))
+        args += ["--constraints", path]          # must be absolute (Appendix B Q8)
+        aux["constraints.dbn"] = path
+    if spec.get("react"):
+        nrng = np.random.default_rng(spec["seed"])
+        vals = np.clip(nrng.exponential(0.4, len(seq)), 0, 4)
+        path = os.path.join(work, "react.shape")
+        with open(path, "w") as f:
+            for k, v in enumerate(vals):
+                if k % 23 == 5:
+                    continue                      # gap -> parser fills -999
+                f.write("%d\t%s\t%s\n" % (k + 1, seq[k], "NA" if k % 17 == 3 else "%.4f" % v))
+        args += ["--react", "react.shape"]       # resolved against the original cwd
+        aux["react.shape"] = path
+    env = dict(os.environ)
+    env["PYTHONPATH"] = os.pathsep.join([os.path.join(HERE, "stubs"), REF])
+    env["SCANFOLD_GOLDEN_SEED"] = str(1000 + spec["seed"])
+    trace_path = os.path.join(work, "trace.json")
+    env["SCANFOLD_GOLDEN_TRACE"] = trace_path
+    cmd = [sys.executable, "-W", "ignore", os.path.join(REF, "ScanFold.py"), "input.fa"] + args
+    p = subprocess.run(cmd, cwd=work, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if p.returncode != 0:
+        print(p.stdout[-3000:])
+        raise SystemExit("reference run failed for " + name)
+    rec = header.split("|")[0]
+    outdir = os.path.join(work, rec)
+
+    # ---- rebuild per-window arrays from the fold trace
+    trace = json.load(open(trace_path))
+    W = int(args[args.index("-w") + 1])
+    r = int(args[args.index("-r") + 1])
+    step = int(args[args.index("-s") + 1]) if "-s" in args else 1
+    L = len(seq)
+    nwin = (L - W) // step + 1
+    n = nwin + 1
+    shuf = np.zeros((n, r, W), dtype=np.uint8)
+    mfe = np.zeros(n, dtype=np.int32)
+    nat = np.zeros(n, dtype=np.int32)
+    she = np.zeros((n, r), dtype=np.int32)
+    pair_tbl = np.zeros((n, W), dtype=np.int16)
+    cen_tbl = np.zeros((n, W), dtype=np.int16)
+    ed = np.zeros(n)
+    dG = np.zeros(n)
+    pos = 0
+    for w in range(n):
+        grp = trace[pos:pos + r + 3]
+        pos += r + 3
+        ops = [g["op"] for g in grp]
+        first_mfe = ops.index("mfe")
+        first_pf = ops.index("pf")
+        assert sorted(ops[:2]) == ["mfe", "pf"] and ops[2:] == ["mfe"] * (r + 1), (name, w, ops)
+        m, q = grp[first_mfe], grp[first_pf]
+        mfe[w], pair_tbl[w] = m["e"], pt_from_db(m["s"])
+        ed[w], dG[w], cen_tbl[w] = q["ed"], q["dG"], pt_from_db(q["centroid"])
+        nat[w] = grp[2]["e"]
+        for k in range(r):
+            she[w, k] = grp[3 + k]["e"]
+            shuf[w, k] = np.frombuffer(grp[3 + k]["seq"].encode(), dtype=np.uint8)
+    dst = os.path.join(HERE, name)
+    if os.path.exists(dst):
+        shutil.rmtree(dst)
+    os.makedirs(os.path.join(dst, "expected"))
+    shutil.copy(fasta, os.path.join(dst, "input.fa"))
+    for fn, path in aux.items():
+        shutil.copy(path, os.path.join(dst, fn))
+    np.savez_compressed(os.path.join(dst, "trace.npz"), shuffles=shuf, mfe_dcal=mfe, native_unconstrained_dcal=nat,
+                        shuffle_dcal=she, pair_tbl=pair_tbl, centroid_tbl=cen_tbl, ed=ed, ensemble_dG=dG)
+    kept = []
+    for fn in sorted(os.listdir(outdir)):
+        if fn.endswith(".ps"):
+            continue
+        shutil.copy(os.path.join(outdir, fn), os.path.join(dst, "expected", fn))
+        kept.append(fn)
+    rel_args = [("constraints.dbn" if a == aux.get("constraints.dbn") else a) for a in args]
+    json.dump({"name": name, "args": rel_args, "record": rec, "L": L, "W": W, "step": step, "r": r,
+               "n_windows": nwin, "files": kept, "python": sys.version.split()[0]},
+              open(os.path.join(dst, "case.json"), "w"), indent=1)
+    shutil.rmtree(work)
+    print("%-14s windows=%d files=%d" % (name, nwin, len(kept)))
+
+
+if __name__ == "__main__":
+    sel = sys.argv[1:] or sorted(CASES)
+    for nm in sel:
+        make_case(nm, CASES[nm])
