@@ -114,20 +114,40 @@ int sfb_scan_plan_run(sfb_scan_plan *plan, float *ms_total, float *ms_mfe, int32
 int sfb_scan_plan_fetch(sfb_scan_plan *plan, sfb_scan_out *out);
 void sfb_scan_plan_destroy(sfb_scan_plan *plan);
 
-/* ScanFold-Fold accumulation step (ScanFold.py:1051-1139): per nucleotide k and partner offset, the
- * number of windows, and the sums of z*100, mfe (dcal) and ED*100 as int64 -- order independent, so a
- * multi-GPU ncclReduce(sum) of these is bit exact.  Layout [L][2W-1]: column (j-k)+(W-1); the unpaired
- * record (k,k) sits at offset 0 -> column W-1.  first_seen[L][2W-1] = lowest window index (INT32_MAX if none).
- * Inputs are per-window arrays for windows [first_window, first_window+n_windows). */
+/* ScanFold-Fold accumulation step: the per-window pair records of ScanFold.py:564-677 gathered per nucleotide
+ * and summed per (nucleotide, partner) as ScanFold.py:1051-1139 does with Python lists.  Runs on the device.
+ * A shard of windows [first_window, first_window + n_windows) touches the nucleotides (0-based)
+ * [first_window*step, (first_window+n_windows-1)*step + W): the table has one row per such nucleotide and
+ * 2W-1 partner-offset columns.  Per cell: the number of windows holding the pair, the lowest window index
+ * (first seen: the reference's dict insertion order) and EXACT sums of the window values z, MFE, ED: each
+ * value d = k/100 enters as A = rint(d*2^20), B = (d - A*2^-20)*2^59, so sum(d) == sumA*2^-20 + sumB*2^-59
+ * exactly -- order independent, which makes the multi-GPU halo merge bit exact.
+ * Inputs are host arrays of the shard: pair_tbl [n_windows*W], z100 = round(z*100), mfe_dcal, ed100 = round(ED*100). */
 typedef struct sfb_accum_args {
     int32_t L, W, step, first_window, n_windows;
-    const int16_t *pair_tbl; /* [n_windows*W] */
-    const int32_t *z100;     /* [n_windows] round(z*100) */
-    const int32_t *mfe_dcal; /* [n_windows] */
-    const int32_t *ed100;    /* [n_windows] round(ED*100) */
+    const int16_t *pair_tbl;
+    const int32_t *z100;
+    const int32_t *mfe_dcal;
+    const int32_t *ed100;
 } sfb_accum_args;
-int sfb_accumulate(const sfb_accum_args *args, int64_t *count, int64_t *sum_z100, int64_t *sum_mfe,
-                   int64_t *sum_ed100, int32_t *first_seen);
+typedef struct sfb_partner_table sfb_partner_table; /* device resident */
+int sfb_accumulate_begin(const sfb_accum_args *args, sfb_partner_table **table);
+int sfb_accumulate_geometry(const sfb_partner_table *table, int32_t *nt0, int32_t *n_nt);
+/* Halo exchange between neighbouring shards (multi-GPU): copy rows [row0, row0+n_rows) out to / merge them in
+ * from DEVICE buffers (count [n_rows*(2W-1)] int32, first_seen likewise, sums [6][n_rows*(2W-1)] int64) that the
+ * caller moves with NCCL.  Merge adds counts and sums and takes the minimum of first_seen. */
+int sfb_accumulate_export(sfb_partner_table *table, int row0, int n_rows, int32_t *d_count, int32_t *d_first_seen,
+                          int64_t *d_sums);
+int sfb_accumulate_merge(sfb_partner_table *table, int row0, int n_rows, const int32_t *d_count,
+                         const int32_t *d_first_seen, const int64_t *d_sums);
+/* Compact rows [row0, row0+n_rows) to per-nucleotide partner lists; returns the number of entries. */
+int sfb_accumulate_compact(sfb_partner_table *table, int row0, int n_rows, int64_t *n_entries);
+/* nparts [n_rows] entries per nucleotide (in column order); partner = 1-based partner coordinate (== own: unpaired);
+ * sums [6][n_entries] = zA zB mfeA mfeB edA edB. */
+int sfb_accumulate_fetch(sfb_partner_table *table, int32_t *nparts, int32_t *partner, int32_t *count,
+                         int32_t *first_seen, int64_t *sums);
+int sfb_accumulate_launches(const sfb_partner_table *table);
+void sfb_accumulate_free(sfb_partner_table *table);
 
 /* Roofline denominators measured on the current device (bench.py): SFB_MICROBENCH_ADDMIN = int32
  * add-min (VIADDMNMX) operations per second over all SMs; SFB_MICROBENCH_SMEM_LD32 = conflict-free

@@ -149,6 +149,17 @@ struct sfb_scan_plan {
     bool keep_shuffles = false;
 };
 
+struct sfb_partner_table {
+    AccumDense D{};
+    DevBuf<int32_t> count, first;
+    DevBuf<long long> sums;
+    DevBuf<int32_t> nparts, c_partner, c_count, c_first;
+    DevBuf<long long> offsets, c_sums;
+    int c_row0 = 0, c_rows = 0;
+    long long n_entries = -1;
+    int n_launches = 0;
+};
+
 extern "C" {
 
 int sfb_version(void) { return SFB_VERSION; }
@@ -651,68 +662,175 @@ int sfb_scan(const sfb_scan_args *args, sfb_scan_out *out) {
     return rc;
 }
 
-int sfb_accumulate(const sfb_accum_args *args, int64_t *count, int64_t *sum_z100, int64_t *sum_mfe,
-                   int64_t *sum_ed100, int32_t *first_seen) {
+int sfb_accumulate_begin(const sfb_accum_args *args, sfb_partner_table **out) {
     std::lock_guard<std::mutex> lk(g_mu);
     if (!g_ctx.ready) return fail(SFB_E_STATE, "sfb_init has not been called");
-    if (!args || !count || !sum_z100 || !sum_mfe || !sum_ed100 || !first_seen) return fail(SFB_E_ARG, "null argument");
+    if (!args || !out) return fail(SFB_E_ARG, "null argument");
     const sfb_accum_args &a = *args;
-    if (a.L < 1 || a.W < 1 || a.step < 1 || a.n_windows < 0) return fail(SFB_E_ARG, "bad geometry");
+    if (a.L < 1 || a.W < 1 || a.W > a.L || a.step < 1 || a.n_windows < 1 || a.first_window < 0)
+        return fail(SFB_E_ARG, "sfb_accumulate_begin: bad geometry");
+    if (!a.pair_tbl || !a.z100 || !a.mfe_dcal || !a.ed100) return fail(SFB_E_ARG, "sfb_accumulate_begin: null input");
+    if ((long long)(a.first_window + a.n_windows - 1) * a.step + a.W > a.L)
+        return fail(SFB_E_ARG, "window range exceeds the record");
     try {
         CK(cudaSetDevice(g_ctx.device));
         cudaStream_t st = g_ctx.stream;
-        const size_t cells = (size_t)a.L * (2 * a.W - 1);
-        DevBuf<long long> d_cnt, d_z, d_m, d_e;
-        DevBuf<int32_t> d_fs, d_z100, d_mfe, d_ed100;
+        auto *T = new sfb_partner_table();
+        std::unique_ptr<sfb_partner_table> guard(T);
+        T->D.W = a.W;
+        T->D.nt0 = a.first_window * a.step;
+        T->D.n_nt = (a.n_windows - 1) * a.step + a.W;
+        const size_t cells = (size_t)T->D.n_nt * (2 * a.W - 1);
+        T->count.alloc(cells);
+        T->first.alloc(cells);
+        T->sums.alloc(6 * cells);
+        T->D.count = T->count.p;
+        T->D.first_seen = T->first.p;
+        T->D.sums = T->sums.p;
+        CK(cudaMemsetAsync(T->count.p, 0, cells * 4, st));
+        CK(cudaMemsetAsync(T->first.p, 0x7F, cells * 4, st));
+        CK(cudaMemsetAsync(T->sums.p, 0, 6 * cells * 8, st));
         DevBuf<int16_t> d_pt;
-        d_cnt.alloc(cells);
-        d_z.alloc(cells);
-        d_m.alloc(cells);
-        d_e.alloc(cells);
-        d_fs.alloc(cells);
-        CK(cudaMemsetAsync(d_cnt.p, 0, cells * 8, st));
-        CK(cudaMemsetAsync(d_z.p, 0, cells * 8, st));
-        CK(cudaMemsetAsync(d_m.p, 0, cells * 8, st));
-        CK(cudaMemsetAsync(d_e.p, 0, cells * 8, st));
-        CK(cudaMemsetAsync(d_fs.p, 0x7F, cells * 4, st));
-        const size_t nw = std::max(a.n_windows, 1);
+        DevBuf<int32_t> d_z100, d_mfe, d_ed100;
+        const size_t nw = a.n_windows;
         d_pt.alloc(nw * a.W);
         d_z100.alloc(nw);
         d_mfe.alloc(nw);
         d_ed100.alloc(nw);
-        if (a.n_windows) {
-            CK(cudaMemcpyAsync(d_pt.p, a.pair_tbl, sizeof(int16_t) * (size_t)a.n_windows * a.W, cudaMemcpyHostToDevice, st));
-            CK(cudaMemcpyAsync(d_z100.p, a.z100, sizeof(int32_t) * a.n_windows, cudaMemcpyHostToDevice, st));
-            CK(cudaMemcpyAsync(d_mfe.p, a.mfe_dcal, sizeof(int32_t) * a.n_windows, cudaMemcpyHostToDevice, st));
-            CK(cudaMemcpyAsync(d_ed100.p, a.ed100, sizeof(int32_t) * a.n_windows, cudaMemcpyHostToDevice, st));
-            AccumLaunch A{};
-            A.L = a.L;
-            A.W = a.W;
-            A.step = a.step;
-            A.first_window = a.first_window;
-            A.n_windows = a.n_windows;
-            A.pair_tbl = d_pt.p;
-            A.z100 = d_z100.p;
-            A.mfe = d_mfe.p;
-            A.ed100 = d_ed100.p;
-            A.count = d_cnt.p;
-            A.sum_z = d_z.p;
-            A.sum_mfe = d_m.p;
-            A.sum_ed = d_e.p;
-            A.first_seen = d_fs.p;
-            launch_accumulate(A, st, nullptr);
-            CK(cudaGetLastError());
-        }
-        CK(cudaMemcpyAsync(count, d_cnt.p, cells * 8, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(sum_z100, d_z.p, cells * 8, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(sum_mfe, d_m.p, cells * 8, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(sum_ed100, d_e.p, cells * 8, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(first_seen, d_fs.p, cells * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(d_pt.p, a.pair_tbl, sizeof(int16_t) * nw * a.W, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(d_z100.p, a.z100, sizeof(int32_t) * nw, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(d_mfe.p, a.mfe_dcal, sizeof(int32_t) * nw, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(d_ed100.p, a.ed100, sizeof(int32_t) * nw, cudaMemcpyHostToDevice, st));
+        AccumLaunch A{};
+        A.step = a.step;
+        A.first_window = a.first_window;
+        A.n_windows = a.n_windows;
+        A.pair_tbl = d_pt.p;
+        A.z100 = d_z100.p;
+        A.mfe = d_mfe.p;
+        A.ed100 = d_ed100.p;
+        A.D = T->D;
+        launch_accumulate(A, st, &T->n_launches);
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(st));  // the staging buffers above die with this scope
+        *out = guard.release();
+        return 0;
+    } catch (const CudaError &e) {
+        return fail(SFB_E_CUDA, e.what());
+    }
+}
+
+int sfb_accumulate_geometry(const sfb_partner_table *T, int32_t *nt0, int32_t *n_nt) {
+    if (!T) return fail(SFB_E_ARG, "null table");
+    if (nt0) *nt0 = T->D.nt0;
+    if (n_nt) *n_nt = T->D.n_nt;
+    return 0;
+}
+
+static int check_rows(const sfb_partner_table *T, int row0, int n_rows) {
+    if (!T) return fail(SFB_E_ARG, "null table");
+    if (row0 < 0 || n_rows < 0 || row0 + n_rows > T->D.n_nt) return fail(SFB_E_ARG, "row range outside the table");
+    return 0;
+}
+
+int sfb_accumulate_export(sfb_partner_table *T, int row0, int n_rows, int32_t *d_count, int32_t *d_first,
+                          int64_t *d_sums) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (int rc = check_rows(T, row0, n_rows)) return rc;
+    if (!d_count || !d_first || !d_sums) return fail(SFB_E_ARG, "null buffer");
+    try {
+        CK(cudaSetDevice(g_ctx.device));
+        cudaStream_t st = g_ctx.stream;
+        const size_t ncol = 2 * T->D.W - 1, n = (size_t)n_rows * ncol, off = (size_t)row0 * ncol;
+        const size_t plane = (size_t)T->D.n_nt * ncol;
+        CK(cudaMemcpyAsync(d_count, T->count.p + off, n * 4, cudaMemcpyDeviceToDevice, st));
+        CK(cudaMemcpyAsync(d_first, T->first.p + off, n * 4, cudaMemcpyDeviceToDevice, st));
+        for (int q = 0; q < 6; q++)
+            CK(cudaMemcpyAsync(d_sums + q * n, T->sums.p + q * plane + off, n * 8, cudaMemcpyDeviceToDevice, st));
         CK(cudaStreamSynchronize(st));
         return 0;
     } catch (const CudaError &e) {
         return fail(SFB_E_CUDA, e.what());
     }
+}
+
+int sfb_accumulate_merge(sfb_partner_table *T, int row0, int n_rows, const int32_t *d_count, const int32_t *d_first,
+                         const int64_t *d_sums) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (int rc = check_rows(T, row0, n_rows)) return rc;
+    if (!d_count || !d_first || !d_sums) return fail(SFB_E_ARG, "null buffer");
+    try {
+        CK(cudaSetDevice(g_ctx.device));
+        launch_accum_merge(T->D, row0, n_rows, d_count, d_first, (const long long *)d_sums, g_ctx.stream, &T->n_launches);
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(g_ctx.stream));
+        return 0;
+    } catch (const CudaError &e) {
+        return fail(SFB_E_CUDA, e.what());
+    }
+}
+
+int sfb_accumulate_compact(sfb_partner_table *T, int row0, int n_rows, int64_t *n_entries) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (int rc = check_rows(T, row0, n_rows)) return rc;
+    if (!n_entries) return fail(SFB_E_ARG, "null argument");
+    try {
+        CK(cudaSetDevice(g_ctx.device));
+        cudaStream_t st = g_ctx.stream;
+        T->c_row0 = row0;
+        T->c_rows = n_rows;
+        T->nparts.alloc(std::max(n_rows, 1));
+        T->offsets.alloc((size_t)n_rows + 1);
+        launch_accum_count(T->D, row0, n_rows, T->nparts.p, T->offsets.p, st, &T->n_launches);
+        long long total = 0;
+        if (n_rows > 0)
+            CK(cudaMemcpyAsync(&total, T->offsets.p + n_rows, 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        T->n_entries = total;
+        const size_t m = (size_t)std::max<long long>(total, 1);
+        T->c_partner.alloc(m);
+        T->c_count.alloc(m);
+        T->c_first.alloc(m);
+        T->c_sums.alloc(6 * m);
+        launch_accum_emit(T->D, row0, n_rows, T->offsets.p, T->c_partner.p, T->c_count.p, T->c_first.p, T->c_sums.p, total,
+                          st, &T->n_launches);
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(st));
+        *n_entries = total;
+        return 0;
+    } catch (const CudaError &e) {
+        return fail(SFB_E_CUDA, e.what());
+    }
+}
+
+int sfb_accumulate_fetch(sfb_partner_table *T, int32_t *nparts, int32_t *partner, int32_t *count, int32_t *first_seen,
+                         int64_t *sums) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!T || T->n_entries < 0) return fail(SFB_E_STATE, "sfb_accumulate_compact has not been called");
+    if (!nparts || !partner || !count || !first_seen || !sums) return fail(SFB_E_ARG, "null buffer");
+    try {
+        CK(cudaSetDevice(g_ctx.device));
+        cudaStream_t st = g_ctx.stream;
+        const size_t m = (size_t)T->n_entries;
+        if (T->c_rows) CK(cudaMemcpyAsync(nparts, T->nparts.p, sizeof(int32_t) * T->c_rows, cudaMemcpyDeviceToHost, st));
+        if (m) {
+            CK(cudaMemcpyAsync(partner, T->c_partner.p, 4 * m, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(count, T->c_count.p, 4 * m, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(first_seen, T->c_first.p, 4 * m, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(sums, T->c_sums.p, 8 * 6 * m, cudaMemcpyDeviceToHost, st));
+        }
+        CK(cudaStreamSynchronize(st));
+        return 0;
+    } catch (const CudaError &e) {
+        return fail(SFB_E_CUDA, e.what());
+    }
+}
+
+int sfb_accumulate_launches(const sfb_partner_table *T) { return T ? T->n_launches : 0; }
+
+void sfb_accumulate_free(sfb_partner_table *T) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    delete T;
 }
 
 }  // extern "C"

@@ -118,13 +118,29 @@ void launch_slice_hc(const uint8_t *hc, int L, int W, int step, int first_window
 void launch_slice_sc(const int32_t *es1, int L, int W, int step, int first_window, int n_windows, int final_slot,
                      int32_t *out, cudaStream_t stream, int *n_launches);
 
+// ScanFold-Fold accumulation (accumulate.cu): dense banded accumulators over the nucleotides a shard touches,
+// then compaction to per-nucleotide partner lists.
+struct AccumDense {
+    int nt0, n_nt, W;           // nucleotides [nt0, nt0 + n_nt) (0-based), 2W-1 partner-offset columns each
+    int32_t *count;             // [n_nt][2W-1] windows holding the pair
+    int32_t *first_seen;        // [n_nt][2W-1] lowest absolute window index (INT32_MAX if none)
+    long long *sums;            // [6][n_nt][2W-1]: zA zB mfeA mfeB edA edB (exact split sums, see scanfold_b200.h)
+};
 struct AccumLaunch {
-    int L, W, step, first_window, n_windows;
-    const int16_t *pair_tbl;
+    int step, first_window, n_windows;
+    const int16_t *pair_tbl;    // [n_windows][W]
     const int32_t *z100, *mfe, *ed100;
-    long long *count, *sum_z, *sum_mfe, *sum_ed;
-    int32_t *first_seen;
+    AccumDense D;
 };
 void launch_accumulate(const AccumLaunch &A, cudaStream_t stream, int *n_launches);
+// adds `src` (same geometry as rows [row0, row0 + n_rows) of D) into D; first_seen takes the minimum
+void launch_accum_merge(const AccumDense &D, int row0, int n_rows, const int32_t *src_count, const int32_t *src_first,
+                        const long long *src_sums, cudaStream_t stream, int *n_launches);
+// per-nucleotide partner counts for rows [row0, row0 + n_rows) -> nparts[n_rows]; offsets[n_rows + 1] = exclusive scan
+void launch_accum_count(const AccumDense &D, int row0, int n_rows, int32_t *nparts, long long *offsets,
+                        cudaStream_t stream, int *n_launches);
+void launch_accum_emit(const AccumDense &D, int row0, int n_rows, const long long *offsets, int32_t *partner,
+                       int32_t *count, int32_t *first_seen, long long *sums, long long n_entries, cudaStream_t stream,
+                       int *n_launches);
 
 }  // namespace sfb

@@ -1,4 +1,4 @@
-// Window gathering, background shuffles (Philox4x32-10) and the ScanFold-Fold accumulation kernel.
+// Window gathering and background shuffles (Philox4x32-10).
 //
 // Replaces scramble() (ScanFoldFunctions.py:834-851): mono = random.sample permutation (:800-802),
 // di = Altschul-Erikson dinucleotide shuffle (:155-277).  The reference shuffles are unseeded, so the
@@ -198,33 +198,6 @@ __global__ void shuffle_kernel(ShuffleLaunch A) {
     dst[W - 1] = (uint8_t)last;
 }
 
-// Per-nucleotide gather over its <= W covering windows in ascending window order:
-// no atomics, deterministic.  One thread per nucleotide.
-__global__ void accumulate_kernel(AccumLaunch A) {
-    int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= A.L) return;
-    const int W = A.W, step = A.step;
-    const int ncol = 2 * W - 1;
-    // windows w (absolute) with w*step <= k < w*step + W, restricted to this shard
-    int w_hi = k / step;
-    int w_lo = (k - W + 1 + step - 1) / step;
-    if (k - W + 1 < 0) w_lo = 0;
-    int lo = max(w_lo, A.first_window), hi = min(w_hi, A.first_window + A.n_windows - 1);
-    long long base = (long long)k * ncol;
-    for (int w = lo; w <= hi; w++) {
-        int slot = w - A.first_window;
-        int pos = k - w * step;
-        int partner = A.pair_tbl[(long long)slot * W + pos];
-        int off = partner ? (w * step + partner - 1) - k : 0;
-        long long idx = base + off + (W - 1);
-        A.count[idx] += 1;
-        A.sum_z[idx] += A.z100[slot];
-        A.sum_mfe[idx] += A.mfe[slot];
-        A.sum_ed[idx] += A.ed100[slot];
-        if (w < A.first_seen[idx]) A.first_seen[idx] = w;
-    }
-}
-
 }  // namespace
 
 void launch_gather_windows(const uint8_t *seq_codes, int L, int W, int step, int first_window, int n_windows,
@@ -254,12 +227,6 @@ void launch_shuffle(const ShuffleLaunch &A, cudaStream_t stream, int *n_launches
     long long n = (long long)A.n_windows * A.r;
     if (n <= 0) return;
     shuffle_kernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(A);
-    if (n_launches) (*n_launches)++;
-}
-
-void launch_accumulate(const AccumLaunch &A, cudaStream_t stream, int *n_launches) {
-    if (A.L <= 0) return;
-    accumulate_kernel<<<(A.L + 127) / 128, 128, 0, stream>>>(A);
     if (n_launches) (*n_launches)++;
 }
 

@@ -20,7 +20,9 @@ SHUFFLE_MONO, SHUFFLE_DI = 0, 1
 
 EXPORTS = ["sfb_version", "sfb_init", "sfb_shutdown", "sfb_last_error", "sfb_params_besteffort", "sfb_fold_batch",
            "sfb_pf_batch", "sfb_deigan", "sfb_scan", "sfb_scan_plan_create", "sfb_scan_plan_keep_shuffles",
-           "sfb_scan_plan_run", "sfb_scan_plan_fetch", "sfb_scan_plan_destroy", "sfb_accumulate", "sfb_microbench", "sfb_set_stream"]
+           "sfb_scan_plan_run", "sfb_scan_plan_fetch", "sfb_scan_plan_destroy", "sfb_accumulate_begin",
+           "sfb_accumulate_geometry", "sfb_accumulate_export", "sfb_accumulate_merge", "sfb_accumulate_compact",
+           "sfb_accumulate_fetch", "sfb_accumulate_launches", "sfb_accumulate_free", "sfb_microbench", "sfb_set_stream"]
 
 
 class EngineError(RuntimeError):
@@ -80,7 +82,15 @@ def load_library():
         L.sfb_scan_plan_fetch.argtypes = [C.c_void_p, C.POINTER(ScanOut)]
         L.sfb_scan_plan_destroy.argtypes = [C.c_void_p]
         L.sfb_scan_plan_destroy.restype = None
-        L.sfb_accumulate.argtypes = [C.POINTER(AccumArgs), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.sfb_accumulate_begin.argtypes = [C.POINTER(AccumArgs), C.POINTER(C.c_void_p)]
+        L.sfb_accumulate_geometry.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+        L.sfb_accumulate_export.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.sfb_accumulate_merge.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.sfb_accumulate_compact.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int64)]
+        L.sfb_accumulate_fetch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.sfb_accumulate_launches.argtypes = [C.c_void_p]
+        L.sfb_accumulate_free.argtypes = [C.c_void_p]
+        L.sfb_accumulate_free.restype = None
         L.sfb_shutdown.restype = None
         L.sfb_set_stream.argtypes = [C.c_void_p]
         L.sfb_microbench.argtypes = [C.c_int, C.POINTER(C.c_double)]
@@ -298,22 +308,67 @@ def scan(seq, W, step, r, **kw):
         plan.close()
 
 
-def accumulate(L, W, step, first_window, pair_tbl, z100, mfe_dcal, ed100):
-    """ScanFold-Fold accumulators (sfb_accumulate): dict of [L, 2W-1] int64 arrays + first_seen int32."""
-    ensure_init()
-    pt = np.ascontiguousarray(pair_tbl, dtype=np.int16)
-    n = pt.shape[0]
-    z = np.ascontiguousarray(z100, dtype=np.int32)
-    m = np.ascontiguousarray(mfe_dcal, dtype=np.int32)
-    e = np.ascontiguousarray(ed100, dtype=np.int32)
-    shape = (L, 2 * W - 1)
-    out = {k: np.zeros(shape, dtype=np.int64) for k in ("count", "sum_z100", "sum_mfe", "sum_ed100")}
-    out["first_seen"] = np.zeros(shape, dtype=np.int32)
-    a = AccumArgs(L, W, step, first_window, n, pt.ctypes.data, z.ctypes.data, m.ctypes.data, e.ctypes.data)
-    _check(load_library().sfb_accumulate(C.byref(a), out["count"].ctypes.data, out["sum_z100"].ctypes.data,
-                                         out["sum_mfe"].ctypes.data, out["sum_ed100"].ctypes.data,
-                                         out["first_seen"].ctypes.data))
-    return out
+class Accumulator:
+    """Device-resident ScanFold-Fold accumulators of one shard of windows (sfb_accumulate_*).
+
+    rows = nucleotides [nt0, nt0 + n_nt) touched by the shard, 0-based; 2W-1 partner-offset columns.
+    export()/merge() move halo rows through caller-provided DEVICE buffers (multi-GPU exchange);
+    compact() returns the per-nucleotide partner lists as numpy arrays."""
+
+    def __init__(self, L, W, step, first_window, pair_tbl, z100, mfe_dcal, ed100):
+        ensure_init()
+        self._lib = load_library()
+        pt = np.ascontiguousarray(pair_tbl, dtype=np.int16)
+        z = np.ascontiguousarray(z100, dtype=np.int32)
+        m = np.ascontiguousarray(mfe_dcal, dtype=np.int32)
+        e = np.ascontiguousarray(ed100, dtype=np.int32)
+        n = pt.shape[0]
+        if not (len(z) == len(m) == len(e) == n):
+            raise ValueError("per-window arrays must have one entry per pair-table row")
+        a = AccumArgs(L, W, step, first_window, n, pt.ctypes.data, z.ctypes.data, m.ctypes.data, e.ctypes.data)
+        self._h = C.c_void_p()
+        _check(self._lib.sfb_accumulate_begin(C.byref(a), C.byref(self._h)))
+        nt0, n_nt = C.c_int32(), C.c_int32()
+        _check(self._lib.sfb_accumulate_geometry(self._h, C.byref(nt0), C.byref(n_nt)))
+        self.W, self.step, self.nt0, self.n_nt, self.ncol = W, step, nt0.value, n_nt.value, 2 * W - 1
+
+    def export_rows(self, row0, n_rows, d_count, d_first, d_sums):
+        """device pointers (ints) of buffers sized n_rows*(2W-1) int32 / int32 / 6x int64"""
+        _check(self._lib.sfb_accumulate_export(self._h, row0, n_rows, d_count, d_first, d_sums))
+
+    def merge_rows(self, row0, n_rows, d_count, d_first, d_sums):
+        _check(self._lib.sfb_accumulate_merge(self._h, row0, n_rows, d_count, d_first, d_sums))
+
+    def compact(self, row0=0, n_rows=None):
+        """-> (nparts [n_rows], partner, count, first_seen [M], sums [6, M]); entries in column order per nucleotide"""
+        if n_rows is None:
+            n_rows = self.n_nt - row0
+        m = C.c_int64()
+        _check(self._lib.sfb_accumulate_compact(self._h, row0, n_rows, C.byref(m)))
+        M = m.value
+        nparts = np.zeros(max(n_rows, 1), dtype=np.int32)
+        partner = np.zeros(max(M, 1), dtype=np.int32)
+        count = np.zeros(max(M, 1), dtype=np.int32)
+        first = np.zeros(max(M, 1), dtype=np.int32)
+        sums = np.zeros((6, max(M, 1)), dtype=np.int64)
+        _check(self._lib.sfb_accumulate_fetch(self._h, nparts.ctypes.data, partner.ctypes.data, count.ctypes.data,
+                                              first.ctypes.data, sums.ctypes.data))
+        return nparts[:n_rows], partner[:M], count[:M], first[:M], sums[:, :M]
+
+    @property
+    def n_launches(self):
+        return self._lib.sfb_accumulate_launches(self._h)
+
+    def close(self):
+        if self._h:
+            self._lib.sfb_accumulate_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def microbench(which):

@@ -1,0 +1,236 @@
+"""The ScanFold-Fold step: per-nucleotide partner statistics -> best partner -> competition -> final
+partners.  Restates ScanFold.py:1036-1453 (aggregation :1051-1260, competition :1273-1453) and the helpers
+competing_pairs / best_basepair (ScanFoldFunctions.py:343-474) on top of the accumulators the CUDA library
+produces (sfb_accumulate_*), replacing the reference's per-record dict-of-lists churn and its O(N^2)
+competition scans by O(N * partners) array code that picks exactly the same winners.
+
+Numerical contract (what makes the outputs byte-identical to the reference run under Python >= 3.12):
+  * every per-partner sum is the correctly rounded exact sum of the window values (CPython >= 3.12 `sum()`
+    uses compensated summation, which is exact here); the accumulators carry each value d = k/100 as the
+    exact pair A = rint(d * 2^20), B = (d - A * 2^-20) * 2^59, so the sum is order independent and a
+    multi-GPU reduction is bit exact;
+  * every mean is statistics.mean = the correctly rounded exact rational mean;
+  * ties in `min(dict, key=dict.get)` go to the partner seen first (lowest window index).
+"""
+import bisect
+
+import numpy as np
+
+SCALE_A = 2.0 ** -20
+SCALE_B = 2.0 ** -59
+
+
+class PartnerTable:
+    """Compact per-nucleotide partner statistics (CSR over covered nucleotides 1..n_nt, 1-based coordinates).
+    Within a nucleotide the entries are in first-seen order (ascending first window index)."""
+
+    def __init__(self, nt_ptr, partner, count, first_seen, sums):
+        self.nt_ptr = np.asarray(nt_ptr, dtype=np.int64)     # [n_nt + 1]
+        self.partner = np.asarray(partner, dtype=np.int64)   # [M] partner coordinate (== own coordinate: unpaired)
+        self.count = np.asarray(count, dtype=np.int64)       # [M] windows holding this pair
+        self.first_seen = np.asarray(first_seen, dtype=np.int64)
+        self.sums = np.asarray(sums, dtype=np.int64)         # [6, M]: zA zB mfeA mfeB edA edB
+        self.n_nt = len(self.nt_ptr) - 1
+
+
+def table_from_compact(nparts, partner, count, first_seen, sums):
+    """sfb_accumulate_fetch arrays (entries in column order) -> PartnerTable in first-seen order"""
+    nparts = np.asarray(nparts, dtype=np.int64)
+    ptr = np.concatenate([[0], np.cumsum(nparts)])
+    own = np.repeat(np.arange(len(nparts)), nparts)
+    order = np.lexsort((np.asarray(first_seen), own))
+    return PartnerTable(ptr, np.asarray(partner)[order], np.asarray(count)[order], np.asarray(first_seen)[order],
+                        np.asarray(sums)[:, order])
+
+
+def concat_tables(tables):
+    """per-shard tables over consecutive nucleotide ranges -> one table"""
+    ptr = [np.zeros(1, dtype=np.int64)]
+    base = 0
+    for t in tables:
+        ptr.append(t.nt_ptr[1:] + base)
+        base += t.nt_ptr[-1]
+    return PartnerTable(np.concatenate(ptr), np.concatenate([t.partner for t in tables]),
+                        np.concatenate([t.count for t in tables]), np.concatenate([t.first_seen for t in tables]),
+                        np.concatenate([t.sums for t in tables], axis=1))
+
+
+def split_exact(values100):
+    """int k (value = k/100) -> (A, B) int64 with fl(k/100) == A * 2^-20 + B * 2^-59 exactly"""
+    d = np.asarray(values100, dtype=np.float64) / 100.0
+    a = np.rint(d * 2.0 ** 20)
+    b = (d - a * SCALE_A) * 2.0 ** 59
+    return a.astype(np.int64), b.astype(np.int64)
+
+
+def _exact_sum(a, b):
+    """correctly rounded value of the exact sum held as (sum A, sum B)"""
+    return a.astype(np.float64) * SCALE_A + b.astype(np.float64) * SCALE_B
+
+
+_THRESHOLDS = np.array([-2.0, -1.0, 0.0, 1.0, 2.0, 10.0])
+
+
+def _exact_mean(a, b, n):
+    """statistics.mean of the values behind (sum A, sum B): correctly rounded exact rational mean.
+    Fast float64 path, exact big-integer path wherever a later rounding / comparison could see the difference."""
+    s = _exact_sum(a, b)
+    m = s / n
+    x100 = m * 100.0
+    x1e6 = m * 1e6
+    risky = (np.abs(x100 - np.floor(x100) - 0.5) < 1e-6) | (np.abs(x1e6 - np.floor(x1e6) - 0.5) < 1e-3)
+    risky |= (np.abs(m[:, None] - _THRESHOLDS[None, :]) < 1e-9).any(axis=1)
+    for k in np.nonzero(risky)[0]:
+        num = (int(a[k]) << 39) + int(b[k])
+        m[k] = num / (int(n[k]) << 59)          # int / int is correctly rounded in Python
+    return m
+
+
+class NtResult:
+    """Per-nucleotide outcome of the aggregation (index 0 <-> coordinate 1)."""
+    pass
+
+
+def aggregate(table, seq, log_total=None, sirna_log=None):
+    """ScanFold.py:1051-1260.  Returns an object with, per covered nucleotide k (arrays of length n_nt):
+       part        best partner coordinate (== k: unpaired)           best_coordinate
+       cov_z       sum z / #total windows of the best partner         best_total_window_mean_bps[k].zscore
+       mean_z      mean z over the windows holding the best pair      best_bps[k].zscore
+       mean_mfe, mean_ed                                              .mfe / .ed of both dictionaries
+    and writes the .ScanFold.log / .ntPairCounts.log text when file objects are given."""
+    n_nt = table.n_nt
+    ptr = table.nt_ptr
+    M = len(table.partner)
+    own = np.repeat(np.arange(1, n_nt + 1, dtype=np.int64), np.diff(ptr))
+    cnt = table.count
+    sum_z = _exact_sum(table.sums[0], table.sums[1])
+    mean_z = _exact_mean(table.sums[0], table.sums[1], cnt)
+    mean_mfe = _exact_mean(table.sums[2], table.sums[3], cnt)
+    mean_ed = _exact_mean(table.sums[4], table.sums[5], cnt)
+    total_windows = np.add.reduceat(cnt, ptr[:-1]) if M else np.zeros(0, dtype=np.int64)
+    num_bp = np.add.reduceat((table.partner != own).astype(np.int64), ptr[:-1])
+    cov_z = sum_z / np.repeat(total_windows, np.diff(ptr))
+    # first minimum of cov_z within each nucleotide (dict order = first-seen order)
+    seg_min = np.minimum.reduceat(cov_z, ptr[:-1])
+    is_min = cov_z == np.repeat(seg_min, np.diff(ptr))
+    idx = np.arange(M, dtype=np.int64)
+    best = np.minimum.reduceat(np.where(is_min, idx, M), ptr[:-1])
+
+    if log_total is not None or sirna_log is not None:
+        _write_logs(table, seq, own, cnt, sum_z, mean_z, mean_mfe, mean_ed, cov_z, total_windows, num_bp,
+                    log_total, sirna_log)
+
+    res = NtResult()
+    res.n_nt = n_nt
+    res.part = table.partner[best]
+    res.cov_z = cov_z[best]
+    res.mean_z = mean_z[best]
+    res.mean_mfe = mean_mfe[best]
+    res.mean_ed = mean_ed[best]
+    res.total_windows = total_windows
+    res.num_bp = num_bp
+    return res
+
+
+def _r2(x):
+    return str(round(float(x), 2))
+
+
+def _write_logs(table, seq, own, cnt, sum_z, mean_z, mean_mfe, mean_ed, cov_z, total_windows, num_bp, log_total,
+                sirna_log):
+    """log lines of ScanFold.py:1150-1184 (not --by_ed)"""
+    ptr = table.nt_ptr
+    partner = table.partner
+    out = []
+    sirna = []
+    for k0 in range(table.n_nt):
+        k = k0 + 1
+        nuc = seq[k0]
+        out.append("\ni-nuc\tBP(j)\tNuc\t#BP_Win\tavgMFE\tavgZ\tavgED\tSumZ\tSumZ/#TotalWindows\tBPs= %d\n" % num_bp[k0])
+        out.append("nt-%d\t-\t%s\t%d\t-\t-\t-\t-\t-\n" % (k, nuc, total_windows[k0]))
+        sirna.append("%d\t%s\t%d\t%d\n" % (k, nuc, total_windows[k0], num_bp[k0]))
+        for m in range(ptr[k0], ptr[k0 + 1]):
+            j = int(partner[m])
+            tail = "%s\t%d\t%s\t%s\t%s\t%s\t%s\n" % (seq[j - 1], cnt[m], _r2(mean_mfe[m]), _r2(mean_z[m]),
+                                                     _r2(mean_ed[m]), _r2(sum_z[m]), _r2(cov_z[m]))
+            out.append(("%d\tNoBP\t" % k if j == k else "%d\t%d\t" % (k, j)) + tail)
+    if log_total is not None:
+        log_total.write("".join(out))
+    if sirna_log is not None:
+        sirna_log.write("".join(sirna))
+
+
+class FinalPartners:
+    """final_partners of ScanFold.py:1404-1442, one entry per covered nucleotide k (index k-1):
+       i, j     icoordinate / jcoordinate of the stored NucPair (i == j: unpaired)
+       z, mfe, ed   its metrics
+    """
+    pass
+
+
+def compete(res, seq, log_win=None):
+    """ScanFold.py:1273-1442 with competition == 1.  `res` comes from aggregate()."""
+    n = res.n_nt
+    part = res.part
+    z = res.cov_z
+    # inverse index: inv[c] = ascending nucleotides whose best partner is c   (competing_pairs scans)
+    order = np.argsort(part, kind="stable")
+    sorted_part = part[order]
+    starts = np.searchsorted(sorted_part, np.arange(1, n + 2))
+    order1 = order + 1
+
+    def comp(c):
+        """entries of best_total_window_mean_bps touching coordinate c, in dictionary (ascending) order
+        (competing_pairs, ScanFoldFunctions.py:343-357)"""
+        lst = order1[starts[c - 1]:starts[c]].tolist()
+        if part[c - 1] != c:              # entry c itself (icoordinate == c) unless already listed
+            bisect.insort(lst, c)
+        return lst
+
+    comp_cache = {}
+
+    def comp_c(c):
+        r = comp_cache.get(c)
+        if r is None:
+            r = comp_cache[c] = comp(c)
+        return r
+
+    fin = FinalPartners()
+    fin.i = np.zeros(n, dtype=np.int64)
+    fin.j = np.zeros(n, dtype=np.int64)
+    fin.z = np.zeros(n)
+    fin.mfe = np.zeros(n)
+    fin.ed = np.zeros(n)
+    zl = z.tolist()
+    partl = part.tolist()
+    lines = []
+    if log_win is not None:
+        lines.append("i\tbp(i)\tbp(j)\tavgMFE\tavgZ\tavgED\t*Indicates most favorable bp has competition; bp(j) has "
+                     "more favorable partner or is more likely to be unpaired\n")
+    for k in range(1, n + 1):
+        i, j = k, partl[k - 1]
+        best_m, best_z = -1, None
+        for c in (i, j):
+            for m in comp_c(c):
+                for cc in (partl[m - 1], m):
+                    for mm in comp_c(cc):
+                        zz = zl[mm - 1]
+                        if best_z is None or zz < best_z:
+                            best_m, best_z = mm, zz
+        wi, wj = best_m, partl[best_m - 1]
+        if k != wi and k != wj:
+            if log_win is not None:
+                lines.append("nt-%d*:\t%d\t%d\t%s\t%s\t%s\n" % (k, i, j, _r2(res.mean_mfe[k - 1]), _r2(res.mean_z[k - 1]),
+                                                             _r2(res.mean_ed[k - 1])))
+            fin.i[k - 1] = fin.j[k - 1] = k
+        else:
+            if log_win is not None:
+                lines.append("nt-%d:\t%d\t%d\t%s\t%s\t%s\n" % (k, wi, wj, _r2(res.mean_mfe[k - 1]), _r2(res.mean_z[k - 1]),
+                                                            _r2(res.mean_ed[k - 1])))
+            fin.i[k - 1], fin.j[k - 1] = wi, wj
+        fin.z[k - 1] = res.mean_z[wi - 1]
+        fin.mfe[k - 1] = res.mean_mfe[wi - 1]
+        fin.ed[k - 1] = res.mean_ed[wi - 1]
+    if log_win is not None:
+        log_win.write("".join(lines))
+    return fin

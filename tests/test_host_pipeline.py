@@ -1,0 +1,83 @@
+"""Host side of the hot path (z/p, ScanFold-Fold aggregation, competition, writers) against golden files
+written by the UNMODIFIED reference ScanFold.py (tests/golden/make_golden.py; its folds came from the CPU
+oracle through the RNA shim).  The per-window engine outputs are replayed from trace.npz, the accumulators
+come from a plain-loop numpy reference, so these tests need neither a GPU nor /root/reference.
+Bar: every output file byte-identical."""
+import json
+import os
+import types
+
+import numpy as np
+import pytest
+
+from util import accumulate_numpy
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+CASES = sorted(d for d in os.listdir(GOLDEN) if os.path.exists(os.path.join(GOLDEN, d, "case.json")))
+# written by the motif-extraction step that follows the hot path
+NEXT_ROW_FILES = ("ExtractedStructures.gff3",)
+
+
+def load_case(name):
+    d = os.path.join(GOLDEN, name)
+    case = json.load(open(os.path.join(d, "case.json")))
+    lines = open(os.path.join(d, "input.fa")).read().split("\n")
+    case["header"] = lines[0][1:]
+    case["seq"] = lines[1].replace("T", "U")
+    case["trace"] = np.load(os.path.join(d, "trace.npz"))
+    case["dir"] = d
+    return case
+
+
+def replay_table(case):
+    from scanfold_b200 import scan
+    t = case["trace"]
+    res = types.SimpleNamespace(W=case["W"], r=case["r"], n=case["n_windows"] + 1, mfe_dcal=t["mfe_dcal"],
+                                native_unconstrained_dcal=t["native_unconstrained_dcal"], shuffle_dcal=t["shuffle_dcal"],
+                                pair_tbl=t["pair_tbl"], centroid_tbl=t["centroid_tbl"], ed=t["ed"],
+                                ensemble_dG=t["ensemble_dG"], ms_total=0.0, ms_mfe=0.0, n_launches=0)
+    return scan.table_from_result(res, 0, case["step"], case["n_windows"], True)
+
+
+def expected_files(case):
+    exp = os.path.join(case["dir"], "expected")
+    return {f: open(os.path.join(exp, f)).read() for f in os.listdir(exp)
+            if f not in NEXT_ROW_FILES and "_motif_" not in f}
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_outputs_byte_identical(name, tmp_path, monkeypatch):
+    from scanfold_b200 import foldstep, pipeline
+    case = load_case(name)
+    table = replay_table(case)
+    args = case["args"]
+    stype = args[args.index("--type") + 1] if "--type" in args else "mono"
+    chrom = args[args.index("--name") + 1] if "--name" in args else "UserInput"
+    names = pipeline.RunNames(case["record"], case["header"].split()[0], case["W"], case["step"], case["r"], stype,
+                              name=chrom)
+    monkeypatch.chdir(tmp_path)
+    minz = pipeline.write_scan_outputs(case["seq"], table, names, 37, case["step"])
+    z100, mfe100, ed100 = pipeline.fold_inputs(table)
+    comp = accumulate_numpy(case["L"], case["W"], case["step"], 0, table.pair_tbl, z100, mfe100, ed100)
+    ptable = foldstep.table_from_compact(*comp)
+    pipeline.write_fold_outputs(case["seq"], ptable, names, minz, case["step"])
+    exp = expected_files(case)
+    got = {f: open(os.path.join(tmp_path, f)).read() for f in os.listdir(tmp_path)}
+    assert sorted(got) == sorted(exp)
+    for f in sorted(exp):
+        assert got[f] == exp[f], "%s differs in case %s" % (f, name)
+
+
+def test_stats_match_golden_out_rows():
+    """z / p columns of the .out file come out of stats.zscore_pvalue exactly (Appendix B Q1-Q3)"""
+    from scanfold_b200 import stats
+    for name in CASES:
+        case = load_case(name)
+        t = case["trace"]
+        z, p = stats.zscore_pvalue(t["native_unconstrained_dcal"], t["shuffle_dcal"])
+        out = [f for f in os.listdir(os.path.join(case["dir"], "expected")) if f.endswith(".out")][0]
+        rows = open(os.path.join(case["dir"], "expected", out)).read().split("\n")[1:-1]
+        assert len(rows) == case["n_windows"]
+        for k, row in enumerate(rows):
+            f = row.split("\t")
+            assert f[4] == str(float(z[k])) and f[5] == str(float(p[k])), (name, k)
