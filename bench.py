@@ -165,7 +165,7 @@ def workload_config(name, n_gpus):
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from scanfold_b200 import engine, scan, stats, workcount
+    from scanfold_b200 import engine, pipeline, scan, workcount
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -223,10 +223,8 @@ def run_ours(args):
     def e2e_step():
         t = scan.scan_record(seq, W, step, r, shuffle_type=stype, seed=42, first_window=w0, n_windows=nwin,
                              final_window=final)
-        z100 = np.rint(t.z * 100).astype(np.int32)
-        ed100 = np.rint(t.ed * 100).astype(np.int32)
-        acc = engine.accumulate(L, W, step, w0, t.pair_tbl, z100, t.mfe_dcal, ed100)
-        return t, acc
+        ptable = pipeline.partner_table_gpu(L, t)
+        return t, ptable
 
     e2e_steps = args.e2e_steps if args.e2e_steps else args.steps
     e2e_step()
@@ -239,7 +237,7 @@ def run_ours(args):
     ms_e2e = (time.perf_counter() - t0) * 1e3
     n_slots = nwin + (1 if final else 0)
     h2d = L + nwin * W * 2 + nwin * 12
-    d2h = n_slots * (4 + 4 + 4 * r + 2 * W + 2 * W + 8 + 8) + L * (2 * W - 1) * 36
+    d2h = n_slots * (4 + 4 + 4 * r + 2 * W + 2 * W + 8 + 8) + len(acc.partner) * 60 + acc.n_nt * 4
 
     # ---------------- max over ranks
     tt = torch.tensor([ms_dev, ms_e2e, ms_mfe], dtype=torch.float64, device="cuda")

@@ -1,0 +1,213 @@
+"""ScanFold.py-compatible command line on the CUDA engine.
+
+Same positional argument, flags and defaults as the reference (ScanFold.py:54-155), same output folder and
+file names (ScanFold.py:310-388,1484-1500), same file contents.  Additive flags only: --seed (Philox key of
+the device shuffles), --parity_shuffles (host-provided shuffles, for bit-exact comparison with a reference
+run), --params (ViennaRNA .par file), --gpu (device ordinal).
+
+Not carried over (out of scope): --lri, --algo rnastructure, --by_ed, -c 0, --global_refold and the
+motif extraction that follows the hot path; selecting one of the first five is an error, not a silent no-op.
+"""
+import argparse
+import os
+import random
+import re
+import sys
+import time
+from datetime import datetime
+
+import numpy as np
+
+from . import pipeline, scan
+
+
+def build_parser():
+    p = argparse.ArgumentParser(prog="ScanFold.py")
+    p.add_argument("filename", type=str, help="input FASTA file")
+    p.add_argument("--react", type=str, help="SHAPE reactivity file (2 or 3 tab-separated columns)")
+    p.add_argument("-m", type=float, default=0.8, help="SHAPE slope")
+    p.add_argument("-b", type=float, default=-0.2, help="SHAPE intercept")
+    p.add_argument("--shapeD", action="store_true", help="Deigan SHAPE pseudo-energies")
+    p.add_argument("--shapeZ", action="store_true", help="Zarringhalam SHAPE pseudo-energies")
+    p.add_argument("--name", type=str, default="UserInput", help="sequence name used as chrom in wig/bp/fa")
+    p.add_argument("--fold_only", action="store_true")
+    p.add_argument("--dont_scan", action="store_true")
+    p.add_argument("--fold", action="store_true", default=True)
+    p.add_argument("-f", type=int, default=-2, help="legacy z-score filter")
+    p.add_argument("-c", type=int, default=1, help="competition on (1) or off (0)")
+    p.add_argument("--out_name", type=str, default=None, help="output folder name")
+    p.add_argument("-s", type=int, default=1, help="step size")
+    p.add_argument("-w", type=int, default=120, help="window size")
+    p.add_argument("-r", type=int, default=100, help="randomizations per window")
+    p.add_argument("-t", type=int, default=37, help="temperature (C)")
+    p.add_argument("--type", type=str, default="mono", help="shuffle type: mono or di")
+    p.add_argument("--print", action="store_true")
+    p.add_argument("--print_random", action="store_true")
+    p.add_argument("--algo", type=str, default="rnafold")
+    p.add_argument("--constraints", type=str, help="hard-constraint file; line 3 holds one symbol per nucleotide")
+    p.add_argument("--span", type=int, help="maximum base-pair span")
+    p.add_argument("--global_refold", action="store_true")
+    p.add_argument("--lri", action="store_true")
+    p.add_argument("--kmer", type=int, default=20)
+    p.add_argument("--kmer_step_size", type=int, default=1)
+    p.add_argument("--lri_cutoff", type=int, default=-25)
+    p.add_argument("--by_ed", action="store_true")
+    p.add_argument("--out1", type=str, default="./ScanFold.NoFilter")
+    p.add_argument("--out2", type=str, default="./ScanFold.-1Filter")
+    p.add_argument("--out3", type=str, default="./ScanFold.-2Filter")
+    p.add_argument("--out4", type=str, default="./ScanFold.Log.txt")
+    p.add_argument("--out5", type=str, default="./ScanFold.FinalPartners.txt")
+    p.add_argument("--out6", type=str, default="./IGV_BP_Track")
+    p.add_argument("--fasta_index", type=str, default="./user_input.fai")
+    p.add_argument("--dbn_file_path", type=str, default="AllDBN-global_refold.txt")
+    p.add_argument("--dbn_file_path1", type=str, default="Zavg_NoFilter")
+    p.add_argument("--dbn_file_path2", type=str, default="Zavg_-1_pairs")
+    p.add_argument("--dbn_file_path3", type=str, default="Zavg_-2_pairs")
+    p.add_argument("--dbn_file_path4", type=str, default="AllDBN.txt")
+    p.add_argument("--structure_extract_file", type=str, default="ExtractedStructures.gff3")
+    p.add_argument("--final_partners_wig", type=str, default="./IGV_BP_Zavg_metrics")
+    # additive
+    p.add_argument("--seed", type=int, default=42, help="[scanfold_b200] Philox key for device shuffles")
+    p.add_argument("--parity_shuffles", type=str, default=None,
+                   help="[scanfold_b200] .npz with `shuffles` [(windows+1), r, W] uint8 to fold instead of device shuffles")
+    p.add_argument("--params", type=str, default=None, help="[scanfold_b200] ViennaRNA parameter file")
+    p.add_argument("--gpu", type=int, default=0, help="[scanfold_b200] CUDA device ordinal")
+    return p
+
+
+def read_fasta(path):
+    """records as (name, sequence); name = header up to the first whitespace (Biopython's record.name)"""
+    name, chunks = None, []
+    with open(path) as f:
+        for line in f:
+            line = line.rstrip("\n")
+            if line.startswith(">"):
+                if name is not None:
+                    yield name, "".join(chunks)
+                parts = line[1:].split()
+                name, chunks = (parts[0] if parts else ""), []
+            elif name is not None:
+                chunks.append(line.strip())
+    if name is not None:
+        yield name, "".join(chunks)
+
+
+def read_reactivities(path):
+    """getShapeDataFromFile (ScanFold.py:218-262): 1-based list, -999 for NA and for positions the file skips"""
+    vec = [-999.0]
+    count = 1
+    lines = open(path).read().splitlines()
+    ncol = len(lines[0].split("\t"))
+    if ncol not in (2, 3):
+        raise ValueError("Trouble parsing reactivity data")
+    for line in lines:
+        f = line.split("\t")
+        pos = int(f[0])
+        value = f[2] if ncol == 3 else f[1]
+        if value == "NA":
+            value = -999
+        if pos != count:
+            vec.extend([-999.0] * (pos - count))
+            count = pos
+        vec.append(float(value))
+        count += 1
+    return vec
+
+
+def make_output_folder(cwd, out_name, read_name):
+    """folder cascade of ScanFold.py:310-369"""
+    stamp = lambda: datetime.now().strftime("%m-%d-%Y-%H.%M.%S")
+    rnd3 = lambda: str(random.randint(100, 999))
+    try:
+        if out_name is not None:
+            try:
+                folder = out_name
+                os.mkdir(os.path.join(cwd, folder))
+            except OSError:
+                folder = out_name + "_" + stamp()
+                os.mkdir(os.path.join(cwd, folder))
+        else:
+            folder = read_name
+            os.mkdir(os.path.join(cwd, folder))
+    except OSError:
+        try:
+            folder = (out_name + "_" + stamp() + "_" + rnd3()) if out_name is not None else "SF_Results_" + stamp()
+            os.mkdir(os.path.join(cwd, folder))
+        except OSError:
+            folder = "ScanFold-Results_" + stamp() + "_" + rnd3()
+            os.mkdir(os.path.join(cwd, folder))
+    print("Making output folder named:" + folder)
+    return folder
+
+
+def run_record(args, record_name, raw_seq, original_directory):
+    t0 = time.time()
+    seq = raw_seq.replace("T", "U").replace("t", "u")      # Seq.transcribe (ScanFold.py:282)
+    if "-" in seq:
+        raise ValueError("Gaps found in sequence. Please submit a complete sequence to ScanFold")
+    read_name = record_name
+    if "|" in read_name:
+        read_name = re.split(r"\|", read_name)[0]
+    cwd = os.getcwd()
+    folder = make_output_folder(cwd, args.out_name, read_name)
+    os.chdir(os.path.join(cwd, folder))
+    try:
+        W, step, r = int(args.w), int(args.s), int(args.r)
+        names = pipeline.RunNames(read_name, record_name, W, step, r, str(args.type), name=args.name, out6=args.out6,
+                                  final_partners_wig=args.final_partners_wig, dbn1=args.dbn_file_path1,
+                                  dbn2=args.dbn_file_path2, dbn3=args.dbn_file_path3, dbn4=args.dbn_file_path4)
+        print("Output name=" + names.outname)
+        if len(seq) < W:
+            print(record_name + " sequence is less than window size. Moving on to next entry.")
+            return
+        hc = None
+        if args.constraints is not None:
+            print("Considering constraint input")
+            hc = open(args.constraints).readlines()[2].rstrip("\n")   # relative to the output folder, as in the reference (Q8)
+        react = None
+        if args.react is not None:
+            print("Considering SHAPE reactivity input")
+            react = read_reactivities(os.path.join(original_directory, args.react))
+            if args.shapeZ and not args.shapeD:
+                raise TypeError("sc_add_SHAPE_zarringhalam() is called with one argument by the reference "
+                                "(ScanFold.py:536) and fails there too; use --shapeD")
+        parity = None
+        if args.parity_shuffles:
+            parity = np.load(args.parity_shuffles if os.path.isabs(args.parity_shuffles)
+                             else os.path.join(original_directory, args.parity_shuffles))["shuffles"]
+        print("Scanning input sequence:", read_name)
+        table = scan.scan_record(seq.upper(), W, step, r, shuffle_type=str(args.type), seed=args.seed,
+                                 parity_shuffles=parity, temperature=float(args.t), max_span=args.span or 0, hc=hc,
+                                 react=react, shape_m=args.m, shape_b=args.b)
+        table_seq = seq                                            # the .out Sequence column keeps the input case (Q11)
+        minz = pipeline.write_scan_outputs(table_seq, table, names, int(args.t), step)
+        print("Elapsed time: %ss" % round(time.time() - t0, 2))
+        print("Determining best base pairs...")
+        ptable = pipeline.partner_table_gpu(len(seq), table)
+        pipeline.write_fold_outputs(seq, ptable, names, minz, step)
+        print("Total runtime: %ss" % round(time.time() - t0, 2))
+        print("ScanFold-Fold analysis complete! Output found in folder named: " + folder)
+    finally:
+        os.chdir(original_directory)
+
+
+def main(argv=None):
+    args = build_parser().parse_args(argv)
+    for flag, why in ((args.lri, "--lri (experimental duplex scan)"), (args.by_ed, "--by_ed"),
+                      (args.global_refold, "--global_refold (full-length fold)"), (args.c != 1, "-c 0"),
+                      (str(args.algo) != "rnafold", "--algo " + str(args.algo)),
+                      (args.fold_only, "--fold_only"), (args.dont_scan, "--dont_scan")):
+        if flag:
+            raise SystemExit("scanfold_b200: %s is outside the scanning hot path this build covers (see DESIGN.md)" % why)
+    if str(args.type) not in ("mono", "di"):
+        raise SystemExit('Shuffle type not properly designated; please input "di" or "mono"')
+    from . import engine
+    engine.init(args.gpu, args.params)
+    original_directory = os.getcwd()
+    print(original_directory)
+    for record_name, raw_seq in read_fasta(args.filename):
+        run_record(args, record_name, raw_seq, original_directory)
+
+
+if __name__ == "__main__":
+    main()

@@ -268,40 +268,3 @@ def test_scan_shape_mode(engine, oracle):
             o2 = oracle.pf(frag, sc_stack=scw)
             assert abs(res.ed[nwin] - o2["ed"]) <= 1e-6 * max(1, abs(o2["ed"]))
             assert res.mfe_dcal[nwin] == eo
-
-
-def test_accumulate(engine):
-    rng = np.random.default_rng(2)
-    L, W, step = 300, 40, 3
-    nwin = (L - W) // step + 1
-    pt = np.zeros((nwin, W), dtype=np.int16)
-    for w in range(nwin):
-        for _ in range(6):
-            i = int(rng.integers(0, W - 5))
-            j = int(rng.integers(i + 4, W))
-            if pt[w, i] == 0 and pt[w, j] == 0:
-                pt[w, i], pt[w, j] = j + 1, i + 1
-    z = rng.integers(-400, 300, nwin).astype(np.int32)
-    m = rng.integers(-3000, 0, nwin).astype(np.int32)
-    e = rng.integers(0, 4000, nwin).astype(np.int32)
-    out = engine.accumulate(L, W, step, 0, pt, z, m, e)
-    cnt = np.zeros((L, 2 * W - 1), dtype=np.int64)
-    sz = np.zeros_like(cnt)
-    fs = np.full((L, 2 * W - 1), 0x7F7F7F7F, dtype=np.int64)
-    for w in range(nwin):
-        for p in range(W):
-            k = w * step + p
-            off = (w * step + pt[w, p] - 1 - k) if pt[w, p] else 0
-            cnt[k, off + W - 1] += 1
-            sz[k, off + W - 1] += z[w]
-            fs[k, off + W - 1] = min(fs[k, off + W - 1], w)
-    assert np.array_equal(out["count"], cnt)
-    assert np.array_equal(out["sum_z100"], sz)
-    assert np.array_equal(out["first_seen"].astype(np.int64), fs)
-    # two shards add up to the whole (multi-GPU reduce property)
-    h = nwin // 2
-    a = engine.accumulate(L, W, step, 0, pt[:h], z[:h], m[:h], e[:h])
-    b = engine.accumulate(L, W, step, h, pt[h:], z[h:], m[h:], e[h:])
-    for key in ("count", "sum_z100", "sum_mfe", "sum_ed100"):
-        assert np.array_equal(a[key] + b[key], out[key])
-    assert np.array_equal(np.minimum(a["first_seen"], b["first_seen"]), out["first_seen"])
