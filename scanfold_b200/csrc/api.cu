@@ -104,13 +104,30 @@ void encode_host(const uint8_t *ascii, size_t n, std::vector<uint8_t> &codes) {
 
 // ---------------------------------------------------------------------------------------------
 struct FoldWork {  // device scratch for one MFE launch
-    DevBuf<int32_t> scratch;
+    DevBuf<int32_t> scratch, scratch2;
     int mode = 0;
-    size_t per_cta = 0;
+    size_t per_cta = 0, per_warp2 = 0;
     void prepare(int W, int n_fold) {
         per_cta = mfe_scratch_ints_per_cta(W, &mode);
         size_t need = per_cta * (size_t)mfe_grid_size(W, g_ctx.n_sm, n_fold);
         if (need > scratch.n) scratch.alloc(need);
+        if (mfe2_supports(W)) {
+            per_warp2 = mfe2_scratch_shorts_per_warp(W);
+            size_t need2 = (per_warp2 * 4 * (size_t)mfe2_grid_size(g_ctx.n_sm, n_fold) + 1) / 2;
+            if (need2 > scratch2.n) scratch2.alloc(need2);
+        }
+    }
+    // energy-only unconstrained folds: int16 warp-per-fold kernel, then the int32 kernel on whatever it flagged
+    void launch_energy_only(MfeLaunch L, cudaStream_t st, int *n_launch) const {
+        if (mfe2_supports(L.W) && !L.hc && !L.sc && L.max_span <= 0 && !L.pair_tbl) {
+            MfeLaunch L2 = L;
+            L2.gscratch = scratch2.p;
+            L2.gscratch_per_cta = (long long)per_warp2;
+            launch_mfe2(L2, g_ctx.d_mfe, g_ctx.n_sm, st, n_launch);
+            L.redo_only = 1;
+        }
+        fill(L);
+        launch_mfe(L, g_ctx.d_mfe, g_ctx.n_sm, st, n_launch);
     }
     void fill(MfeLaunch &L) const {
         L.gscratch = scratch.p;
@@ -192,6 +209,8 @@ int sfb_init(int device_ordinal, const char *par_file_or_null) {
         if (!g_ctx.stream) g_ctx.stream = g_ctx.own_stream;
         if (!g_ctx.d_mfe) CK(cudaMalloc(&g_ctx.d_mfe, sizeof(MfeTables)));
         CK(cudaMemcpy(g_ctx.d_mfe, &g_ctx.hp.mfe, sizeof(MfeTables), cudaMemcpyHostToDevice));
+        mfe2_upload_tables(g_ctx.hp.mfe);
+        CK(cudaGetLastError());
         g_ctx.pf_temperature = -1e9;
         g_ctx.ready = true;
         ensure_pf_tables(37.0);
@@ -264,8 +283,7 @@ int sfb_fold_batch(const uint8_t *seqs, int n_seq, int len, const sfb_model *mod
         L.max_span = model ? model->max_bp_span : 0;
         L.e_out = d_e.p;
         L.pair_tbl = d_pt.p;
-        fw.fill(L);
-        launch_mfe(L, g_ctx.d_mfe, g_ctx.n_sm, g_ctx.stream, nullptr);
+        fw.launch_energy_only(L, g_ctx.stream, nullptr);
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(e_dcal, d_e.p, sizeof(int32_t) * n_seq, cudaMemcpyDeviceToHost, g_ctx.stream));
         if (pair_tbl)
@@ -509,8 +527,7 @@ int sfb_scan_plan_run(sfb_scan_plan *P, float *ms_total, float *ms_mfe, int32_t 
                 L.W = W;
                 L.max_span = 0;
                 L.e_out = P->shuf_e.p + (size_t)c0 * r;
-                P->fw.fill(L);
-                launch_mfe(L, g_ctx.d_mfe, g_ctx.n_sm, st, &n_launch);
+                P->fw.launch_energy_only(L, st, &n_launch);
             }
             // energy_list[0]: native without constraints / span (ScanFoldFunctions.py:774-789)
             const bool need_unc = P->constrained || a.model.max_bp_span > 0;

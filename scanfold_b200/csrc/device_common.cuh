@@ -76,7 +76,9 @@ struct MfeLaunch {
     int32_t *gscratch;    // global scratch for matrices that do not fit shared memory
     long long gscratch_per_cta;  // ints
     int mats_in_gmem;     // 0: everything in shared memory; 1: C/FML in global; 2: rolling buffers too
+    int redo_only;        // 1: only folds whose e_out holds MFE_REDO (flagged by the int16 kernel)
 };
+constexpr int MFE_REDO = 0x7fffff00;  // e_out marker: int16 range exceeded, fold again in int32
 
 struct PfLaunch {
     const uint8_t *seqs;  // [n_fold][W] codes
@@ -92,6 +94,12 @@ struct PfLaunch {
 
 void launch_mfe(const MfeLaunch &L, const MfeTables *d_tab, int n_sm, cudaStream_t stream, int *n_launches);
 size_t mfe_scratch_ints_per_cta(int W, int *mats_in_gmem);
+// second-generation energy-only kernel (mfe2.cu): one warp per fold, W <= 128, no constraints
+bool mfe2_supports(int W);
+int mfe2_grid_size(int n_sm, int n_fold);
+size_t mfe2_scratch_shorts_per_warp(int W);
+void mfe2_upload_tables(const MfeTables &M);
+void launch_mfe2(const MfeLaunch &L, const MfeTables *d_tab, int n_sm, cudaStream_t stream, int *n_launches);
 int mfe_grid_size(int W, int n_sm, int n_fold);
 
 void launch_pf(const PfLaunch &L, const MfeTables *d_mfe, const PfTables *d_pf, int n_sm, cudaStream_t stream,

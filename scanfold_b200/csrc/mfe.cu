@@ -348,6 +348,7 @@ __global__ void __launch_bounds__(NT) mfe_fold_kernel(MfeLaunch L, const MfeTabl
     c.h.max_span = L.max_span;
 
     for (int fold = blockIdx.x; fold < L.n_fold; fold += gridDim.x) {
+        if (L.redo_only && L.e_out[fold] != MFE_REDO) continue;
         // ---- per-fold prologue
         for (int k = tid; k < W; k += NT) S[k] = L.seqs[(long long)fold * W + k];
         c.h.hcf = nullptr;

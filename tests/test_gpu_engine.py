@@ -268,3 +268,18 @@ def test_scan_shape_mode(engine, oracle):
             o2 = oracle.pf(frag, sc_stack=scw)
             assert abs(res.ed[nwin] - o2["ed"]) <= 1e-6 * max(1, abs(o2["ed"]))
             assert res.mfe_dcal[nwin] == eo
+
+
+@pytest.mark.parametrize("W", [16, 17, 33, 40, 64, 65, 97, 120, 127, 128])
+def test_warp_per_fold_kernel_matches_int32_kernel(engine, oracle, W):
+    """energy-only folds take the int16 warp-per-fold kernel (mfe2.cu); with structure they take the int32 CTA
+    kernel (mfe.cu).  Same energies, bit for bit, including sequences that overflow int16 and get redone."""
+    seqs = rand_seqs(7000 + W, 600, W, gc_rich=True)
+    seqs += ["G" * (W // 2) + "C" * (W - W // 2), ("GC" * W)[:W], "A" * W, ("GGGGAAAACCCC" * W)[:W], ("AU" * W)[:W],
+             ("GGGGGCCCCC" * W)[:W], ("CUUCGG" * W)[:W], "N" * W, ("ACGUN" * W)[:W]]
+    e_fast, _ = engine.fold_batch(seqs, structure=False)
+    e_ref, _ = engine.fold_batch(seqs, structure=True)
+    bad = np.nonzero(e_fast != e_ref)[0]
+    assert len(bad) == 0, (W, [(int(k), seqs[k], int(e_fast[k]), int(e_ref[k])) for k in bad[:5]])
+    for k in list(range(0, 40)) + list(range(len(seqs) - 9, len(seqs))):
+        assert e_fast[k] == oracle.mfe(seqs[k], structure=False)[0], (W, k, seqs[k])
