@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <dlfcn.h>
 #include <memory>
@@ -125,6 +126,8 @@ struct FoldWork {  // device scratch for one MFE launch
             L2.gscratch_per_cta = (long long)per_warp2;
             launch_mfe2(L2, g_ctx.d_mfe, g_ctx.n_sm, st, n_launch);
             L.redo_only = 1;
+            static const bool no_redo = getenv("SFB_DEBUG_NO_REDO") != nullptr;  // debugging: leave MFE_REDO markers
+            if (no_redo) return;
         }
         fill(L);
         launch_mfe(L, g_ctx.d_mfe, g_ctx.n_sm, st, n_launch);

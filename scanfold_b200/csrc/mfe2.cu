@@ -32,7 +32,7 @@ constexpr int ROLL = 34;   // rows d-32 .. d+1 are live while a pair of diagonal
 constexpr int RCR = 16;    // raw-C / type ring: rows d-7 .. d+1
 constexpr int FOLDS_PER_CTA = 4;
 
-struct Tab2 {
+struct alignas(16) Tab2 {
     short stack[64], mmI[200], mm1n[200], mm23[200], mmH[200];
     short mlclose[200];        // mismatchM + TerminalAU + MLintern + MLclosing (closing pair of a multiloop)
     short mlstem[8 * 36];      // [type][5' code][3' code], code 5 = no neighbour: E_MLstem
@@ -146,6 +146,7 @@ mfe2_kernel(MfeLaunch L, const MfeTables *__restrict__ T, const Tab2 *__restrict
     {
         const int *src = reinterpret_cast<const int *>(gtab);
         int *dst = reinterpret_cast<int *>(&tb);
+        static_assert(sizeof(Tab2) % 4 == 0, "Tab2 is copied as 32-bit words");
         for (int k = threadIdx.x; k < (int)(sizeof(Tab2) / 4); k += blockDim.x) dst[k] = src[k];
     }
     __syncthreads();
