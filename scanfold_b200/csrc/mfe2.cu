@@ -20,6 +20,8 @@
 // keeps the 32 lanes busy with pairable cells.
 // int16 storage is exact as long as no stored energy drops below LOW16; a fold that does is flagged and redone
 // by the int32 kernel (mfe.cu) in the same stream, so results never depend on which kernel ran.
+#include <cstdlib>
+
 #include "device_common.cuh"
 
 namespace sfb {
@@ -135,14 +137,26 @@ __device__ int hairpin_special(const MfeTables *T, const Tab2 &tb, const unsigne
     return e + tb.mmH[(type * 5 + sx[i + 2]) * 5 + sx[j]];
 }
 
-template <int P>
-__global__ void __launch_bounds__(FOLDS_PER_CTA * 32, 1)
+// TW warps work on one fold ("team"); TW = 1 needs no block-level synchronisation at all, TW = 2 trades
+// three 64-thread named barriers per diagonal pair for twice the resident warps per scheduler.
+template <int TW>
+__device__ __forceinline__ void team_sync(int team) {
+    if constexpr (TW == 1)
+        __syncwarp();
+    else
+        asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "n"(32 * TW) : "memory");
+}
+
+template <int P, int TW>
+__global__ void __launch_bounds__(FOLDS_PER_CTA * 32 * TW, 1)
 mfe2_kernel(MfeLaunch L, const MfeTables *__restrict__ T, const Tab2 *__restrict__ gtab) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Tab2 &tb = *reinterpret_cast<Tab2 *>(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int team = warp / TW, tw = warp % TW, tlane = tw * 32 + lane;
+    constexpr int TL = 32 * TW;
     FoldSmem<P> &sm = *reinterpret_cast<FoldSmem<P> *>(smem_raw + ((sizeof(Tab2) + 15) & ~15) +
-                                                       (size_t)warp * ((sizeof(FoldSmem<P>) + 15) & ~15));
+                                                       (size_t)team * ((sizeof(FoldSmem<P>) + 15) & ~15));
     {
         const int *src = reinterpret_cast<const int *>(gtab);
         int *dst = reinterpret_cast<int *>(&tb);
@@ -153,31 +167,32 @@ mfe2_kernel(MfeLaunch L, const MfeTables *__restrict__ T, const Tab2 *__restrict
 
     const int W = L.W, H = W / 2;
     const unsigned full = 0xffffffffu;
-    short *gC = reinterpret_cast<short *>(L.gscratch) + (size_t)(blockIdx.x * FOLDS_PER_CTA + warp) * L.gscratch_per_cta;
+    short *gC = reinterpret_cast<short *>(L.gscratch) + (size_t)(blockIdx.x * FOLDS_PER_CTA + team) * L.gscratch_per_cta;
     short *RG = sm.roll;
     const unsigned char *sx = sm.sx;
+    short *list = sm.list + tw * P;
 
-    for (int fold = blockIdx.x * FOLDS_PER_CTA + warp; fold < L.n_fold; fold += gridDim.x * FOLDS_PER_CTA) {
+    for (int fold = blockIdx.x * FOLDS_PER_CTA + team; fold < L.n_fold; fold += gridDim.x * FOLDS_PER_CTA) {
         // ---- prologue: sequence with sentinels, INF in every rolling row
-        for (int k = lane; k < W + 2; k += 32)
+        for (int k = tlane; k < W + 2; k += TL)
             sm.sx[k] = (k == 0 || k == W + 1) ? 5 : L.seqs[(size_t)fold * W + k - 1];
         {
             const int4 inf4 = make_int4(INF16 * 65537, INF16 * 65537, INF16 * 65537, INF16 * 65537);
             int4 *p = reinterpret_cast<int4 *>(sm.roll);
-            for (int k = lane; k < (int)(sizeof(sm.roll) / 16); k += 32) p[k] = inf4;
+            for (int k = tlane; k < (int)(sizeof(sm.roll) / 16); k += TL) p[k] = inf4;
             p = reinterpret_cast<int4 *>(sm.rc);
-            for (int k = lane; k < (int)(sizeof(sm.rc) / 16); k += 32) p[k] = inf4;
+            for (int k = tlane; k < (int)(sizeof(sm.rc) / 16); k += TL) p[k] = inf4;
             p = reinterpret_cast<int4 *>(sm.dml);
-            for (int k = lane; k < (int)(sizeof(sm.dml) / 16); k += 32) p[k] = inf4;
+            for (int k = tlane; k < (int)(sizeof(sm.dml) / 16); k += TL) p[k] = inf4;
         }
         int minv = 0;
-        __syncwarp();
+        team_sync<TW>(team);
 
         for (int d0 = TURN + 1; d0 < W; d0 += 2) {
             const int nd = d0 + 1 < W ? 2 : 1;
-            // ---- phase T: pair types of both diagonals, compaction of the pairable cells
+            // ---- phase T: pair types, compaction of the pairable cells (TW = 2: one diagonal per warp)
             int nlist = 0;
-            for (int ds = 0; ds < nd; ds++) {
+            for (int ds = tw; ds < nd; ds += TW) {
                 const int d = d0 + ds, ncells = W - d, slot = d % ROLL, t4 = tri4(d, W);
                 for (int i0 = 0; i0 < ncells; i0 += 32) {
                     const int i = i0 + lane;
@@ -194,17 +209,18 @@ mfe2_kernel(MfeLaunch L, const MfeTables *__restrict__ T, const Tab2 *__restrict
                         }
                     }
                     const unsigned m = __ballot_sync(full, t != 0);
-                    if (t) sm.list[nlist + __popc(m & ((1u << lane) - 1))] = (short)(i | (ds << 8));
+                    if (t) list[nlist + __popc(m & ((1u << lane) - 1))] = (short)(i | (ds << 8));
                     nlist += __popc(m);
                 }
             }
             __syncwarp();
             // ---- phase C: one lane per pairable cell
-            const int umax = min(MAXLOOP, d0 + nd - 1 - 2 - (TURN + 1));
+            const int dhi = TW == 1 ? d0 + nd - 1 : d0 + tw;
+            const int umax = min(MAXLOOP, dhi - 2 - (TURN + 1));
             const int hp0 = T->hairpin_len[d0 - 1], hp1 = T->hairpin_len[d0];
             for (int base = 0; base < nlist; base += 32) {
                 const bool active = base + lane < nlist;
-                const int code = active ? sm.list[base + lane] : 0;
+                const int code = active ? list[base + lane] : (TW == 1 ? 0 : tw << 8);
                 const int i = code & 0xff, ds = code >> 8, d = d0 + ds, j = i + d;
                 const int type = tb.ptype[sx[i + 1] * 6 + sx[j + 1]];
                 const int si1 = sx[i + 2], sj1 = sx[j];
@@ -275,51 +291,56 @@ mfe2_kernel(MfeLaunch L, const MfeTables *__restrict__ T, const Tab2 *__restrict
                     gC[tri4(d, W) + i] = (short)(e < FIN16 ? e + tb.ext[type * 36 + sx[i] * 6 + sx[j + 2]] : INF16);
                 }
             }
-            __syncwarp();
+            team_sync<TW>(team);
             // ---- phase M: FML of diagonal d0, then d0 + 1
             for (int ds = 0; ds < nd; ds++) {
                 const int d = d0 + ds, ncells = W - d;
                 const int klo = TURN + 1, khi = d - 2 - TURN;       // split k: FML[i,i+k] + FML[i+k+1,j]
                 const int kb = d - 1 - H;                            // operand B is in the low half for k >= kb
-                for (int i0 = 0; i0 < ncells; i0 += 32) {
+                for (int i0 = tw * 32; i0 < ncells; i0 += TL) {
                     const int i = min(i0 + lane, ncells - 1);
-                    int m0 = 2 * INF16, m1 = 2 * INF16;
+                    int m0 = 2 * INF16, m1 = 2 * INF16, m2 = 2 * INF16, m3 = 2 * INF16;
                     int k = klo;
                     {   // segment 1: A low (+P), B high (+P)
                         const int kend = min(kb - 1, khi);
                         const short *pa = sm.fml + k * P + i;
                         const short *pb = sm.fml + (W - d + 1 + k) * P + d + i;
-                        for (; k + 1 <= kend; k += 2, pa += 2 * P, pb += 2 * P) {
+                        for (; k + 3 <= kend; k += 4, pa += 4 * P, pb += 4 * P) {
                             m0 = __viaddmin_s32(pa[0], pb[0], m0);
                             m1 = __viaddmin_s32(pa[P], pb[P], m1);
+                            m2 = __viaddmin_s32(pa[2 * P], pb[2 * P], m2);
+                            m3 = __viaddmin_s32(pa[3 * P], pb[3 * P], m3);
                         }
-                        if (k <= kend) {
-                            m0 = __viaddmin_s32(pa[0], pb[0], m0);
-                            k++;
-                        }
+                        for (; k <= kend; k++, pa += P, pb += P) m0 = __viaddmin_s32(pa[0], pb[0], m0);
                     }
                     {   // segment 2: A low (+P), B low (-P+1)
                         const int kend = min(H, khi);
                         const short *pa = sm.fml + k * P + i;
                         const short *pb = sm.fml + (d - 1 - k) * P + i + k + 1;
-                        for (; k + 3 <= kend; k += 4, pa += 4 * P, pb -= 4 * (P - 1)) {
+                        for (; k + 7 <= kend; k += 8, pa += 8 * P, pb -= 8 * (P - 1)) {
                             m0 = __viaddmin_s32(pa[0], pb[0], m0);
                             m1 = __viaddmin_s32(pa[P], pb[-(P - 1)], m1);
-                            m0 = __viaddmin_s32(pa[2 * P], pb[-2 * (P - 1)], m0);
-                            m1 = __viaddmin_s32(pa[3 * P], pb[-3 * (P - 1)], m1);
+                            m2 = __viaddmin_s32(pa[2 * P], pb[-2 * (P - 1)], m2);
+                            m3 = __viaddmin_s32(pa[3 * P], pb[-3 * (P - 1)], m3);
+                            m0 = __viaddmin_s32(pa[4 * P], pb[-4 * (P - 1)], m0);
+                            m1 = __viaddmin_s32(pa[5 * P], pb[-5 * (P - 1)], m1);
+                            m2 = __viaddmin_s32(pa[6 * P], pb[-6 * (P - 1)], m2);
+                            m3 = __viaddmin_s32(pa[7 * P], pb[-7 * (P - 1)], m3);
                         }
                         for (; k <= kend; k++, pa += P, pb -= P - 1) m0 = __viaddmin_s32(pa[0], pb[0], m0);
                     }
                     {   // segment 3: A high (-P+1), B low (-P+1)
                         const short *pa = sm.fml + (W - k) * P + k + i;
                         const short *pb = sm.fml + (d - 1 - k) * P + i + k + 1;
-                        for (; k + 1 <= khi; k += 2, pa -= 2 * (P - 1), pb -= 2 * (P - 1)) {
+                        for (; k + 3 <= khi; k += 4, pa -= 4 * (P - 1), pb -= 4 * (P - 1)) {
                             m0 = __viaddmin_s32(pa[0], pb[0], m0);
                             m1 = __viaddmin_s32(pa[-(P - 1)], pb[-(P - 1)], m1);
+                            m2 = __viaddmin_s32(pa[-2 * (P - 1)], pb[-2 * (P - 1)], m2);
+                            m3 = __viaddmin_s32(pa[-3 * (P - 1)], pb[-3 * (P - 1)], m3);
                         }
-                        if (k <= khi) m0 = __viaddmin_s32(pa[0], pb[0], m0);
+                        for (; k <= khi; k++, pa -= P - 1, pb -= P - 1) m0 = __viaddmin_s32(pa[0], pb[0], m0);
                     }
-                    int dec = min(m0, m1);
+                    int dec = min(min(m0, m1), min(m2, m3));
                     if (dec >= FIN16) dec = INF16;
                     int m = dec;
                     if (d - 1 > TURN) {
@@ -336,29 +357,36 @@ mfe2_kernel(MfeLaunch L, const MfeTables *__restrict__ T, const Tab2 *__restrict
                         sm.fml[d <= H ? d * P + i : (W - d) * P + d + i] = (short)m;
                     }
                 }
-                __syncwarp();
+                team_sync<TW>(team);
             }
         }
 
-        // ---- exterior loop: stage C (+ stem term) back from the scratch row, then F5 sequentially
+        // ---- exterior loop: stage C (+ stem term) back from the scratch row, then F5 sequentially (warp 0)
         {
             short *cx = sm.roll;
             const int ntri = tri4(W, W);
-            for (int k = lane; k < ntri; k += 32) cx[k] = __ldcg(gC + k);
-            for (int k = lane; k <= min(W, TURN + 1); k += 32) sm.f5[k] = 0;
-            __syncwarp();
-            for (int len = TURN + 2; len <= W; len++) {
-                const int j = len - 1;
-                int best = INF16;
-                for (int i = lane; i <= j - TURN - 1; i += 32) best = min(best, sm.f5[i] + cx[tri4(j - i, W) + i]);
-                best = __reduce_min_sync(full, best);
-                if (lane == 0) sm.f5[len] = (short)min((int)sm.f5[len - 1], best);
-                __syncwarp();
-            }
+            for (int k = tlane; k < ntri; k += TL) cx[k] = __ldcg(gC + k);
+            for (int k = tlane; k <= min(W, TURN + 1); k += TL) sm.f5[k] = 0;
             minv = __reduce_min_sync(full, minv);
-            if (lane == 0) L.e_out[fold] = minv < LOW16 ? MFE_REDO : (int)sm.f5[W];
+            if (lane == 0) sm.f5[P + 2 + tw] = (short)max(minv, -32000);
+            team_sync<TW>(team);
+            if (tw == 0) {
+                for (int len = TURN + 2; len <= W; len++) {
+                    const int j = len - 1;
+                    int best = INF16;
+                    for (int i = lane; i <= j - TURN - 1; i += 32) best = min(best, sm.f5[i] + cx[tri4(j - i, W) + i]);
+                    best = __reduce_min_sync(full, best);
+                    if (lane == 0) sm.f5[len] = (short)min((int)sm.f5[len - 1], best);
+                    __syncwarp();
+                }
+                if (lane == 0) {
+                    int mv = sm.f5[P + 2];
+                    for (int q = 1; q < TW; q++) mv = min(mv, (int)sm.f5[P + 2 + q]);
+                    L.e_out[fold] = mv < LOW16 ? MFE_REDO : (int)sm.f5[W];
+                }
+            }
         }
-        __syncwarp();
+        team_sync<TW>(team);
     }
 }
 
@@ -427,25 +455,27 @@ void mfe2_upload_tables(const MfeTables &M) {
     cudaMemcpy(g_dtab2, &h, sizeof(Tab2), cudaMemcpyHostToDevice);
 }
 
+template <int P, int TW>
+static void launch_mfe2_t(const MfeLaunch &L, const MfeTables *d_tab, int grid, cudaStream_t stream) {
+    const size_t smem = ((sizeof(Tab2) + 15) & ~15) + FOLDS_PER_CTA * ((sizeof(FoldSmem<P>) + 15) & ~15);
+    static bool cfg = false;
+    if (!cfg) {
+        cudaFuncSetAttribute(mfe2_kernel<P, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cfg = true;
+    }
+    mfe2_kernel<P, TW><<<grid, FOLDS_PER_CTA * 32 * TW, smem, stream>>>(L, d_tab, g_dtab2);
+}
+
 void launch_mfe2(const MfeLaunch &L, const MfeTables *d_tab, int n_sm, cudaStream_t stream, int *n_launches) {
     if (L.n_fold <= 0) return;
     const int grid = mfe2_grid_size(n_sm, L.n_fold);
+    static const int tw = getenv("SFB_MFE2_TEAM") ? atoi(getenv("SFB_MFE2_TEAM")) : 2;  // warps per fold (tuning knob)
     if (L.W <= 64) {
-        const size_t smem = ((sizeof(Tab2) + 15) & ~15) + FOLDS_PER_CTA * ((sizeof(FoldSmem<64>) + 15) & ~15);
-        static bool cfg = false;
-        if (!cfg) {
-            cudaFuncSetAttribute(mfe2_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            cfg = true;
-        }
-        mfe2_kernel<64><<<grid, FOLDS_PER_CTA * 32, smem, stream>>>(L, d_tab, g_dtab2);
+        if (tw == 1) launch_mfe2_t<64, 1>(L, d_tab, grid, stream);
+        else launch_mfe2_t<64, 2>(L, d_tab, grid, stream);
     } else {
-        const size_t smem = ((sizeof(Tab2) + 15) & ~15) + FOLDS_PER_CTA * ((sizeof(FoldSmem<128>) + 15) & ~15);
-        static bool cfg = false;
-        if (!cfg) {
-            cudaFuncSetAttribute(mfe2_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            cfg = true;
-        }
-        mfe2_kernel<128><<<grid, FOLDS_PER_CTA * 32, smem, stream>>>(L, d_tab, g_dtab2);
+        if (tw == 1) launch_mfe2_t<128, 1>(L, d_tab, grid, stream);
+        else launch_mfe2_t<128, 2>(L, d_tab, grid, stream);
     }
     if (n_launches) (*n_launches)++;
 }
