@@ -21,9 +21,17 @@ struct PfSmall {
     double d5[40], d3[40];
     double bulge[31], il[31], ninio[31];
     double expMLbase, expMLclosing, expMLintern, expTermAU, kT, pf_scale;
-    short cand[NCAND];  // u1 | u2 << 5
+    short cand[NCAND];  // u1 | u2 << 5 | class << 10
     int ncand_upto[32];
+    double fac[NCAND];  // separable classes: size factor * scale[u+2] of candidate ci (0 for table-driven shapes)
+    int rowoff[32];     // ring row of the inner (inside) / outer (outside) diagonal for total loop size u
 };
+
+// Interior loops whose Boltzmann factor separates into (size term) x (outer mismatch) x (inner mismatch):
+// the inner-pair part is folded into 34-row ring copies of qb (inside) / P (outside) when that cell is final,
+// so a candidate costs one load and one FMA instead of a full loop-energy evaluation.
+enum { PCLS_GENERIC = 0, PCLS_1N = 1, PCLS_BULGE = 2, PCLS_TABLE = 3 };
+constexpr int PRING = 34;
 
 struct PfCtx {
     const PfTables *T;
@@ -157,7 +165,8 @@ __global__ void __launch_bounds__(NT) pf_kernel(PfLaunch L, const MfeTables *__r
     double *Pm = g;            g += ntri;
     double *PMm = g;           g += ntri;
     double *X1 = g;            g += ntri;
-    double *X2 = g;
+    double *X2 = g;            g += ntri;
+    double *ring = g;          // [3][PRING][W]: generic | 1xn | bulge class copies
 
     {
         auto cp = [&](double *dst, const double *s, int n) {
@@ -184,7 +193,14 @@ __global__ void __launch_bounds__(NT) pf_kernel(PfLaunch L, const MfeTables *__r
             st->pf_scale = T->pf_scale;
             int n = 0;
             for (int u = 0; u <= MAXLOOP; u++) {
-                for (int u1 = 0; u1 <= u; u1++) st->cand[n++] = (short)(u1 | ((u - u1) << 5));
+                for (int u1 = 0; u1 <= u; u1++) {
+                    const int u2 = u - u1, ul = max(u1, u2), us = min(u1, u2);
+                    int cls = PCLS_TABLE;
+                    if (us == 0 && ul >= 2) cls = PCLS_BULGE;
+                    else if (us == 1 && ul >= 3) cls = PCLS_1N;
+                    else if (us >= 2 && !(us == 2 && ul <= 3)) cls = PCLS_GENERIC;
+                    st->cand[n++] = (short)(u1 | (u2 << 5) | (cls << 10));
+                }
                 st->ncand_upto[u] = n;
             }
             scale[0] = 1.;
@@ -194,6 +210,15 @@ __global__ void __launch_bounds__(NT) pf_kernel(PfLaunch L, const MfeTables *__r
                 eMLb[k] = eMLb[k - 1] * T->expMLbase / T->pf_scale;
             }
         }
+    }
+    __syncthreads();
+    for (int ci = tid; ci < NCAND; ci += NT) {
+        const int cd = st->cand[ci], u1 = cd & 31, u2 = (cd >> 5) & 31, cls = cd >> 10;
+        const int ul = max(u1, u2), us = min(u1, u2);
+        double f = 0.;
+        if (cls == PCLS_BULGE) f = st->bulge[ul];
+        else if (cls == PCLS_1N || cls == PCLS_GENERIC) f = st->il[ul + us] * st->ninio[ul - us];
+        st->fac[ci] = f * scale[u1 + u2 + 2];
     }
     __syncthreads();
 
@@ -257,13 +282,18 @@ __global__ void __launch_bounds__(NT) pf_kernel(PfLaunch L, const MfeTables *__r
             const int ncells = W - d;
             const int tri_d = tri_off(d, W);
             if (tid == 0) misc[0] = 0;
+            if (tid < 32) st->rowoff[tid] = ((d - 2 - tid + 2 * PRING) % PRING) * W;
             __syncthreads();
+            const int ring_row = (d % PRING) * W;
             for (int i = tid; i < ncells; i += NT) {
                 int t = allowed_type(c.h, i, i + d);
                 ctype[i] = (uint8_t)t;
-                if (!t)
+                if (!t) {
                     qb[tri_d + i] = 0.;
-                else
+                    ring[ring_row + i] = 0.;
+                    ring[PRING * W + ring_row + i] = 0.;
+                    ring[2 * PRING * W + ring_row + i] = 0.;
+                } else
                     list[atomicAdd(&misc[0], 1)] = (int16_t)i;
             }
             __syncthreads();
@@ -285,10 +315,18 @@ __global__ void __launch_bounds__(NT) pf_kernel(PfLaunch L, const MfeTables *__r
                         type = ctype[i];
                         const int gl = item & (G - 1);
                         const int si1 = S[i + 1], sj1 = S[j - 1];
+                        const int mi = mm_idx(type, si1, sj1);
+                        const double oG = st->mmI[mi], o1 = st->mm1n[mi], oB = type > 2 ? st->expTermAU : 1.;
                         for (int ci = gl; ci < ncand; ci += G) {
                             const int cd = st->cand[ci];
-                            const int u1 = cd & 31, u2 = cd >> 5;
+                            const int u1 = cd & 31, u2 = (cd >> 5) & 31, cls = cd >> 10;
                             const int p = i + 1 + u1, q = j - 1 - u2;
+                            if (cls != PCLS_TABLE) {
+                                const double v = ring[cls * PRING * W + st->rowoff[u1 + u2] + p];
+                                const double o = cls == PCLS_GENERIC ? oG : (cls == PCLS_1N ? o1 : oB);
+                                acc += v * st->fac[ci] * o;
+                                continue;
+                            }
                             const double qpq = qb[TRI(q - p, p)];
                             if (qpq != 0.) {
                                 const int t2 = rtype_of(pair_type(S[p], S[q]));
@@ -304,8 +342,21 @@ __global__ void __launch_bounds__(NT) pf_kernel(PfLaunch L, const MfeTables *__r
                         acc += ml * closing * x_mlstem(*st, rtype_of(type), sj1, si1) * scale[2];
                     }
                     acc = group_sum(acc, G);
-                    if (active && (item & (G - 1)) == 0)
-                        qb[tri_d + i] = acc + x_hairpin(c, i, j, type) * scale[d + 1];
+                    if (active && (item & (G - 1)) == 0) {
+                        const double qv = acc + x_hairpin(c, i, j, type) * scale[d + 1];
+                        qb[tri_d + i] = qv;
+                        double vG = 0., v1 = 0., vB = 0.;
+                        if (i > 0 && j < W - 1) {  // (i,j) as the inner pair of an enclosing loop
+                            const int t2 = rtype_of(type);
+                            const int m2 = mm_idx(t2, S[j + 1], S[i - 1]);
+                            vG = qv * st->mmI[m2];
+                            v1 = qv * st->mm1n[m2];
+                            vB = t2 > 2 ? qv * st->expTermAU : qv;
+                        }
+                        ring[ring_row + i] = vG;
+                        ring[PRING * W + ring_row + i] = v1;
+                        ring[2 * PRING * W + ring_row + i] = vB;
+                    }
                 }
             }
             __syncthreads();
@@ -385,6 +436,9 @@ __global__ void __launch_bounds__(NT) pf_kernel(PfLaunch L, const MfeTables *__r
             const int G = min(32, floor_pow2(NT / ncells));
             const int gsh = 31 - __clz(G);
             const int items = ncells << gsh;
+            if (tid < 32) st->rowoff[tid] = ((d + 2 + tid) % PRING) * W;
+            __syncthreads();
+            const int ring_row = (d % PRING) * W;
             // P[k,l]: exterior + enclosing interior loops + enclosing multiloops
             for (int base = tid - lane; base < items; base += NT) {
                 const int item = base + lane;
@@ -404,11 +458,19 @@ __global__ void __launch_bounds__(NT) pf_kernel(PfLaunch L, const MfeTables *__r
                             const int sp1 = S[k - 1], sq1 = S[l + 1];
                             const int umax = min(MAXLOOP, W - 3 - d);
                             const int ncand = umax >= 0 ? st->ncand_upto[umax] : 0;
+                            const int m2 = mm_idx(t2, sq1, sp1);
+                            const double iG = st->mmI[m2], i1 = st->mm1n[m2], iB = t2 > 2 ? st->expTermAU : 1.;
                             for (int ci = gl; ci < ncand; ci += G) {
                                 const int cd = st->cand[ci];
-                                const int u1 = cd & 31, u2 = cd >> 5;
+                                const int u1 = cd & 31, u2 = (cd >> 5) & 31, cls = cd >> 10;
                                 const int i = k - 1 - u1, j = l + 1 + u2;
                                 if (i < 0 || j > W - 1) continue;
+                                if (cls != PCLS_TABLE) {
+                                    const double v = ring[cls * PRING * W + st->rowoff[u1 + u2] + i];
+                                    const double o = cls == PCLS_GENERIC ? iG : (cls == PCLS_1N ? i1 : iB);
+                                    acc += v * st->fac[ci] * o;
+                                    continue;
+                                }
                                 const double pij = Pm[TRI(j - i, i)];
                                 if (pij > 0.) {
                                     const int tij = pair_type(S[i], S[j]);
@@ -435,6 +497,18 @@ __global__ void __launch_bounds__(NT) pf_kernel(PfLaunch L, const MfeTables *__r
                 acc = group_sum(acc, G);
                 if (active && (item & (G - 1)) == 0) {
                     Pm[tri_d + k] = acc;
+                    {   // (k,l) as the OUTER pair of loops enclosing pairs on shorter diagonals
+                        double vG = 0., v1 = 0., vB = 0.;
+                        if (acc != 0.) {
+                            const int mo = mm_idx(tkl, S[k + 1], S[l - 1]);
+                            vG = acc * st->mmI[mo];
+                            v1 = acc * st->mm1n[mo];
+                            vB = tkl > 2 ? acc * st->expTermAU : acc;
+                        }
+                        ring[ring_row + k] = vG;
+                        ring[PRING * W + ring_row + k] = v1;
+                        ring[2 * PRING * W + ring_row + k] = vB;
+                    }
                     double pm = 0.;
                     if (qkl != 0. && k + 1 < W && l >= 1)
                         pm = acc * closing * x_mlstem(*st, rtype_of(tkl), S[l - 1], S[k + 1]);
@@ -501,7 +575,7 @@ size_t pf_smem_bytes(int W) {
 
 }  // namespace
 
-size_t pf_scratch_doubles_per_cta(int W) { return 7 * ((size_t)W * (W + 1) / 2); }
+size_t pf_scratch_doubles_per_cta(int W) { return 7 * ((size_t)W * (W + 1) / 2) + 3 * (size_t)PRING * W; }
 
 int pf_grid_size(int W, int n_sm, int n_fold) {
     long long g = (long long)n_sm * 4;
