@@ -159,13 +159,14 @@ def workload_config(name, n_gpus):
     return {"workload": "%s: %d-nt synthetic record per GPU, window %d, step %d, %d %s shuffles, PF/ED on, "
                         "ScanFold-Fold accumulation" % (name, L, W, step, r, stype),
             "record_nt": L * n_gpus, "window": W, "step": step, "shuffles": r, "shuffle_type": stype,
-            "seed": seed, "l2": "flushed between steps (256 MiB write)", "parallelism": "windows sharded by range"}
+            "seed": seed, "l2": "flushed between steps (256 MiB write)",
+            "parallelism": "windows sharded by range over %d GPU(s); accumulator halo over NCCL send/recv" % n_gpus}
 
 
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from scanfold_b200 import engine, pipeline, scan, workcount
+    from scanfold_b200 import engine, foldstep, multigpu, pipeline, scan, workcount
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -223,16 +224,25 @@ def run_ours(args):
     def e2e_step():
         t = scan.scan_record(seq, W, step, r, shuffle_type=stype, seed=42, first_window=w0, n_windows=nwin,
                              final_window=final)
-        ptable = pipeline.partner_table_gpu(L, t)
-        return t, ptable
+        z100, mfe100, ed100 = pipeline.fold_inputs(t)
+        acc = engine.Accumulator(L, W, step, w0, t.pair_tbl, z100, mfe100, ed100)
+        try:        # halo rows go to the right neighbour over NCCL; rank 0 gathers the compact partner lists
+            own = multigpu.exchange_halo(acc, W, step, rank, world, dist if world > 1 else None)
+            ptable = foldstep.table_from_compact(*acc.compact(0, own))
+            launches_e2e[0] = acc.n_launches
+        finally:
+            acc.close()
+        whole = multigpu.gather_tables(ptable, rank, world, dist if world > 1 else None)
+        return t, ptable, whole
 
+    launches_e2e = [0]
     e2e_steps = args.e2e_steps if args.e2e_steps else args.steps
     e2e_step()
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         flush.zero_()
-        t, acc = e2e_step()
+        t, acc, whole = e2e_step()
     barrier()
     ms_e2e = (time.perf_counter() - t0) * 1e3
     n_slots = nwin + (1 if final else 0)
@@ -272,7 +282,7 @@ def run_ours(args):
             "folds_per_s": value * folds_per_window, "dp_cells_per_s": value * folds_per_window * cells,
             "e2e": {"value": e2e, "unit": "windows/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps},
-            "gpu_launches": int(total_launches),
+            "gpu_launches": int(total_launches), "gpu_launches_e2e_per_step": int(t.n_launches + launches_e2e[0]),
             "roofline": {"bound": "int_alu", "kernel": "mfe_fold_kernel", "achieved": achieved / 1e9,
                          "peak": peak_addmin / 1e9, "unit": "G add-min/s", "frac": achieved / peak_addmin,
                          "peak_source": "sfb_microbench VIADDMNMX rate measured in this run (MEASURED_PEAKS.json "

@@ -140,8 +140,13 @@ def make_output_folder(cwd, out_name, read_name):
     return folder
 
 
-def run_record(args, record_name, raw_seq, original_directory):
+def run_record(args, record_name, raw_seq, original_directory, dist=None):
+    """One FASTA record.  With a torch.distributed process group (torchrun, one process per GPU) the windows are
+    sharded by range over the ranks; rank 0 owns the output folder and writes every file."""
+    from . import engine, multigpu
     t0 = time.time()
+    rank = dist.get_rank() if dist is not None else 0
+    world = dist.get_world_size() if dist is not None else 1
     seq = raw_seq.replace("T", "U").replace("t", "u")      # Seq.transcribe (ScanFold.py:282)
     if "-" in seq:
         raise ValueError("Gaps found in sequence. Please submit a complete sequence to ScanFold")
@@ -149,41 +154,58 @@ def run_record(args, record_name, raw_seq, original_directory):
     if "|" in read_name:
         read_name = re.split(r"\|", read_name)[0]
     cwd = os.getcwd()
-    folder = make_output_folder(cwd, args.out_name, read_name)
-    os.chdir(os.path.join(cwd, folder))
+    folder = None
+    if rank == 0:
+        folder = make_output_folder(cwd, args.out_name, read_name)
+        os.chdir(os.path.join(cwd, folder))
     try:
         W, step, r = int(args.w), int(args.s), int(args.r)
         names = pipeline.RunNames(read_name, record_name, W, step, r, str(args.type), name=args.name, out6=args.out6,
                                   final_partners_wig=args.final_partners_wig, dbn1=args.dbn_file_path1,
                                   dbn2=args.dbn_file_path2, dbn3=args.dbn_file_path3, dbn4=args.dbn_file_path4)
-        print("Output name=" + names.outname)
+        if rank == 0:
+            print("Output name=" + names.outname)
         if len(seq) < W:
-            print(record_name + " sequence is less than window size. Moving on to next entry.")
+            if rank == 0:
+                print(record_name + " sequence is less than window size. Moving on to next entry.")
             return
         hc = None
         if args.constraints is not None:
-            print("Considering constraint input")
-            hc = open(args.constraints).readlines()[2].rstrip("\n")   # relative to the output folder, as in the reference (Q8)
+            # opened after the chdir into the output folder in the reference (Appendix B Q8): absolute paths only
+            path = args.constraints if os.path.isabs(args.constraints) or rank != 0 else os.path.join(os.getcwd(), args.constraints)
+            hc = open(path).readlines()[2].rstrip("\n")
         react = None
         if args.react is not None:
-            print("Considering SHAPE reactivity input")
             react = read_reactivities(os.path.join(original_directory, args.react))
             if args.shapeZ and not args.shapeD:
                 raise TypeError("sc_add_SHAPE_zarringhalam() is called with one argument by the reference "
                                 "(ScanFold.py:536) and fails there too; use --shapeD")
+        total = scan.n_windows_of(len(seq), W, step)
+        w0, w1 = multigpu.shard_windows(total, world, rank)
+        last = w1 == total
         parity = None
         if args.parity_shuffles:
-            parity = np.load(args.parity_shuffles if os.path.isabs(args.parity_shuffles)
-                             else os.path.join(original_directory, args.parity_shuffles))["shuffles"]
-        print("Scanning input sequence:", read_name)
-        table = scan.scan_record(seq.upper(), W, step, r, shuffle_type=str(args.type), seed=args.seed,
+            allsh = np.load(args.parity_shuffles if os.path.isabs(args.parity_shuffles)
+                            else os.path.join(original_directory, args.parity_shuffles))["shuffles"]
+            parity = allsh[w0:w1 + (1 if last else 0)]
+        if rank == 0:
+            print("Scanning input sequence:", read_name)
+        shard = scan.scan_record(seq.upper(), W, step, r, shuffle_type=str(args.type), seed=args.seed,
                                  parity_shuffles=parity, temperature=float(args.t), max_span=args.span or 0, hc=hc,
-                                 react=react, shape_m=args.m, shape_b=args.b)
-        table_seq = seq                                            # the .out Sequence column keeps the input case (Q11)
-        minz = pipeline.write_scan_outputs(table_seq, table, names, int(args.t), step)
+                                 react=react, shape_m=args.m, shape_b=args.b, first_window=w0, n_windows=w1 - w0,
+                                 final_window=last)
+        z100, mfe100, ed100 = pipeline.fold_inputs(shard)
+        acc = engine.Accumulator(len(seq), W, step, w0, shard.pair_tbl, z100, mfe100, ed100)
+        try:
+            ptable = multigpu.partner_table_distributed(acc, W, step, rank, world, dist)
+        finally:
+            acc.close()
+        table = multigpu.gather_window_tables(shard, rank, world, dist)
+        if rank != 0:
+            return
+        minz = pipeline.write_scan_outputs(seq, table, names, int(args.t), step)   # Sequence column keeps input case (Q11)
         print("Elapsed time: %ss" % round(time.time() - t0, 2))
         print("Determining best base pairs...")
-        ptable = pipeline.partner_table_gpu(len(seq), table)
         pipeline.write_fold_outputs(seq, ptable, names, minz, step)
         print("Total runtime: %ss" % round(time.time() - t0, 2))
         print("ScanFold-Fold analysis complete! Output found in folder named: " + folder)
@@ -202,11 +224,22 @@ def main(argv=None):
     if str(args.type) not in ("mono", "di"):
         raise SystemExit('Shuffle type not properly designated; please input "di" or "mono"')
     from . import engine
-    engine.init(args.gpu, args.params)
+    dist = None
+    device = args.gpu
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:       # torchrun: one process per GPU, windows sharded by range
+        import torch
+        import torch.distributed as dist
+        device = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(device)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", device))
+    engine.init(device, args.params)
     original_directory = os.getcwd()
-    print(original_directory)
+    if dist is None or dist.get_rank() == 0:
+        print(original_directory)
     for record_name, raw_seq in read_fasta(args.filename):
-        run_record(args, record_name, raw_seq, original_directory)
+        run_record(args, record_name, raw_seq, original_directory, dist)
+    if dist is not None:
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

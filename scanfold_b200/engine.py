@@ -339,6 +339,21 @@ class Accumulator:
     def merge_rows(self, row0, n_rows, d_count, d_first, d_sums):
         _check(self._lib.sfb_accumulate_merge(self._h, row0, n_rows, d_count, d_first, d_sums))
 
+    # ---- torch views of the halo rows (multi-GPU exchange over NCCL, scanfold_b200.multigpu)
+    def empty_tensors(self, n_rows):
+        import torch
+        n = n_rows * self.ncol
+        return (torch.empty(n, dtype=torch.int32, device="cuda"), torch.empty(n, dtype=torch.int32, device="cuda"),
+                torch.empty(6 * n, dtype=torch.int64, device="cuda"))
+
+    def export_tensors(self, row0, n_rows):
+        t = self.empty_tensors(n_rows)
+        self.export_rows(row0, n_rows, t[0].data_ptr(), t[1].data_ptr(), t[2].data_ptr())
+        return t
+
+    def merge_tensors(self, row0, n_rows, count, first, sums):
+        self.merge_rows(row0, n_rows, count.data_ptr(), first.data_ptr(), sums.data_ptr())
+
     def compact(self, row0=0, n_rows=None):
         """-> (nparts [n_rows], partner, count, first_seen [M], sums [6, M]); entries in column order per nucleotide"""
         if n_rows is None:

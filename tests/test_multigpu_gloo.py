@@ -1,0 +1,57 @@
+"""Multi-rank host logic on CPU: two gloo ranks shard the windows of one golden case, exchange the accumulator
+halo, and rank 0 must end up with exactly the single-process partner table (and byte-identical output files)."""
+import json
+import os
+import subprocess
+import sys
+import textwrap
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+WORKER = textwrap.dedent("""
+    import json, os, sys
+    import numpy as np
+    import torch.distributed as dist
+    sys.path.insert(0, %(root)r); sys.path.insert(0, os.path.join(%(root)r, "tests"))
+    from util import NumpyAccumulator, accumulate_numpy
+    from test_host_pipeline import load_case, replay_table
+    from scanfold_b200 import foldstep, multigpu, pipeline
+    dist.init_process_group("gloo")
+    rank, world = dist.get_rank(), dist.get_world_size()
+    case = load_case(%(case)r)
+    table = replay_table(case)
+    z100, mfe100, ed100 = pipeline.fold_inputs(table)
+    W, step, n = case["W"], case["step"], case["n_windows"]
+    w0, w1 = multigpu.shard_windows(n, world, rank)
+    acc = NumpyAccumulator(case["L"], W, step, w0, table.pair_tbl[w0:w1], z100[w0:w1], mfe100[w0:w1], ed100[w0:w1])
+    merged = multigpu.partner_table_distributed(acc, W, step, rank, world, dist)
+    if rank == 0:
+        whole = foldstep.table_from_compact(*accumulate_numpy(case["L"], W, step, 0, table.pair_tbl, z100, mfe100, ed100))
+        for name in ("nt_ptr", "partner", "count", "first_seen", "sums"):
+            assert np.array_equal(getattr(merged, name), getattr(whole, name)), name
+        print("MERGE_OK", len(merged.partner))
+    dist.destroy_process_group()
+""")
+
+
+@pytest.mark.parametrize("case,world", [("mono_w40", 2), ("step7_w40", 2), ("mono_w60_gc", 3)])
+def test_two_rank_halo_exchange_equals_single_process(case, world, tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER % {"root": ROOT, "case": case})
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+           "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 400), str(script)]
+    p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
+    assert p.returncode == 0, p.stdout[-3000:]
+    assert "MERGE_OK" in p.stdout, p.stdout[-3000:]
+
+
+def test_shard_windows_partition():
+    from scanfold_b200 import multigpu
+    for total in (1, 7, 100, 29784):
+        for world in (1, 2, 3, 8):
+            edges = [multigpu.shard_windows(total, world, r) for r in range(world)]
+            assert edges[0][0] == 0 and edges[-1][1] == total
+            assert all(a[1] == b[0] for a, b in zip(edges, edges[1:]))

@@ -52,3 +52,54 @@ def accumulate_numpy(L, W, step, first_window, pair_tbl, z100, mfe_dcal, ed100):
     nparts = np.bincount(rows, minlength=n_nt)
     partner = nt0 + rows + 1 + cols - (W - 1)
     return nparts, partner, count[rows, cols], first[rows, cols], sums[:, rows, cols]
+
+
+class NumpyAccumulator:
+    """CPU stand-in for engine.Accumulator with the same halo / compact interface (gloo tests of multigpu.py)"""
+
+    def __init__(self, L, W, step, first_window, pair_tbl, z100, mfe_dcal, ed100):
+        from scanfold_b200.foldstep import split_exact
+        n = len(pair_tbl)
+        self.W, self.step, self.nt0, self.n_nt, self.ncol = W, step, first_window * step, (n - 1) * step + W, 2 * W - 1
+        self.count = np.zeros((self.n_nt, self.ncol), dtype=np.int32)
+        self.first = np.full((self.n_nt, self.ncol), 0x7F7F7F7F, dtype=np.int32)
+        self.sums = np.zeros((6, self.n_nt, self.ncol), dtype=np.int64)
+        parts = [split_exact(z100), split_exact(mfe_dcal), split_exact(ed100)]
+        for s in range(n):
+            w = first_window + s
+            for pos in range(W):
+                row = s * step + pos
+                p = int(pair_tbl[s][pos])
+                col = ((p - 1) - pos if p else 0) + W - 1
+                self.count[row, col] += 1
+                self.first[row, col] = min(self.first[row, col], w)
+                for q in range(3):
+                    self.sums[2 * q, row, col] += parts[q][0][s]
+                    self.sums[2 * q + 1, row, col] += parts[q][1][s]
+
+    def empty_tensors(self, n_rows):
+        import torch
+        n = n_rows * self.ncol
+        return (torch.empty(n, dtype=torch.int32), torch.empty(n, dtype=torch.int32), torch.empty(6 * n, dtype=torch.int64))
+
+    def export_tensors(self, row0, n_rows):
+        import torch
+        sl = slice(row0, row0 + n_rows)
+        return (torch.from_numpy(self.count[sl].reshape(-1).copy()), torch.from_numpy(self.first[sl].reshape(-1).copy()),
+                torch.from_numpy(self.sums[:, sl].reshape(-1).copy()))
+
+    def merge_tensors(self, row0, n_rows, count, first, sums):
+        sl = slice(row0, row0 + n_rows)
+        self.count[sl] += count.numpy().reshape(n_rows, self.ncol)
+        self.first[sl] = np.minimum(self.first[sl], first.numpy().reshape(n_rows, self.ncol))
+        self.sums[:, sl] += sums.numpy().reshape(6, n_rows, self.ncol)
+
+    def compact(self, row0=0, n_rows=None):
+        if n_rows is None:
+            n_rows = self.n_nt - row0
+        cnt = self.count[row0:row0 + n_rows]
+        rows, cols = np.nonzero(cnt)
+        nparts = np.bincount(rows, minlength=n_rows)
+        partner = self.nt0 + row0 + rows + 1 + cols - (self.W - 1)
+        return (nparts, partner, cnt[rows, cols], self.first[row0:row0 + n_rows][rows, cols],
+                self.sums[:, row0:row0 + n_rows][:, rows, cols])
