@@ -1,4 +1,4 @@
-// MFE fold kernel, second generation: ONE WARP PER FOLD, energy only, windows up to 128 nt.
+// MFE fold kernel, second generation: a team of one or two warps per fold, energy only, windows up to 120 nt.
 //
 // Replaces the r background folds per window of energies()/rna_folder (ScanFoldFunctions.py:774-789,805-814)
 // -- more than 99 % of all fold arithmetic of a scan.  The first-generation kernel (mfe.cu: one 256-thread CTA
@@ -50,11 +50,15 @@ struct alignas(16) Tab2 {
 __constant__ int c_sizeG[31][32];  // [u][u1]: internal_loop[u] + min(MAX_NINIO, |u1-u2|*ninio)
 __constant__ int c_size1[32];      // 1xn loops of total size u
 __constant__ int c_sizeB[32];      // bulge[u]
+__constant__ int c_cap[32];        // internal_loop[u] + MAX_NINIO: every generic loop with |u1-u2| >= NEAR
 Tab2 *g_dtab2 = nullptr;
+bool g_mfe2_ok = false;            // the table set has the asymmetry cap structure the kernel assumes
+constexpr int NEAR = 5;            // |u1-u2| >= NEAR  =>  the ninio term is capped (5*ninio >= MAX_NINIO, checked on upload)
+constexpr unsigned INF16X2 = (unsigned)INF16 * 65537u;
 
 template <int P>
 struct FoldSmem {
-    short roll[3 * ROLL * P];  // RG | R1 | RB  (also the F5 staging area for C)
+    short roll[4 * ROLL * P];  // RG0 | RG1 (RG shifted by one element) | R1 | RB  (also the F5 staging area for C)
     short fml[(P / 2 + 1) * P];
     short rc[RCR * P];
     short dml[4 * P];
@@ -68,44 +72,77 @@ __host__ __device__ __forceinline__ int tri4(int d, int W) {  // first cell of d
     return (d - 4) * W - ((d - 1) * d / 2 - 6);
 }
 
-// one u-block: candidates (u1, U-u1) of the separable classes; rp = &RG[slot(d-2-U)][i+1]
+// One u-block: candidates (u1, U-u1) of the separable classes of a cell whose inner diagonal is d-2-U.
+//   rpG  the lane's view of the generic-class row: rpG[u1] is candidate u1 and &rpG[u1] is 4-byte aligned for
+//        even u1 (lanes with odd i+1 read the copy that is shifted by one element), so two candidates come in
+//        with one LDS.32;
+//   rp1  &R1[row][i+1]; the bulge class sits ROLL*P further.
+// Generic loops with |u1-u2| >= NEAR all carry the same size term c_cap[U], so they only need a running
+// minimum (VIMNMX.S16x2 on packed pairs) and one add at the end of the block; the few near-symmetric ones,
+// the two 1xn and the two bulge candidates take one VIADDMNMX each.
 template <int U, int P>
-__device__ __forceinline__ void ublock(const short *rp, int &g0, int &g1, int &g2, int &g3, int &a1, int &aB) {
-    constexpr int O1 = ROLL * P, OB = 2 * ROLL * P;
+__device__ __forceinline__ void ublock(const short *rpG, const short *rp1, int &g0, int &g1, int &a1, int &aB) {
+    constexpr int OB = ROLL * P;
     if constexpr (U >= 2) {
-        aB = __viaddmin_s32(rp[OB], c_sizeB[U], aB);
-        aB = __viaddmin_s32(rp[OB + U], c_sizeB[U], aB);
+        aB = __viaddmin_s32(rp1[OB], c_sizeB[U], aB);
+        aB = __viaddmin_s32(rp1[OB + U], c_sizeB[U], aB);
     }
     if constexpr (U >= 4) {
-        a1 = __viaddmin_s32(rp[O1 + 1], c_size1[U], a1);
-        a1 = __viaddmin_s32(rp[O1 + U - 1], c_size1[U], a1);
+        a1 = __viaddmin_s32(rp1[1], c_size1[U], a1);
+        a1 = __viaddmin_s32(rp1[U - 1], c_size1[U], a1);
     }
     if constexpr (U >= 6) {
+        unsigned f0 = INF16X2, f1 = INF16X2;
+        int fs = INF16;
+        bool anyfar = false;
 #pragma unroll
-        for (int u1 = 2; u1 <= U - 2; u1++) {
-            const int v = rp[u1];
-            if ((u1 & 3) == 0) g0 = __viaddmin_s32(v, c_sizeG[U][u1], g0);
-            if ((u1 & 3) == 1) g1 = __viaddmin_s32(v, c_sizeG[U][u1], g1);
-            if ((u1 & 3) == 2) g2 = __viaddmin_s32(v, c_sizeG[U][u1], g2);
-            if ((u1 & 3) == 3) g3 = __viaddmin_s32(v, c_sizeG[U][u1], g3);
+        for (int k = 2; k <= U - 2; k += 2) {
+            const int da = 2 * k - U, db = 2 * (k + 1) - U;
+            const bool hasb = k + 1 <= U - 2;
+            const bool fara = da >= NEAR || da <= -NEAR, farb = hasb && (db >= NEAR || db <= -NEAR);
+            if (fara && farb) {
+                const unsigned w = *reinterpret_cast<const unsigned *>(rpG + k);
+                if ((k & 2) == 0) f0 = __vmins2(f0, w); else f1 = __vmins2(f1, w);
+                anyfar = true;
+            } else {
+                if (fara) {
+                    fs = min(fs, (int)rpG[k]);
+                    anyfar = true;
+                } else {
+                    g0 = __viaddmin_s32(rpG[k], c_sizeG[U][k], g0);
+                }
+                if (hasb) {
+                    if (farb) {
+                        fs = min(fs, (int)rpG[k + 1]);
+                        anyfar = true;
+                    } else {
+                        g1 = __viaddmin_s32(rpG[k + 1], c_sizeG[U][k + 1], g1);
+                    }
+                }
+            }
+        }
+        if (anyfar) {
+            const unsigned f = __vmins2(f0, f1);
+            const int lo = (short)(f & 0xffffu), hi = (int)f >> 16;
+            g0 = __viaddmin_s32(min(min(lo, hi), fs), c_cap[U], g0);
         }
     }
 }
 
 template <int U, int P>
 struct UBlocks {
-    __device__ __forceinline__ static void run(const short *rollbase, int lane_off, int &slot, int umax, int &g0, int &g1,
-                                               int &g2, int &g3, int &a1, int &aB) {
-        UBlocks<U - 1, P>::run(rollbase, lane_off, slot, umax, g0, g1, g2, g3, a1, aB);
+    __device__ __forceinline__ static void run(const short *roll, int goff, int loff, int &slot, int umax, int &g0,
+                                               int &g1, int &a1, int &aB) {
+        UBlocks<U - 1, P>::run(roll, goff, loff, slot, umax, g0, g1, a1, aB);
         if (U <= umax) {
-            if constexpr (U >= 2) ublock<U, P>(rollbase + slot * P + lane_off, g0, g1, g2, g3, a1, aB);
+            if constexpr (U >= 2) ublock<U, P>(roll + slot * P + goff, roll + slot * P + loff, g0, g1, a1, aB);
             slot = slot == 0 ? ROLL - 1 : slot - 1;
         }
     }
 };
 template <int P>
 struct UBlocks<-1, P> {
-    __device__ __forceinline__ static void run(const short *, int, int &, int, int &, int &, int &, int &, int &, int &) {}
+    __device__ __forceinline__ static void run(const short *, int, int, int &, int, int &, int &, int &, int &) {}
 };
 
 __device__ int hairpin_special(const MfeTables *T, const Tab2 &tb, const unsigned char *sx, int i, int j, int type) {
@@ -203,8 +240,9 @@ mfe2_kernel(MfeLaunch L, const MfeTables *__restrict__ T, const Tab2 *__restrict
                         if (!t) {
                             sm.rc[(d & (RCR - 1)) * P + i] = INF16;
                             RG[slot * P + i] = INF16;
-                            RG[(ROLL + slot) * P + i] = INF16;
+                            RG[(ROLL + slot) * P + i + 1] = INF16;
                             RG[(2 * ROLL + slot) * P + i] = INF16;
+                            RG[(3 * ROLL + slot) * P + i] = INF16;
                             gC[t4 + i] = INF16;
                         }
                     }
@@ -225,7 +263,7 @@ mfe2_kernel(MfeLaunch L, const MfeTables *__restrict__ T, const Tab2 *__restrict
                 const int type = tb.ptype[sx[i + 1] * 6 + sx[j + 1]];
                 const int si1 = sx[i + 2], sj1 = sx[j];
                 const int mi = (type * 5 + si1) * 5 + sj1;
-                int g0 = INF16, g1 = INF16, g2 = INF16, g3 = INF16, a1 = INF16, aB = INF16, aT = INF16;
+                int g0 = INF16, g1 = INF16, a1 = INF16, aB = INF16, aT = INF16;
                 // the nine table-driven shapes
                 {
                     auto inner = [&](int u1, int u2, int &c, int &t2, int &sp1, int &sq1) {
@@ -259,9 +297,11 @@ mfe2_kernel(MfeLaunch L, const MfeTables *__restrict__ T, const Tab2 *__restrict
                 // separable classes
                 {
                     int slot = (d - 2) % ROLL;
-                    UBlocks<MAXLOOP, P>::run(RG, i + 1, slot, umax, g0, g1, g2, g3, a1, aB);
+                    const int par = (i + 1) & 1;
+                    UBlocks<MAXLOOP, P>::run(RG, (par ? ROLL * P : 0) + i + 1 + par, 2 * ROLL * P + i + 1, slot, umax, g0, g1,
+                                             a1, aB);
                 }
-                int e = min(min(g0, g1), min(g2, g3)) + tb.mmI[mi];
+                int e = min(g0, g1) + tb.mmI[mi];
                 e = min(e, a1 + tb.mm1n[mi]);
                 e = min(e, aB + tb.tAU[type]);
                 e = min(e, aT);
@@ -286,8 +326,9 @@ mfe2_kernel(MfeLaunch L, const MfeTables *__restrict__ T, const Tab2 *__restrict
                         vb = e + tb.tAU[t2];
                     }
                     RG[slot * P + i] = (short)vg;
-                    RG[(ROLL + slot) * P + i] = (short)v1;
-                    RG[(2 * ROLL + slot) * P + i] = (short)vb;
+                    RG[(ROLL + slot) * P + i + 1] = (short)vg;
+                    RG[(2 * ROLL + slot) * P + i] = (short)v1;
+                    RG[(3 * ROLL + slot) * P + i] = (short)vb;
                     gC[tri4(d, W) + i] = (short)(e < FIN16 ? e + tb.ext[type * 36 + sx[i] * 6 + sx[j + 2]] : INF16);
                 }
             }
@@ -394,7 +435,7 @@ mfe2_kernel(MfeLaunch L, const MfeTables *__restrict__ T, const Tab2 *__restrict
 
 size_t mfe2_scratch_shorts_per_warp(int W) { return ((size_t)tri4(W, W) + 63) & ~(size_t)63; }
 
-bool mfe2_supports(int W) { return W >= 16 && W <= 128; }
+bool mfe2_supports(int W) { return g_mfe2_ok && W >= 16 && W <= 120; }
 
 int mfe2_grid_size(int n_sm, int n_fold) {
     const int need = (n_fold + FOLDS_PER_CTA - 1) / FOLDS_PER_CTA;
@@ -439,8 +480,10 @@ void mfe2_upload_tables(const MfeTables &M) {
     h.bulge1 = (short)M.bulge[1];
     h.il5_ninio = (short)(M.internal_loop[5] + M.ninio);
     h.MLbase = (short)M.MLbase;
-    static int sG[31][32], s1[32], sB[32];
+    static int sG[31][32], s1[32], sB[32], sC[32];
+    g_mfe2_ok = M.ninio >= 0 && NEAR * M.ninio >= M.max_ninio;
     for (int u = 0; u <= MAXLOOP; u++) {
+        sC[u] = M.internal_loop[u] < INF ? M.internal_loop[u] + M.max_ninio : INF16;
         sB[u] = M.bulge[u] < INF ? M.bulge[u] : INF16;
         s1[u] = M.internal_loop[u] < INF ? M.internal_loop[u] + std::min(M.max_ninio, (u - 2) * M.ninio) : INF16;
         for (int u1 = 0; u1 < 32; u1++) {
@@ -451,6 +494,7 @@ void mfe2_upload_tables(const MfeTables &M) {
     cudaMemcpyToSymbol(c_sizeG, sG, sizeof(sG));
     cudaMemcpyToSymbol(c_size1, s1, sizeof(s1));
     cudaMemcpyToSymbol(c_sizeB, sB, sizeof(sB));
+    cudaMemcpyToSymbol(c_cap, sC, sizeof(sC));
     if (!g_dtab2) cudaMalloc(&g_dtab2, sizeof(Tab2));
     cudaMemcpy(g_dtab2, &h, sizeof(Tab2), cudaMemcpyHostToDevice);
 }
@@ -474,8 +518,8 @@ void launch_mfe2(const MfeLaunch &L, const MfeTables *d_tab, int n_sm, cudaStrea
         if (tw == 1) launch_mfe2_t<64, 1>(L, d_tab, grid, stream);
         else launch_mfe2_t<64, 2>(L, d_tab, grid, stream);
     } else {
-        if (tw == 1) launch_mfe2_t<128, 1>(L, d_tab, grid, stream);
-        else launch_mfe2_t<128, 2>(L, d_tab, grid, stream);
+        if (tw == 1) launch_mfe2_t<120, 1>(L, d_tab, grid, stream);
+        else launch_mfe2_t<120, 2>(L, d_tab, grid, stream);
     }
     if (n_launches) (*n_launches)++;
 }
