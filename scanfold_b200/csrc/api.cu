@@ -112,19 +112,28 @@ struct FoldWork {  // device scratch for one MFE launch
         per_cta = mfe_scratch_ints_per_cta(W, &mode);
         size_t need = per_cta * (size_t)mfe_grid_size(W, g_ctx.n_sm, n_fold);
         if (need > scratch.n) scratch.alloc(need);
-        if (mfe2_supports(W)) {
+        if (mfe2_supports(W) || mfe3_supports(W)) {
             per_warp2 = mfe2_scratch_shorts_per_warp(W);
-            size_t need2 = (per_warp2 * 4 * (size_t)mfe2_grid_size(g_ctx.n_sm, n_fold) + 1) / 2;
+            size_t rows = std::max((size_t)4 * mfe2_grid_size(g_ctx.n_sm, n_fold), (size_t)mfe3_max_ctas(g_ctx.n_sm));
+            size_t need2 = (per_warp2 * rows + 1) / 2;
             if (need2 > scratch2.n) scratch2.alloc(need2);
         }
     }
+    static int engine() {  // SFB_MFE_ENGINE=2 selects the second-generation kernel (tuning / debugging knob)
+        static const int e = getenv("SFB_MFE_ENGINE") ? atoi(getenv("SFB_MFE_ENGINE")) : 3;
+        return e;
+    }
     // energy-only unconstrained folds: int16 warp-per-fold kernel, then the int32 kernel on whatever it flagged
     void launch_energy_only(MfeLaunch L, cudaStream_t st, int *n_launch) const {
-        if (mfe2_supports(L.W) && !L.hc && !L.sc && L.max_span <= 0 && !L.pair_tbl) {
+        const bool use3 = engine() == 3 && mfe3_supports(L.W), use2 = engine() != 1 && mfe2_supports(L.W);
+        if ((use3 || use2) && !L.hc && !L.sc && L.max_span <= 0 && !L.pair_tbl) {
             MfeLaunch L2 = L;
             L2.gscratch = scratch2.p;
             L2.gscratch_per_cta = (long long)per_warp2;
-            launch_mfe2(L2, g_ctx.d_mfe, g_ctx.n_sm, st, n_launch);
+            if (use3)
+                launch_mfe3(L2, g_ctx.d_mfe, g_ctx.n_sm, st, n_launch);
+            else
+                launch_mfe2(L2, g_ctx.d_mfe, g_ctx.n_sm, st, n_launch);
             L.redo_only = 1;
             static const bool no_redo = getenv("SFB_DEBUG_NO_REDO") != nullptr;  // debugging: leave MFE_REDO markers
             if (no_redo) return;
@@ -213,6 +222,7 @@ int sfb_init(int device_ordinal, const char *par_file_or_null) {
         if (!g_ctx.d_mfe) CK(cudaMalloc(&g_ctx.d_mfe, sizeof(MfeTables)));
         CK(cudaMemcpy(g_ctx.d_mfe, &g_ctx.hp.mfe, sizeof(MfeTables), cudaMemcpyHostToDevice));
         mfe2_upload_tables(g_ctx.hp.mfe);
+        mfe3_upload_tables(g_ctx.hp.mfe);
         CK(cudaGetLastError());
         g_ctx.pf_temperature = -1e9;
         g_ctx.ready = true;

@@ -100,6 +100,11 @@ int mfe2_grid_size(int n_sm, int n_fold);
 size_t mfe2_scratch_shorts_per_warp(int W);
 void mfe2_upload_tables(const MfeTables &M);
 void launch_mfe2(const MfeLaunch &L, const MfeTables *d_tab, int n_sm, cudaStream_t stream, int *n_launches);
+// third-generation energy-only kernel (mfe3.cu): one CTA per fold, stencil / range-minimum interior loops
+bool mfe3_supports(int W);
+int mfe3_max_ctas(int n_sm);
+void mfe3_upload_tables(const MfeTables &M);
+void launch_mfe3(const MfeLaunch &L, const MfeTables *d_tab, int n_sm, cudaStream_t stream, int *n_launches);
 int mfe_grid_size(int W, int n_sm, int n_fold);
 
 void launch_pf(const PfLaunch &L, const MfeTables *d_mfe, const PfTables *d_pf, int n_sm, cudaStream_t stream,
