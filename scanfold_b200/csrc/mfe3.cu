@@ -22,8 +22,8 @@
 // multiloop matrix FML of both diagonals, sharing the left operand of the split loop.
 // int16 storage is exact as long as no stored energy drops below LOW16; a fold that does is flagged and redone
 // by the int32 kernel (mfe.cu) in the same stream, so results never depend on which kernel ran.
+#include <cstddef>
 #include <cstdlib>
-#include <type_traits>
 
 #include "device_common.cuh"
 
@@ -60,35 +60,39 @@ __constant__ int c3_sG6[4];     // generic loops of size 6: (2,4) (3,3) (4,2)
 Tab3 *g_dtab3 = nullptr;
 bool g_mfe3_ok = false;
 
+constexpr int BIG = 1 << 20;  // size term of a disabled tap: the sum never wins whatever the load returns
+constexpr int KSMAX = 4;      // the split loop of a tile diagonal is cut into at most 4 work items
+
 template <int P>
 struct Smem3 {
+    // ring pitch in shorts: PR/2 words = 31 (mod 32), so lane U reading row (c-U) at offset a*U (a = 0, 1/2, 1) lands in
+    // bank (1+a/2)*U: the 32 taps of one warp load hit 32 different banks
+    static constexpr int PR = P <= 64 ? P + 2 : ((P + 2 + 63) / 64) * 64 - 2;   // small windows: shared memory first
     Tab3 tb;
-    // ring rows, INF-initialised per fold; ne..rb double as the staging area of C for the exterior loop
-    short ne[R32 * P], no[R32 * P], m8[R32 * P], r1[R32 * P], rb[R32 * P];
-    short g[R16 * P];
-    short rc[R16 * P];
-    short dml[4 * P];
-    short fml[(P / 2 + 1) * P + 8];
-    short part[4 * 2 * P];
+    // ring rows and the square FML matrix, INF-initialised per fold; ne.. doubles as the staging area of C for
+    // the exterior loop
+    short ne[R32 * PR], no[R32 * PR], m8[R32 * PR], r1[R32 * PR], rb[R32 * PR];
+    short g[R16 * PR];
+    short rc[R16 * PR];
+    short dml[4 * PR];
+    short padrow[PR + 38];
+    short fm[P * P];          // fm[a][b]: FML[a,b] for b > a (row = 5' end), FML[b,a] for b < a (row = 3' end)
+    short decp[KSMAX * 8 * PR];
+    short part[2 * 2 * PR];
     short f5[P + 8];
-    unsigned char ctx[R16 * P];
-    unsigned char list[2 * P];
+    alignas(16) int list[(2 * PR + 8) * 4];     // per pairable cell: i, mismatchI / mismatch1nI / TerminalAU term of the closing pair
+    unsigned char ctx[R16 * PR];
     unsigned char sx[P + 8];   // sx[k+1] = code of nucleotide k, sx[0] = sx[W+1] = 5
     int cnt[2];
     int minv[32];
+    int fbest[32];
 };
 
 __host__ __device__ __forceinline__ int tri4(int d, int W) {  // first cell of diagonal d in the d >= 4 triangle
     return (d - 4) * W - ((d - 1) * d / 2 - 6);
 }
 
-template <int A, int B, class F>
-__device__ __forceinline__ void sfor(F &&f) {
-    if constexpr (A <= B) {
-        f(std::integral_constant<int, A>{});
-        sfor<A + 1, B>(f);
-    }
-}
+__host__ __device__ __forceinline__ int ksplit(int D) { return D < 36 ? 1 : (D < 72 ? 2 : 4); }
 
 __device__ int hairpin_special3(const MfeTables *T, const Tab3 &tb, const unsigned char *sx, int i, int j, int type) {
     // loops of 3, 4 and 6 nucleotides: tabulated tri- / tetra- / hexaloops; sx is offset by one
@@ -119,53 +123,13 @@ __device__ int hairpin_special3(const MfeTables *T, const Tab3 &tb, const unsign
     return e + tb.mmH[(type * 5 + sx[i + 2]) * 5 + sx[j]];
 }
 
-// ---- phase C, class A: generic interior loops of size U (see the header) -------------------------------------
-template <int U, int P>
-__device__ __forceinline__ void generic_u(const Smem3<P> &sm, int d, int i, int &g0, int &g1) {
-    const int dd = d - 2 - U;
-    const int r32 = (dd & (R32 - 1)) * P + i, r16 = (dd & (R16 - 1)) * P + i;
-    if constexpr (U == 6) {
-        g0 = __viaddmin_s32(sm.g[r16 + 3], c3_sG6[0], g0);
-        g1 = __viaddmin_s32(sm.g[r16 + 4], c3_sG6[1], g1);
-        g0 = __viaddmin_s32(sm.g[r16 + 5], c3_sG6[2], g0);
-    } else {
-        constexpr int m = U / 2;
-        if constexpr (U % 2 == 0)
-            g0 = __viaddmin_s32(sm.ne[r32 + 3 + m], c3_il[U], g0);
-        else
-            g1 = __viaddmin_s32(sm.no[r32 + 3 + m], c3_il[U], g1);
-        if constexpr (U == 9 || U == 10) {  // the two capped candidates (u1 = 2 and u2 = 2)
-            g0 = __viaddmin_s32(sm.g[r16 + 3], c3_cap[U], g0);
-            g1 = __viaddmin_s32(sm.g[r16 + U - 1], c3_cap[U], g1);
-        }
-        if constexpr (U >= 11) {  // range minimum over u1 = 2 .. U-2, i.e. row positions i+3 .. i+U-1
-            int f = sm.m8[r32 + 10];
-            if constexpr (U > 11) f = min(f, (int)sm.m8[r32 + U - 1]);
-            if constexpr (U > 19) f = min(f, (int)sm.m8[r32 + 18]);
-            if constexpr (U > 27) f = min(f, (int)sm.m8[r32 + 26]);
-            if constexpr (U % 2 == 0)
-                g1 = __viaddmin_s32(f, c3_cap[U], g1);
-            else
-                g0 = __viaddmin_s32(f, c3_cap[U], g0);
-        }
-    }
-}
-
-// ---- phase C, classes L / R: bulges and 1xn loops with the unpaired stretch on the 3' (L) or 5' (R) side --------
-template <int U, int P, bool RIGHT>
-__device__ __forceinline__ void side_u(const Smem3<P> &sm, int d, int i, int &aB, int &a1) {
-    const int dd = d - 2 - U;
-    const int r32 = (dd & (R32 - 1)) * P + i;
-    aB = __viaddmin_s32(sm.rb[r32 + (RIGHT ? 1 + U : 1)], c3_sizeB[U], aB);
-    if constexpr (U >= 4) a1 = __viaddmin_s32(sm.r1[r32 + (RIGHT ? U : 2)], c3_size1[U], a1);
-}
-
 template <int P, int NW, int OCC>
 __global__ void __launch_bounds__(NW * 32, OCC)
 mfe3_kernel(MfeLaunch L, const MfeTables *__restrict__ T, const Tab3 *__restrict__ gtab) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    Smem3<P> &sm = *reinterpret_cast<Smem3<P> *>(smem_raw);
-    constexpr int NT = NW * 32;
+    using SM = Smem3<P>;
+    SM &sm = *reinterpret_cast<SM *>(smem_raw);
+    constexpr int NT = NW * 32, PR = SM::PR, NWH = NW / 2;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const unsigned full = 0xffffffffu;
     {
@@ -176,11 +140,24 @@ mfe3_kernel(MfeLaunch L, const MfeTables *__restrict__ T, const Tab3 *__restrict
     }
     const Tab3 &tb = sm.tb;
     const unsigned char *sx = sm.sx;
-    const int W = L.W, H = W / 2;
+    const int W = L.W;
     short *gC = reinterpret_cast<short *>(L.gscratch) + (size_t)blockIdx.x * L.gscratch_per_cta;
-    auto fidx = [&](int dd, int idx) { return dd <= H ? dd * P + idx : (W - dd) * P + dd + idx; };
+    const short *smb = sm.ne;   // every tap address below is an offset (in shorts) from here
+    constexpr int O_NE = 0, O_NO = R32 * PR, O_M8 = 2 * R32 * PR, O_R1 = 3 * R32 * PR, O_RB = 4 * R32 * PR,
+                  O_G = 5 * R32 * PR, O_PAD = 5 * R32 * PR + 2 * R16 * PR + 4 * PR;
 
-    // compacted list of the pairable cells of diagonal d -> sm.list[slot], sm.cnt[slot] (one warp)
+    // ---- per-lane loop size U = lane: size terms of its nine taps (see the header); BIG disables a tap
+    const int U = lane;
+    const bool uok = U <= MAXLOOP;
+    const int cSB = (uok && U >= 2) ? c3_sizeB[U] : BIG;
+    const int cS1 = (uok && U >= 4) ? c3_size1[U] : BIG;
+    const int cA = !uok ? BIG : (U == 6 ? c3_sG6[0] : (U >= 7 ? c3_il[U] : BIG));
+    const int cB10 = !uok ? BIG : (U == 6 ? c3_sG6[1] : (U >= 9 ? c3_cap[U] : BIG));
+    const int cB18 = (uok && U > 19) ? c3_cap[U] : BIG;
+    const int cB26 = (uok && U > 27) ? c3_cap[U] : BIG;
+    const int cC = !uok ? BIG : (U == 6 ? c3_sG6[2] : ((U == 9 || U == 10 || U > 11) ? c3_cap[U] : BIG));
+
+    // compacted list of the pairable cells of diagonal d with the closing-pair terms (one warp)
     auto build_list = [&](int slot, int d) {
         int nl = 0;
         const int ncells = W - d;
@@ -188,7 +165,11 @@ mfe3_kernel(MfeLaunch L, const MfeTables *__restrict__ T, const Tab3 *__restrict
             const int i = i0 + lane;
             const int t = i < ncells ? tb.ptype[sx[i + 1] * 6 + sx[i + d + 1]] : 0;
             const unsigned m = __ballot_sync(full, t != 0);
-            if (t) sm.list[slot * P + nl + __popc(m & ((1u << lane) - 1))] = (unsigned char)i;
+            if (t) {
+                const int mi = (t * 5 + sx[i + 2]) * 5 + sx[i + d];
+                int4 en = make_int4(i, tb.mmI[mi], tb.mm1n[mi], tb.tAU[t]);
+                reinterpret_cast<int4 *>(sm.list)[slot * PR + nl + __popc(m & ((1u << lane) - 1))] = en;
+            }
             nl += __popc(m);
         }
         if (lane == 0) sm.cnt[slot] = nl;
@@ -196,15 +177,14 @@ mfe3_kernel(MfeLaunch L, const MfeTables *__restrict__ T, const Tab3 *__restrict
 
     for (int fold = blockIdx.x; fold < L.n_fold; fold += gridDim.x) {
         __syncthreads();
-        // ---- prologue: sequence with sentinels, INF in every ring row
+        // ---- prologue: sequence with sentinels, INF in every ring row and in the FML matrix
         for (int k = tid; k < W + 2; k += NT)
             sm.sx[k] = (k == 0 || k == W + 1) ? 5 : L.seqs[(size_t)fold * W + k - 1];
         {
             const int4 inf4 = make_int4(INF16 * 65537, INF16 * 65537, INF16 * 65537, INF16 * 65537);
             int4 *p = reinterpret_cast<int4 *>(sm.ne);
-            constexpr int n16 = (int)((5 * R32 * P + 2 * R16 * P + 4 * P) * sizeof(short) / 16);  // ne .. dml
-            static_assert(((5 * R32 * P + 2 * R16 * P + 4 * P) * sizeof(short)) % 16 == 0, "ring area is filled as int4");
-            for (int k = tid; k < n16; k += NT) p[k] = inf4;
+            constexpr int n16 = (int)((offsetof(SM, decp) - offsetof(SM, ne) + 15) / 16);   // a ragged tail spills
+            for (int k = tid; k < n16; k += NT) p[k] = inf4;                                 // into decp (rewritten before use)
         }
         int minv = 0;
         __syncthreads();
@@ -213,37 +193,82 @@ mfe3_kernel(MfeLaunch L, const MfeTables *__restrict__ T, const Tab3 *__restrict
 
         for (int d0 = TURN + 1; d0 < W; d0 += 2) {
             const int nd = d0 + 1 < W ? 2 : 1;
-            // =================== phase C: partial minima of the pairable cells =======================
+            // =================== phase 1a: interior loops of size >= 2, one pairable cell per warp pass ==========
+            {
+                const int ds = warp >= NWH ? 1 : 0, wc = ds ? warp - NWH : warp;
+                const int d = d0 + ds;
+                const int n = ds < nd ? sm.cnt[ds] : 0;
+                if (wc < n) {
+                    const int s32 = ((d - 2 - U) & (R32 - 1)) * PR, s16 = ((d - 2 - U) & (R16 - 1)) * PR;
+                    const int oL = O_RB + s32, oR = O_RB + s32 + U;
+                    int oA = O_PAD, oB = O_PAD, oC = O_PAD;
+                    if (uok) {
+                        if (U == 6) {
+                            oA = O_G + s16 + 3;
+                            oB = O_G + s16 + 4 - 10;
+                            oC = O_G + s16 + 5;
+                        } else if (U >= 7) {
+                            oA = ((U & 1) ? O_NO : O_NE) + s32 + 3 + (U >> 1);
+                            if (U == 9 || U == 10) {
+                                oB = O_G + s16 + 3 - 10;
+                                oC = O_G + s16 + U - 1;
+                            } else if (U >= 11) {
+                                oB = O_M8 + s32;
+                                oC = O_M8 + s32 + (U > 11 ? U - 1 : 10);
+                            }
+                        }
+                    }
+                    const int4 *lst = reinterpret_cast<const int4 *>(sm.list) + ds * PR;
+                    const short *qL = smb + oL, *qR = smb + oR, *qA = smb + oA, *qB = smb + oB, *qC = smb + oC;
+                    short *qP = sm.part + ds * PR;
+                    int4 en = lst[wc];
+                    for (int k = wc; k < n; k += NWH) {
+                        const int i = en.x, eI = en.y, e1 = en.z, eB = en.w;
+                        en = lst[k + NWH];   // next entry (at most NWH past the list end: still inside sm.list)
+                        const short *pl = qL + i, *pr = qR + i, *pa = qA + i, *pb = qB + i, *pc = qC + i;
+                        const int xbl = pl[1], x1l = pl[O_R1 - O_RB + 2];
+                        const int xbr = pr[1], x1r = pr[O_R1 - O_RB];
+                        const int xa = pa[0], xb10 = pb[10], xb18 = pb[18], xb26 = pb[26], xc = pc[0];
+                        int g = xa + cA;
+                        g = __viaddmin_s32(xb10, cB10, g);
+                        int g2 = xb18 + cB18;
+                        g2 = __viaddmin_s32(xb26, cB26, g2);
+                        g = __viaddmin_s32(xc, cC, g);
+                        const int aB = min(xbl, xbr) + cSB, a1 = min(x1l, x1r) + cS1;
+                        int v = min(g, g2) + eI;
+                        v = __viaddmin_s32(a1, e1, v);
+                        v = __viaddmin_s32(aB, eB, v);
+                        v = __reduce_min_sync(full, v);
+                        if (lane == 0) qP[i] = (short)v;   // <= INF16 + size and mismatch terms: fits
+                    }
+                }
+            }
+            // =================== phase 1b: table-driven shapes / hairpin / multiloop closing (lane = cell) and
+            //                     the split minima of tile diagonal d0+2 (lane = 2x2 tile) as work items ===========
             {
                 const int n0 = sm.cnt[0], n1 = nd == 2 ? sm.cnt[1] : 0;
                 const int nch0 = (n0 + 31) >> 5, nch = nch0 + ((n1 + 31) >> 5);
-                for (int it = warp; it < 4 * nch; it += NW) {
-                    const int part = it / nch, ch = it - part * nch;
-                    const int ds = ch >= nch0 ? 1 : 0, c = ds ? ch - nch0 : ch;
-                    const int d = d0 + ds, n = ds ? n1 : n0;
-                    const int idx = c * 32 + lane;
-                    const bool active = idx < n;
-                    const int i = active ? sm.list[ds * P + idx] : 0;
-                    const int j = i + d;
-                    const int type = tb.ptype[sx[i + 1] * 6 + sx[j + 1]];
-                    const int si1 = sx[i + 2], sj1 = sx[j];
-                    const int mi = (type * 5 + si1) * 5 + sj1;
-                    const int umax = d - 2 - (TURN + 1);   // largest loop size with an inner diagonal > TURN
-                    int res;
-                    if (part == 0) {
-                        int g0 = INF16, g1 = INF16;
-                        if (umax >= 6) sfor<6, 13>([&](auto U) { generic_u<decltype(U)::value, P>(sm, d, i, g0, g1); });
-                        if (umax >= 14) sfor<14, 21>([&](auto U) { generic_u<decltype(U)::value, P>(sm, d, i, g0, g1); });
-                        if (umax >= 22) sfor<22, 30>([&](auto U) { generic_u<decltype(U)::value, P>(sm, d, i, g0, g1); });
-                        res = min(g0, g1) + tb.mmI[mi];
-                    } else if (part == 1) {
-                        // the nine table-driven shapes, the hairpin and the multiloop closing
+                const int D = d0 + 2;
+                const int ntile = D <= W - 1 ? (W - 1 - D) / 2 + 1 : 0;
+                const int KS = ksplit(D), ksh = KS >> 1 /* log2 of 1, 2, 4 */, ngrp = (ntile + 31) >> 5;
+                const int nitem = nch + ngrp * KS;
+                for (int it = NW - 1 - warp; it < nitem; it += NW) {
+                    if (it < nch) {
+                        const int ds = it >= nch0 ? 1 : 0, c = ds ? it - nch0 : it;
+                        const int d = d0 + ds, n = ds ? n1 : n0;
+                        const int idx = c * 32 + lane;
+                        const bool active = idx < n;
+                        const int i = active ? sm.list[(ds * PR + idx) * 4] : 0;
+                        const int j = i + d;
+                        const int type = tb.ptype[sx[i + 1] * 6 + sx[j + 1]];
+                        const int si1 = sx[i + 2], sj1 = sx[j];
+                        const int mi = (type * 5 + si1) * 5 + sj1;
                         int aT = INF16;
                         auto inner = [&](int u1, int u2, int &cc, int &t2, int &sp1, int &sq1) {
                             const int dd = d - 2 - u1 - u2, p = i + 1 + u1, q = j - 1 - u2;
                             const bool ok = dd > TURN;
-                            cc = ok ? sm.rc[(dd & (R16 - 1)) * P + p] : INF16;
-                            t2 = ok ? sm.ctx[(dd & (R16 - 1)) * P + p] : 0;
+                            cc = ok ? sm.rc[(dd & (R16 - 1)) * PR + p] : INF16;
+                            t2 = ok ? sm.ctx[(dd & (R16 - 1)) * PR + p] : 0;
                             sp1 = sx[p];       // S[p-1]
                             sq1 = sx[q + 2];   // S[q+1]
                         };
@@ -268,31 +293,55 @@ mfe3_kernel(MfeLaunch L, const MfeTables *__restrict__ T, const Tab3 *__restrict
                         aT = min(aT, cc + tb.il5_ninio + tb.mm23[mi] + tb.mm23[(t2 * 5 + sq1) * 5 + sp1]);
                         int eh = __ldg(&T->hairpin_len[d - 1]) + tb.mmH[mi];
                         if (d <= 7 && active) eh = hairpin_special3(T, tb, sx, i, j, type);
-                        const int dm = sm.dml[((d - 2) & 3) * P + i + 1];
-                        res = min(min(aT, eh), dm + tb.mlclose[(tb.rtype[type] * 5 + sj1) * 5 + si1]);
-                    } else if (part == 2) {
-                        int aB = INF16, a1 = INF16, bB = INF16, b1 = INF16;
-                        if (umax >= 2) sfor<2, 9>([&](auto U) { side_u<decltype(U)::value, P, false>(sm, d, i, (decltype(U)::value & 1) ? bB : aB, (decltype(U)::value & 1) ? b1 : a1); });
-                        if (umax >= 10) sfor<10, 19>([&](auto U) { side_u<decltype(U)::value, P, false>(sm, d, i, (decltype(U)::value & 1) ? bB : aB, (decltype(U)::value & 1) ? b1 : a1); });
-                        if (umax >= 20) sfor<20, 30>([&](auto U) { side_u<decltype(U)::value, P, false>(sm, d, i, (decltype(U)::value & 1) ? bB : aB, (decltype(U)::value & 1) ? b1 : a1); });
-                        res = min(min(a1, b1) + tb.mm1n[mi], min(aB, bB) + tb.tAU[type]);
+                        const int dm = sm.dml[((d - 2) & 3) * PR + i + 1];
+                        const int res = min(min(aT, eh), dm + tb.mlclose[(tb.rtype[type] * 5 + sj1) * 5 + si1]);
+                        if (active) sm.part[(2 + ds) * PR + i] = (short)min(res, INF16);
                     } else {
-                        int aB = INF16, a1 = INF16, bB = INF16, b1 = INF16;
-                        if (umax >= 2) sfor<2, 9>([&](auto U) { side_u<decltype(U)::value, P, true>(sm, d, i, (decltype(U)::value & 1) ? bB : aB, (decltype(U)::value & 1) ? b1 : a1); });
-                        if (umax >= 10) sfor<10, 19>([&](auto U) { side_u<decltype(U)::value, P, true>(sm, d, i, (decltype(U)::value & 1) ? bB : aB, (decltype(U)::value & 1) ? b1 : a1); });
-                        if (umax >= 20) sfor<20, 30>([&](auto U) { side_u<decltype(U)::value, P, true>(sm, d, i, (decltype(U)::value & 1) ? bB : aB, (decltype(U)::value & 1) ? b1 : a1); });
-                        res = min(min(a1, b1) + tb.mm1n[mi], min(aB, bB) + tb.tAU[type]);
+                        // 2x2 tile (i, i+1) x (j, j+1), i and j even, j - i = D: all four split minima share their
+                        // operands; both operand pairs are one aligned 32-bit load from the square matrix
+                        const int q = it - nch, grp = q >> ksh, kp = q & (KS - 1);
+                        const int tl = grp * 32 + lane;
+                        const bool valid = tl < ntile;
+                        const int i = 2 * min(tl, ntile - 1), j = i + D;
+                        const int cntk = D - 7;   // k = i+4 .. j-4; the band |a-b| < 4 of fm stays INF
+                        const int k0 = i + 4 + ((cntk * kp) >> ksh), k1 = i + 4 + ((cntk * (kp + 1)) >> ksh);
+                        const unsigned *pa = reinterpret_cast<const unsigned *>(sm.fm + k0 * P + i);
+                        const unsigned *pb = reinterpret_cast<const unsigned *>(sm.fm + (k0 + 1) * P + j);
+                        unsigned acc0 = INF16 * 65537u, acc1 = INF16 * 65537u;
+                        int k = k0;
+                        for (; k + 3 < k1; k += 4, pa += 2 * P, pb += 2 * P) {
+#pragma unroll
+                            for (int z = 0; z < 4; z++) {
+                                const unsigned a = pa[z * (P / 2)], b = pb[z * (P / 2)];
+                                acc0 = __viaddmin_s16x2(a, __byte_perm(b, 0, 0x1010), acc0);
+                                acc1 = __viaddmin_s16x2(a, __byte_perm(b, 0, 0x3232), acc1);
+                            }
+                        }
+                        for (; k < k1; k++, pa += P / 2, pb += P / 2) {
+                            const unsigned a = pa[0], b = pb[0];
+                            acc0 = __viaddmin_s16x2(a, __byte_perm(b, 0, 0x1010), acc0);
+                            acc1 = __viaddmin_s16x2(a, __byte_perm(b, 0, 0x3232), acc1);
+                        }
+                        if (valid) {
+                            auto fin = [](int v) { return (short)(v >= FIN16 ? INF16 : v); };
+                            short *dp = sm.decp + kp * 8 * PR;
+                            dp[(D & 7) * PR + i] = fin((short)(acc0 & 0xffffu));
+                            dp[((D - 1) & 7) * PR + i + 1] = fin((int)acc0 >> 16);
+                            if (j + 1 < W) {
+                                dp[((D + 1) & 7) * PR + i] = fin((short)(acc1 & 0xffffu));
+                                dp[(D & 7) * PR + i + 1] = fin((int)acc1 >> 16);
+                            }
+                        }
                     }
-                    if (active) sm.part[(part * 2 + ds) * P + i] = (short)min(res, INF16);
                 }
             }
             __syncthreads();
-            // =================== lists of the next diagonal pair (warps 0, 1) ==========================
-            if (warp < 2) build_list(warp, d0 + 2 + warp);
-            // =================== phase S: C and the derived rows of diagonals d0, d0+1 =================
+            // =================== phase 2: lists of the next diagonal pair (two warps) ===========================
+            if (warp >= NW - 2) build_list(warp - (NW - 2), d0 + 2 + warp - (NW - 2));
+            // ---- C and the derived rows of diagonals d0, d0+1 (25 row elements per warp pass)
             {
                 const int nseg0 = (W - d0 + SEG - 1) / SEG, nseg = nseg0 + (nd == 2 ? (W - d0 - 1 + SEG - 1) / SEG : 0);
-                for (int un = warp; un < nseg; un += NW) {
+                for (int un = NW - 1 - warp; un < nseg; un += NW) {
                     const int ds = un >= nseg0 ? 1 : 0, sg = ds ? un - nseg0 : un;
                     const int d = d0 + ds, ncells = W - d;
                     const int x = sg * SEG - 7 + lane;
@@ -301,8 +350,7 @@ mfe3_kernel(MfeLaunch L, const MfeTables *__restrict__ T, const Tab3 *__restrict
                     const int t = valid ? tb.ptype[sx[i + 1] * 6 + sx[j + 1]] : 0;
                     int e = INF16;
                     if (t) {
-                        const short *pp = sm.part + ds * P + i;
-                        e = min(min((int)pp[0], (int)pp[2 * P]), min((int)pp[4 * P], (int)pp[6 * P]));
+                        e = min((int)sm.part[ds * PR + i], (int)sm.part[(2 + ds) * PR + i]);
                         if (e >= FIN16) e = INF16;
                     }
                     int vg = INF16, v1 = INF16, vb = INF16;
@@ -322,7 +370,7 @@ mfe3_kernel(MfeLaunch L, const MfeTables *__restrict__ T, const Tab3 *__restrict
                     m8 = min(m8, __shfl_up_sync(full, m8, 4));
                     if (valid && lane >= 7) {
                         minv = min(minv, e);
-                        const int o16 = (d & (R16 - 1)) * P + i, o32 = (d & (R32 - 1)) * P + i;
+                        const int o16 = (d & (R16 - 1)) * PR + i, o32 = (d & (R32 - 1)) * PR + i;
                         sm.rc[o16] = (short)e;
                         sm.ctx[o16] = (unsigned char)t2;
                         sm.g[o16] = (short)vg;
@@ -335,124 +383,52 @@ mfe3_kernel(MfeLaunch L, const MfeTables *__restrict__ T, const Tab3 *__restrict
                     }
                 }
             }
-            // =================== phase M: multiloop matrix of both diagonals ===========================
+            // ---- multiloop matrix of both diagonals: 31 cells per warp, the neighbour on d0 comes by shuffle
             {
-                const int d = d0, nc0 = W - d, nc1 = nd == 2 ? W - d - 1 : 0;
-                const int khi = d - 2 - TURN;   // last split of diagonal d0; diagonal d0+1 has one more
-                const int kB = d - 1 - H;       // right operand of diagonal d0 sits in the low half for k >= kB
-                for (int i0 = 0; i0 < nc0; i0 += NT) {
-                    const int ir = i0 + tid;
-                    const int i = min(ir, nc0 - 1);   // the last cell has no neighbour on d0+1: it reads in-bounds garbage there
-                    int a0 = 2 * INF16, a1 = 2 * INF16, b0 = 2 * INF16, b1 = 2 * INF16;
-                    int k = TURN + 1;
-                    {   // A low (+P), B high (+P), B' high (+P)
-                        const int kend = min(kB - 1, khi);
-                        const short *pa = sm.fml + k * P + i;
-                        const short *pb = sm.fml + (W - d + 1 + k) * P + d + i;   // B'(k) = pb[-P + 1]
-                        for (; k + 1 <= kend; k += 2, pa += 2 * P, pb += 2 * P) {
-                            const int x0 = pa[0], x1 = pa[P];
-                            a0 = __viaddmin_s32(x0, pb[0], a0);
-                            b0 = __viaddmin_s32(x0, pb[-P + 1], b0);
-                            a1 = __viaddmin_s32(x1, pb[P], a1);
-                            b1 = __viaddmin_s32(x1, pb[1], b1);
-                        }
-                        for (; k <= kend; k++, pa += P, pb += P) {
-                            const int x0 = pa[0];
-                            a0 = __viaddmin_s32(x0, pb[0], a0);
-                            b0 = __viaddmin_s32(x0, pb[-P + 1], b0);
-                        }
+                const int nc0 = W - d0, nc1 = nd == 2 ? W - d0 - 1 : 0;
+                if (warp * 31 < nc0) {
+                    const int x = warp * 31 + lane;
+                    const bool v0 = x < nc0;
+                    const int xx = v0 ? x : nc0 - 1;
+                    // split minimum of cell (xx, d): which tile diagonal produced it decides how many partials exist
+                    auto decof = [&](int d, int xi) {
+                        if (d < 2 * TURN + 3) return INF16;
+                        const int Dsrc = (d & 1) ? ((xi & 1) ? d + 1 : d - 1) : d;
+                        const int ks = ksplit(Dsrc);
+                        int v = sm.decp[(d & 7) * PR + xi];
+                        for (int kp = 1; kp < ks; kp++) v = min(v, (int)sm.decp[(kp * 8 + (d & 7)) * PR + xi]);
+                        return v;
+                    };
+                    auto stemof = [&](int ds, int d, int xi) {
+                        const int j = xi + d;
+                        const int t = tb.ptype[sx[xi + 1] * 6 + sx[j + 1]];
+                        if (!t) return INF16;
+                        const int e = min((int)sm.part[ds * PR + xi], (int)sm.part[(2 + ds) * PR + xi]);
+                        return e < FIN16 ? e + tb.mlstem[t * 36 + sx[xi] * 6 + sx[j + 2]] : INF16;
+                    };
+                    const int dec0 = decof(d0, xx);
+                    int m0 = min(dec0, stemof(0, d0, xx));
+                    if (d0 - 1 > TURN)
+                        m0 = min(m0, min((int)sm.fm[(xx + 1) * P + xx + d0], (int)sm.fm[xx * P + xx + d0 - 1]) + tb.MLbase);
+                    if (m0 >= FIN16) m0 = INF16;
+                    if (v0) {
+                        minv = min(minv, m0);
+                        sm.dml[(d0 & 3) * PR + x] = (short)dec0;
+                        sm.fm[x * P + x + d0] = (short)m0;
+                        sm.fm[(x + d0) * P + x] = (short)m0;
                     }
-                    if (k == kB && k <= khi) {   // A low, B low, B' high
-                        const int x0 = sm.fml[k * P + i];
-                        a0 = __viaddmin_s32(x0, sm.fml[(d - 1 - k) * P + i + k + 1], a0);
-                        b0 = __viaddmin_s32(x0, sm.fml[(W - d + k) * P + d + 1 + i], b0);
-                        k++;
+                    const int m0n = __shfl_down_sync(full, m0, 1);
+                    if (lane < 31 && x < nc1) {
+                        const int d = d0 + 1;
+                        const int dec1 = decof(d, x);
+                        int m1 = min(dec1, stemof(1, d, x));
+                        m1 = min(m1, min(m0, m0n) + tb.MLbase);
+                        if (m1 >= FIN16) m1 = INF16;
+                        minv = min(minv, m1);
+                        sm.dml[(d & 3) * PR + x] = (short)dec1;
+                        sm.fm[x * P + x + d] = (short)m1;
+                        sm.fm[(x + d) * P + x] = (short)m1;
                     }
-                    {   // A low (+P), B low (-P+1), B' low: B'(k) = pb[P]
-                        const int kend = min(H, khi);
-                        const short *pa = sm.fml + k * P + i;
-                        const short *pb = sm.fml + (d - 1 - k) * P + i + k + 1;
-                        for (; k + 1 <= kend; k += 2, pa += 2 * P, pb -= 2 * (P - 1)) {
-                            const int x0 = pa[0], x1 = pa[P];
-                            a0 = __viaddmin_s32(x0, pb[0], a0);
-                            b0 = __viaddmin_s32(x0, pb[P], b0);
-                            a1 = __viaddmin_s32(x1, pb[-(P - 1)], a1);
-                            b1 = __viaddmin_s32(x1, pb[1], b1);
-                        }
-                        for (; k <= kend; k++, pa += P, pb -= P - 1) {
-                            const int x0 = pa[0];
-                            a0 = __viaddmin_s32(x0, pb[0], a0);
-                            b0 = __viaddmin_s32(x0, pb[P], b0);
-                        }
-                    }
-                    {   // A high (-P+1), B low (-P+1), B' low
-                        const short *pa = sm.fml + (W - k) * P + k + i;
-                        const short *pb = sm.fml + (d - 1 - k) * P + i + k + 1;
-                        for (; k + 1 <= khi; k += 2, pa -= 2 * (P - 1), pb -= 2 * (P - 1)) {
-                            const int x0 = pa[0], x1 = pa[-(P - 1)];
-                            a0 = __viaddmin_s32(x0, pb[0], a0);
-                            b0 = __viaddmin_s32(x0, pb[P], b0);
-                            a1 = __viaddmin_s32(x1, pb[-(P - 1)], a1);
-                            b1 = __viaddmin_s32(x1, pb[1], b1);
-                        }
-                        for (; k <= khi; k++, pa -= P - 1, pb -= P - 1) {
-                            const int x0 = pa[0];
-                            a0 = __viaddmin_s32(x0, pb[0], a0);
-                            b0 = __viaddmin_s32(x0, pb[P], b0);
-                        }
-                    }
-                    // the extra split of diagonal d0+1: k = d0 - 4, right operand on diagonal 4
-                    if (nd == 2 && d - (TURN + 1) >= TURN + 1) {
-                        const int kx = d - (TURN + 1);
-                        b1 = __viaddmin_s32(sm.fml[fidx(kx, i)], sm.fml[fidx(TURN + 1, i + kx + 1)], b1);
-                    }
-                    if (ir < nc0) {
-                        const int j = ir + d;
-                        int dec = min(a0, a1);
-                        if (dec >= FIN16) dec = INF16;
-                        int m = dec;
-                        if (d - 1 > TURN) {
-                            const short *prev = sm.fml + fidx(d - 1, ir);
-                            m = min(m, min((int)prev[0], (int)prev[1]) + tb.MLbase);
-                        }
-                        const int t = tb.ptype[sx[ir + 1] * 6 + sx[j + 1]];
-                        if (t) {
-                            const short *pp = sm.part + ir;
-                            int e = min(min((int)pp[0], (int)pp[2 * P]), min((int)pp[4 * P], (int)pp[6 * P]));
-                            if (e < FIN16) m = min(m, e + tb.mlstem[t * 36 + sx[ir] * 6 + sx[j + 2]]);
-                        }
-                        if (m >= FIN16) m = INF16;
-                        minv = min(minv, m);
-                        sm.dml[(d & 3) * P + ir] = (short)dec;
-                        sm.fml[fidx(d, ir)] = (short)m;
-                    }
-                    if (ir < nc1) {   // diagonal d0+1: split minimum and stem term now, the neighbour terms after the barrier
-                        const int j = ir + d + 1;
-                        int dec = min(b0, b1);
-                        if (dec >= FIN16) dec = INF16;
-                        int m = dec;
-                        const int t = tb.ptype[sx[ir + 1] * 6 + sx[j + 1]];
-                        if (t) {
-                            const short *pp = sm.part + P + ir;
-                            int e = min(min((int)pp[0], (int)pp[2 * P]), min((int)pp[4 * P], (int)pp[6 * P]));
-                            if (e < FIN16) m = min(m, e + tb.mlstem[t * 36 + sx[ir] * 6 + sx[j + 2]]);
-                        }
-                        if (m >= FIN16) m = INF16;
-                        sm.dml[((d + 1) & 3) * P + ir] = (short)dec;
-                        sm.fml[fidx(d + 1, ir)] = (short)m;
-                    }
-                }
-            }
-            __syncthreads();
-            if (nd == 2) {
-                const int d = d0 + 1;
-                for (int ir = tid; ir < W - d; ir += NT) {
-                    const short *prev = sm.fml + fidx(d - 1, ir);
-                    int m = sm.fml[fidx(d, ir)];
-                    m = min(m, min((int)prev[0], (int)prev[1]) + tb.MLbase);
-                    if (m >= FIN16) m = INF16;
-                    minv = min(minv, m);
-                    sm.fml[fidx(d, ir)] = (short)m;
                 }
             }
             __syncthreads();
@@ -467,20 +443,31 @@ mfe3_kernel(MfeLaunch L, const MfeTables *__restrict__ T, const Tab3 *__restrict
             minv = __reduce_min_sync(full, minv);
             if (lane == 0) sm.minv[warp] = minv;
             __syncthreads();
-            if (warp == 0) {
-                for (int len = TURN + 2; len <= W; len++) {
-                    const int j = len - 1;
-                    int best = INF16;
-                    for (int i = lane; i <= j - TURN - 1; i += 32) best = min(best, sm.f5[i] + cx[tri4(j - i, W) + i]);
-                    best = __reduce_min_sync(full, best);
-                    if (lane == 0) sm.f5[len] = (short)min((int)sm.f5[len - 1], best);
-                    __syncwarp();
+            // F5[len] only needs F5[i] for i <= len - 5, so four consecutive lengths are independent: one (or two)
+            // warps per length, then the running minimum along the block
+            constexpr int WPL = NW / 4;   // warps per length
+            for (int len0 = TURN + 2; len0 <= W; len0 += 4) {
+                const int len = len0 + (warp & 3), j = len - 1;
+                int best = INF16;
+                if (len <= W)
+                    for (int i = lane + 32 * (warp >> 2); i <= j - TURN - 1; i += 32 * WPL)
+                        best = min(best, sm.f5[i] + cx[tri4(j - i, W) + i]);
+                best = __reduce_min_sync(full, best);
+                if (lane == 0) sm.fbest[warp] = best;
+                __syncthreads();
+                if (tid == 0) {
+                    int run = sm.f5[len0 - 1];
+                    for (int t = 0; t < 4 && len0 + t <= W; t++) {
+                        for (int h = 0; h < WPL; h++) run = min(run, sm.fbest[t + 4 * h]);
+                        sm.f5[len0 + t] = (short)run;
+                    }
                 }
-                if (lane == 0) {
-                    int mv = sm.minv[0];
-                    for (int q = 1; q < NW; q++) mv = min(mv, sm.minv[q]);
-                    L.e_out[fold] = mv < LOW16 ? MFE_REDO : (int)sm.f5[W];
-                }
+                __syncthreads();
+            }
+            if (tid == 0) {
+                int mv = sm.minv[0];
+                for (int q = 1; q < NW; q++) mv = min(mv, sm.minv[q]);
+                L.e_out[fold] = mv < LOW16 ? MFE_REDO : (int)sm.f5[W];
             }
         }
     }
@@ -575,10 +562,13 @@ void mfe3_upload_tables(const MfeTables &M) {
 
 void launch_mfe3(const MfeLaunch &L, const MfeTables *d_tab, int n_sm, cudaStream_t stream, int *n_launches) {
     if (L.n_fold <= 0) return;
+    static const int nw = getenv("SFB_MFE3_WARPS") ? atoi(getenv("SFB_MFE3_WARPS")) : 8;  // tuning knob
     if (L.W <= 64)
-        launch_mfe3_t<64, 4, 6>(L, d_tab, n_sm, stream);
+        launch_mfe3_t<64, 4, 4>(L, d_tab, n_sm, stream);
+    else if (nw == 4)
+        launch_mfe3_t<120, 4, 2>(L, d_tab, n_sm, stream);
     else
-        launch_mfe3_t<120, 4, 3>(L, d_tab, n_sm, stream);
+        launch_mfe3_t<120, 8, 2>(L, d_tab, n_sm, stream);
     if (n_launches) (*n_launches)++;
 }
 
