@@ -61,7 +61,7 @@ Tab3 *g_dtab3 = nullptr;
 bool g_mfe3_ok = false;
 
 constexpr int BIG = 1 << 20;  // size term of a disabled tap: the sum never wins whatever the load returns
-constexpr int KSMAX = 4;      // the split loop of a tile diagonal is cut into at most 4 work items
+constexpr int KSMAX = 2;      // the split loop of a tile diagonal is cut into at most 2 work items
 
 template <int P>
 struct Smem3 {
@@ -74,16 +74,16 @@ struct Smem3 {
     short ne[R32 * PR], no[R32 * PR], m8[R32 * PR], r1[R32 * PR], rb[R32 * PR];
     short g[R16 * PR];
     short rc[R16 * PR];
-    short dml[4 * PR];
     short padrow[PR + 38];
     short fm[P * P];          // fm[a][b]: FML[a,b] for b > a (row = 5' end), FML[b,a] for b < a (row = 3' end)
     short decp[KSMAX * 8 * PR];
-    short part[2 * 2 * PR];
+    short partc[4 * PR], parts[4 * PR];   // partial minima by diagonal & 3: loops of size >= 2 / everything else
     short f5[P + 8];
-    alignas(16) int list[(2 * PR + 8) * 4];     // per pairable cell: i, mismatchI / mismatch1nI / TerminalAU term of the closing pair
+    alignas(16) int list[(4 * PR + 32) * 4];     // per pairable cell: i, mismatchI / mismatch1nI / TerminalAU term of the closing pair
     unsigned char ctx[R16 * PR];
     unsigned char sx[P + 8];   // sx[k+1] = code of nucleotide k, sx[0] = sx[W+1] = 5
-    int cnt[2];
+    int cnt[4];
+    int ctr[2];
     int minv[32];
     int fbest[32];
 };
@@ -92,7 +92,9 @@ __host__ __device__ __forceinline__ int tri4(int d, int W) {  // first cell of d
     return (d - 4) * W - ((d - 1) * d / 2 - 6);
 }
 
-__host__ __device__ __forceinline__ int ksplit(int D) { return D < 36 ? 1 : (D < 72 ? 2 : 4); }
+// work units the split loop of tile diagonal D is cut into (long diagonals have few tiles: their k range is
+// split over the lanes of one warp instead)
+__host__ __device__ __forceinline__ int ksplit(int D, int W) { return (D < 36 || (W - 1 - D) / 2 + 1 <= 16) ? 1 : 2; }
 
 __device__ int hairpin_special3(const MfeTables *T, const Tab3 &tb, const unsigned char *sx, int i, int j, int type) {
     // loops of 3, 4 and 6 nucleotides: tabulated tri- / tetra- / hexaloops; sx is offset by one
@@ -144,7 +146,7 @@ mfe3_kernel(MfeLaunch L, const MfeTables *__restrict__ T, const Tab3 *__restrict
     short *gC = reinterpret_cast<short *>(L.gscratch) + (size_t)blockIdx.x * L.gscratch_per_cta;
     const short *smb = sm.ne;   // every tap address below is an offset (in shorts) from here
     constexpr int O_NE = 0, O_NO = R32 * PR, O_M8 = 2 * R32 * PR, O_R1 = 3 * R32 * PR, O_RB = 4 * R32 * PR,
-                  O_G = 5 * R32 * PR, O_PAD = 5 * R32 * PR + 2 * R16 * PR + 4 * PR;
+                  O_G = 5 * R32 * PR, O_PAD = 5 * R32 * PR + 2 * R16 * PR;
 
     // ---- per-lane loop size U = lane: size terms of its nine taps (see the header); BIG disables a tap
     const int U = lane;
@@ -157,10 +159,10 @@ mfe3_kernel(MfeLaunch L, const MfeTables *__restrict__ T, const Tab3 *__restrict
     const int cB26 = (uok && U > 27) ? c3_cap[U] : BIG;
     const int cC = !uok ? BIG : (U == 6 ? c3_sG6[2] : ((U == 9 || U == 10 || U > 11) ? c3_cap[U] : BIG));
 
-    // compacted list of the pairable cells of diagonal d with the closing-pair terms (one warp)
-    auto build_list = [&](int slot, int d) {
+    // compacted list of the pairable cells of diagonal d with the closing-pair terms (one warp) -> slot d & 3
+    auto build_list = [&](int d) {
         int nl = 0;
-        const int ncells = W - d;
+        const int ncells = W - d, slot = d & 3;
         for (int i0 = 0; i0 < ncells; i0 += 32) {
             const int i = i0 + lane;
             const int t = i < ncells ? tb.ptype[sx[i + 1] * 6 + sx[i + d + 1]] : 0;
@@ -174,6 +176,59 @@ mfe3_kernel(MfeLaunch L, const MfeTables *__restrict__ T, const Tab3 *__restrict
         }
         if (lane == 0) sm.cnt[slot] = nl;
     };
+    // split minimum of cell (xi, d): which tile diagonal produced it decides how many partials exist
+    auto decof = [&](int d, int xi) {
+        if (d < 2 * TURN + 3) return INF16;
+        const int Dsrc = (d & 1) ? ((xi & 1) ? d + 1 : d - 1) : d;
+        const int ks = ksplit(Dsrc, W);
+        int v = sm.decp[(d & 7) * PR + xi];
+        for (int kp = 1; kp < ks; kp++) v = min(v, (int)sm.decp[(kp * 8 + (d & 7)) * PR + xi]);
+        return v;
+    };
+    // table-driven shapes, hairpin and multiloop closing of the pairable cells of diagonal d, list chunk c (lane = cell)
+    auto do_special = [&](int d, int c) {
+        const int slot = d & 3, n = sm.cnt[slot];
+        const int idx = c * 32 + lane;
+        const bool active = idx < n;
+        const int i = active ? sm.list[(slot * PR + idx) * 4] : 0;
+        const int j = i + d;
+        const int type = tb.ptype[sx[i + 1] * 6 + sx[j + 1]];
+        const int si1 = sx[i + 2], sj1 = sx[j];
+        const int mi = (type * 5 + si1) * 5 + sj1;
+        int aT = INF16;
+        auto inner = [&](int u1, int u2, int &cc, int &t2, int &sp1, int &sq1) {
+            const int dd = d - 2 - u1 - u2, p = i + 1 + u1, q = j - 1 - u2;
+            const bool ok = dd > TURN;
+            cc = ok ? sm.rc[(dd & (R16 - 1)) * PR + p] : INF16;
+            t2 = ok ? sm.ctx[(dd & (R16 - 1)) * PR + p] : 0;
+            sp1 = sx[p];       // S[p-1]
+            sq1 = sx[q + 2];   // S[q+1]
+        };
+        int cc, t2, sp1, sq1;
+        inner(0, 0, cc, t2, sp1, sq1);
+        aT = min(aT, cc + tb.stack[type * 8 + t2]);
+        inner(0, 1, cc, t2, sp1, sq1);
+        aT = min(aT, cc + tb.bulge1 + tb.stack[type * 8 + t2]);
+        inner(1, 0, cc, t2, sp1, sq1);
+        aT = min(aT, cc + tb.bulge1 + tb.stack[type * 8 + t2]);
+        inner(1, 1, cc, t2, sp1, sq1);
+        aT = min(aT, cc + __ldg(&T->int11[type][t2][si1][sj1]));
+        inner(1, 2, cc, t2, sp1, sq1);
+        aT = min(aT, cc + __ldg(&T->int21[type][t2][si1][sq1][sj1]));
+        inner(2, 1, cc, t2, sp1, sq1);
+        aT = min(aT, cc + __ldg(&T->int21[t2][type][sq1][si1][sp1]));
+        inner(2, 2, cc, t2, sp1, sq1);
+        aT = min(aT, cc + __ldg(&T->int22[type][t2][si1][sp1][sq1][sj1]));
+        inner(2, 3, cc, t2, sp1, sq1);
+        aT = min(aT, cc + tb.il5_ninio + tb.mm23[mi] + tb.mm23[(t2 * 5 + sq1) * 5 + sp1]);
+        inner(3, 2, cc, t2, sp1, sq1);
+        aT = min(aT, cc + tb.il5_ninio + tb.mm23[mi] + tb.mm23[(t2 * 5 + sq1) * 5 + sp1]);
+        int eh = __ldg(&T->hairpin_len[d - 1]) + tb.mmH[mi];
+        if (d <= 7 && active) eh = hairpin_special3(T, tb, sx, i, j, type);
+        const int dm = decof(d - 2, i + 1);
+        const int res = min(min(aT, eh), dm + tb.mlclose[(tb.rtype[type] * 5 + sj1) * 5 + si1]);
+        if (active) sm.parts[slot * PR + i] = (short)min(res, INF16);
+    };
 
     for (int fold = blockIdx.x; fold < L.n_fold; fold += gridDim.x) {
         __syncthreads();
@@ -185,126 +240,88 @@ mfe3_kernel(MfeLaunch L, const MfeTables *__restrict__ T, const Tab3 *__restrict
             int4 *p = reinterpret_cast<int4 *>(sm.ne);
             constexpr int n16 = (int)((offsetof(SM, decp) - offsetof(SM, ne) + 15) / 16);   // a ragged tail spills
             for (int k = tid; k < n16; k += NT) p[k] = inf4;                                 // into decp (rewritten before use)
+            for (int k = tid; k < 4 * PR; k += NT) sm.partc[k] = INF16;   // diagonals 4, 5 have no interior loops
+            if (tid < 2) sm.ctr[tid] = 0;
         }
         int minv = 0;
         __syncthreads();
-        if (warp < 2) build_list(warp, TURN + 1 + warp);
+        if (warp < 4) build_list(TURN + 1 + warp);
+        __syncthreads();
+        for (int it = warp; it < 8; it += NW) {   // the other terms of diagonals 4, 5 (at most 4 chunks each)
+            const int d = TURN + 1 + (it >> 2), c = it & 3;
+            if (d < W && c * 32 < sm.cnt[d & 3]) do_special(d, c);
+        }
         __syncthreads();
 
         for (int d0 = TURN + 1; d0 < W; d0 += 2) {
             const int nd = d0 + 1 < W ? 2 : 1;
-            // =================== phase 1a: interior loops of size >= 2, one pairable cell per warp pass ==========
+            // =================== phase X: statically balanced work units ================================
+            //   S  C and the derived rows of diagonals d0, d0+1 (25 row elements per unit)
+            //   T  split minima of tile diagonal d0+2 (2x2 tiles, packed)
+            //   L  lists of diagonals d0+4, d0+5
+            //   C  interior loops of size >= 2 of the pairable cells of diagonals d0+2, d0+3 (two cells per unit)
             {
-                const int ds = warp >= NWH ? 1 : 0, wc = ds ? warp - NWH : warp;
-                const int d = d0 + ds;
-                const int n = ds < nd ? sm.cnt[ds] : 0;
-                if (wc < n) {
-                    const int s32 = ((d - 2 - U) & (R32 - 1)) * PR, s16 = ((d - 2 - U) & (R16 - 1)) * PR;
-                    const int oL = O_RB + s32, oR = O_RB + s32 + U;
-                    int oA = O_PAD, oB = O_PAD, oC = O_PAD;
-                    if (uok) {
-                        if (U == 6) {
-                            oA = O_G + s16 + 3;
-                            oB = O_G + s16 + 4 - 10;
-                            oC = O_G + s16 + 5;
-                        } else if (U >= 7) {
-                            oA = ((U & 1) ? O_NO : O_NE) + s32 + 3 + (U >> 1);
-                            if (U == 9 || U == 10) {
-                                oB = O_G + s16 + 3 - 10;
-                                oC = O_G + s16 + U - 1;
-                            } else if (U >= 11) {
-                                oB = O_M8 + s32;
-                                oC = O_M8 + s32 + (U > 11 ? U - 1 : 10);
-                            }
-                        }
-                    }
-                    const int4 *lst = reinterpret_cast<const int4 *>(sm.list) + ds * PR;
-                    const short *qL = smb + oL, *qR = smb + oR, *qA = smb + oA, *qB = smb + oB, *qC = smb + oC;
-                    short *qP = sm.part + ds * PR;
-                    int4 en = lst[wc];
-                    for (int k = wc; k < n; k += NWH) {
-                        const int i = en.x, eI = en.y, e1 = en.z, eB = en.w;
-                        en = lst[k + NWH];   // next entry (at most NWH past the list end: still inside sm.list)
-                        const short *pl = qL + i, *pr = qR + i, *pa = qA + i, *pb = qB + i, *pc = qC + i;
-                        const int xbl = pl[1], x1l = pl[O_R1 - O_RB + 2];
-                        const int xbr = pr[1], x1r = pr[O_R1 - O_RB];
-                        const int xa = pa[0], xb10 = pb[10], xb18 = pb[18], xb26 = pb[26], xc = pc[0];
-                        int g = xa + cA;
-                        g = __viaddmin_s32(xb10, cB10, g);
-                        int g2 = xb18 + cB18;
-                        g2 = __viaddmin_s32(xb26, cB26, g2);
-                        g = __viaddmin_s32(xc, cC, g);
-                        const int aB = min(xbl, xbr) + cSB, a1 = min(x1l, x1r) + cS1;
-                        int v = min(g, g2) + eI;
-                        v = __viaddmin_s32(a1, e1, v);
-                        v = __viaddmin_s32(aB, eB, v);
-                        v = __reduce_min_sync(full, v);
-                        if (lane == 0) qP[i] = (short)v;   // <= INF16 + size and mismatch terms: fits
-                    }
-                }
-            }
-            // =================== phase 1b: table-driven shapes / hairpin / multiloop closing (lane = cell) and
-            //                     the split minima of tile diagonal d0+2 (lane = 2x2 tile) as work items ===========
-            {
-                const int n0 = sm.cnt[0], n1 = nd == 2 ? sm.cnt[1] : 0;
-                const int nch0 = (n0 + 31) >> 5, nch = nch0 + ((n1 + 31) >> 5);
+                const int nseg0 = (W - d0 + SEG - 1) / SEG, nS = nseg0 + (nd == 2 ? (W - d0 - 1 + SEG - 1) / SEG : 0);
                 const int D = d0 + 2;
                 const int ntile = D <= W - 1 ? (W - 1 - D) / 2 + 1 : 0;
-                const int KS = ksplit(D), ksh = KS >> 1 /* log2 of 1, 2, 4 */, ngrp = (ntile + 31) >> 5;
-                const int nitem = nch + ngrp * KS;
-                for (int it = NW - 1 - warp; it < nitem; it += NW) {
-                    if (it < nch) {
-                        const int ds = it >= nch0 ? 1 : 0, c = ds ? it - nch0 : it;
-                        const int d = d0 + ds, n = ds ? n1 : n0;
-                        const int idx = c * 32 + lane;
-                        const bool active = idx < n;
-                        const int i = active ? sm.list[(ds * PR + idx) * 4] : 0;
-                        const int j = i + d;
-                        const int type = tb.ptype[sx[i + 1] * 6 + sx[j + 1]];
-                        const int si1 = sx[i + 2], sj1 = sx[j];
-                        const int mi = (type * 5 + si1) * 5 + sj1;
-                        int aT = INF16;
-                        auto inner = [&](int u1, int u2, int &cc, int &t2, int &sp1, int &sq1) {
-                            const int dd = d - 2 - u1 - u2, p = i + 1 + u1, q = j - 1 - u2;
-                            const bool ok = dd > TURN;
-                            cc = ok ? sm.rc[(dd & (R16 - 1)) * PR + p] : INF16;
-                            t2 = ok ? sm.ctx[(dd & (R16 - 1)) * PR + p] : 0;
-                            sp1 = sx[p];       // S[p-1]
-                            sq1 = sx[q + 2];   // S[q+1]
-                        };
-                        int cc, t2, sp1, sq1;
-                        inner(0, 0, cc, t2, sp1, sq1);
-                        aT = min(aT, cc + tb.stack[type * 8 + t2]);
-                        inner(0, 1, cc, t2, sp1, sq1);
-                        aT = min(aT, cc + tb.bulge1 + tb.stack[type * 8 + t2]);
-                        inner(1, 0, cc, t2, sp1, sq1);
-                        aT = min(aT, cc + tb.bulge1 + tb.stack[type * 8 + t2]);
-                        inner(1, 1, cc, t2, sp1, sq1);
-                        aT = min(aT, cc + __ldg(&T->int11[type][t2][si1][sj1]));
-                        inner(1, 2, cc, t2, sp1, sq1);
-                        aT = min(aT, cc + __ldg(&T->int21[type][t2][si1][sq1][sj1]));
-                        inner(2, 1, cc, t2, sp1, sq1);
-                        aT = min(aT, cc + __ldg(&T->int21[t2][type][sq1][si1][sp1]));
-                        inner(2, 2, cc, t2, sp1, sq1);
-                        aT = min(aT, cc + __ldg(&T->int22[type][t2][si1][sp1][sq1][sj1]));
-                        inner(2, 3, cc, t2, sp1, sq1);
-                        aT = min(aT, cc + tb.il5_ninio + tb.mm23[mi] + tb.mm23[(t2 * 5 + sq1) * 5 + sp1]);
-                        inner(3, 2, cc, t2, sp1, sq1);
-                        aT = min(aT, cc + tb.il5_ninio + tb.mm23[mi] + tb.mm23[(t2 * 5 + sq1) * 5 + sp1]);
-                        int eh = __ldg(&T->hairpin_len[d - 1]) + tb.mmH[mi];
-                        if (d <= 7 && active) eh = hairpin_special3(T, tb, sx, i, j, type);
-                        const int dm = sm.dml[((d - 2) & 3) * PR + i + 1];
-                        const int res = min(min(aT, eh), dm + tb.mlclose[(tb.rtype[type] * 5 + sj1) * 5 + si1]);
-                        if (active) sm.part[(2 + ds) * PR + i] = (short)min(res, INF16);
-                    } else {
-                        // 2x2 tile (i, i+1) x (j, j+1), i and j even, j - i = D: all four split minima share their
-                        // operands; both operand pairs are one aligned 32-bit load from the square matrix
-                        const int q = it - nch, grp = q >> ksh, kp = q & (KS - 1);
-                        const int tl = grp * 32 + lane;
+                const int KS = ksplit(D, W), ksh = KS >> 1 /* log2 of 1, 2, 4 */;
+                const int kwsh = ntile > 16 ? 0 : (ntile > 8 ? 1 : 2), TPW = 32 >> kwsh;   // k parts inside a warp
+                const int nT = ((ntile + TPW - 1) >> (5 - kwsh)) << ksh;
+                const int n2 = d0 + 2 < W ? sm.cnt[(d0 + 2) & 3] : 0, n3 = d0 + 3 < W ? sm.cnt[(d0 + 3) & 3] : 0;
+                const int uT = nS, uL = uT + nT, nH = uL + 2;   // heavy units: S, T, L (about three cells' worth each)
+                for (int u = warp; u < nH; u += NW) {
+                    if (u < uT) {
+                        // ---- S
+                        const int ds = u >= nseg0 ? 1 : 0, sg = ds ? u - nseg0 : u;
+                        const int d = d0 + ds, ncells = W - d;
+                        const int x = sg * SEG - 7 + lane;
+                        const bool valid = x >= 0 && x < ncells;
+                        const int i = valid ? x : 0, j = i + d;
+                        const int t = valid ? tb.ptype[sx[i + 1] * 6 + sx[j + 1]] : 0;
+                        int e = INF16;
+                        if (t) {
+                            e = min((int)sm.partc[(d & 3) * PR + i], (int)sm.parts[(d & 3) * PR + i]);
+                            if (e >= FIN16) e = INF16;
+                        }
+                        int vg = INF16, v1 = INF16, vb = INF16;
+                        const int t2 = tb.rtype[t];
+                        if (t && i > 0 && j < W - 1 && e < FIN16) {
+                            const int m2 = (t2 * 5 + sx[j + 2]) * 5 + sx[i];
+                            vg = e + tb.mmI[m2];
+                            v1 = e + tb.mm1n[m2];
+                            vb = e + tb.tAU[t2];
+                        }
+                        const int g1 = __shfl_up_sync(full, vg, 1), g2 = __shfl_up_sync(full, vg, 2);
+                        const int g3 = __shfl_up_sync(full, vg, 3), g4 = __shfl_up_sync(full, vg, 4);
+                        const int ne = min(g2, min(min(g1, g3) + tb.w2, min(vg, g4) + tb.w4));
+                        const int no = min(min(g1, g2) + tb.w1, min(vg, g3) + tb.w3);
+                        int m8 = min(vg, g1);
+                        m8 = min(m8, __shfl_up_sync(full, m8, 2));
+                        m8 = min(m8, __shfl_up_sync(full, m8, 4));
+                        if (valid && lane >= 7) {
+                            minv = min(minv, e);
+                            const int o16 = (d & (R16 - 1)) * PR + i, o32 = (d & (R32 - 1)) * PR + i;
+                            sm.rc[o16] = (short)e;
+                            sm.ctx[o16] = (unsigned char)t2;
+                            sm.g[o16] = (short)vg;
+                            sm.r1[o32] = (short)v1;
+                            sm.rb[o32] = (short)vb;
+                            sm.ne[o32] = (short)ne;
+                            sm.no[o32] = (short)no;
+                            sm.m8[o32] = (short)m8;
+                            gC[tri4(d, W) + i] = (short)(e < FIN16 ? e + tb.ext[t * 36 + sx[i] * 6 + sx[j + 2]] : INF16);
+                        }
+                    } else if (u < uL) {
+                        // ---- T: 2x2 tile (i, i+1) x (j, j+1), i and j even, j - i = D: all four split minima share
+                        // their operands; both operand pairs are one aligned 32-bit load from the square matrix.
+                        // Lanes = tiles x k parts; further k parts are separate units (partials in decp).
+                        const int q = u - uT, grp = q >> ksh, kp = q & (KS - 1);
+                        const int tl = grp * TPW + (lane & (TPW - 1)), kq = lane >> (5 - kwsh);
                         const bool valid = tl < ntile;
                         const int i = 2 * min(tl, ntile - 1), j = i + D;
                         const int cntk = D - 7;   // k = i+4 .. j-4; the band |a-b| < 4 of fm stays INF
-                        const int k0 = i + 4 + ((cntk * kp) >> ksh), k1 = i + 4 + ((cntk * (kp + 1)) >> ksh);
+                        const int pidx = (kp << kwsh) + kq, psh = ksh + kwsh;
+                        const int k0 = i + 4 + ((cntk * pidx) >> psh), k1 = i + 4 + ((cntk * (pidx + 1)) >> psh);
                         const unsigned *pa = reinterpret_cast<const unsigned *>(sm.fm + k0 * P + i);
                         const unsigned *pb = reinterpret_cast<const unsigned *>(sm.fm + (k0 + 1) * P + j);
                         unsigned acc0 = INF16 * 65537u, acc1 = INF16 * 65537u;
@@ -322,7 +339,15 @@ mfe3_kernel(MfeLaunch L, const MfeTables *__restrict__ T, const Tab3 *__restrict
                             acc0 = __viaddmin_s16x2(a, __byte_perm(b, 0, 0x1010), acc0);
                             acc1 = __viaddmin_s16x2(a, __byte_perm(b, 0, 0x3232), acc1);
                         }
-                        if (valid) {
+                        if (kwsh >= 1) {
+                            acc0 = __vmins2(acc0, __shfl_xor_sync(full, acc0, 16));
+                            acc1 = __vmins2(acc1, __shfl_xor_sync(full, acc1, 16));
+                        }
+                        if (kwsh == 2) {
+                            acc0 = __vmins2(acc0, __shfl_xor_sync(full, acc0, 8));
+                            acc1 = __vmins2(acc1, __shfl_xor_sync(full, acc1, 8));
+                        }
+                        if (valid && kq == 0) {
                             auto fin = [](int v) { return (short)(v >= FIN16 ? INF16 : v); };
                             short *dp = sm.decp + kp * 8 * PR;
                             dp[(D & 7) * PR + i] = fin((short)(acc0 & 0xffffu));
@@ -332,104 +357,106 @@ mfe3_kernel(MfeLaunch L, const MfeTables *__restrict__ T, const Tab3 *__restrict
                                 dp[(D & 7) * PR + i + 1] = fin((int)acc1 >> 16);
                             }
                         }
+                    } else {
+                        build_list(d0 + 4 + (u - uL));
+                    }
+                }
+                // ---- C: one pairable cell per pass; lane = loop size U with its nine taps (see the header).
+                // The cells continue the round robin of the heavy units, so the warps that got one unit fewer start.
+                {
+                    int c = warp - nH % NW;
+                    if (c < 0) c += NW;
+#pragma unroll 1
+                    for (int ds = 0; ds < 2; ds++) {
+                        const int d = d0 + 2 + ds, n = ds ? n3 : n2;
+                        if (c < n) {
+                            const int s32 = ((d - 2 - U) & (R32 - 1)) * PR, s16 = ((d - 2 - U) & (R16 - 1)) * PR;
+                            int oA = O_PAD, oB = O_PAD, oC = O_PAD;
+                            if (uok) {
+                                if (U == 6) {
+                                    oA = O_G + s16 + 3;
+                                    oB = O_G + s16 + 4 - 10;
+                                    oC = O_G + s16 + 5;
+                                } else if (U >= 7) {
+                                    oA = ((U & 1) ? O_NO : O_NE) + s32 + 3 + (U >> 1);
+                                    if (U == 9 || U == 10) {
+                                        oB = O_G + s16 + 3 - 10;
+                                        oC = O_G + s16 + U - 1;
+                                    } else if (U >= 11) {
+                                        oB = O_M8 + s32;
+                                        oC = O_M8 + s32 + (U > 11 ? U - 1 : 10);
+                                    }
+                                }
+                            }
+                            const short *qL = smb + O_RB + s32, *qR = smb + O_RB + s32 + U;
+                            const short *qA = smb + oA, *qB = smb + oB, *qC = smb + oC;
+                            short *qP = sm.partc + (d & 3) * PR;
+                            const int4 *lst = reinterpret_cast<const int4 *>(sm.list) + (d & 3) * PR;
+                            int4 en = lst[c];
+                            for (; c < n; c += NW) {
+                                const int i = en.x, eI = en.y, e1 = en.z, eB = en.w;
+                                en = lst[c + NW];   // next entry (at most NW past the list end: still inside sm.list)
+                                const short *pl = qL + i, *pr = qR + i, *pa = qA + i, *pb = qB + i, *pc = qC + i;
+                                const int xbl = pl[1], x1l = pl[O_R1 - O_RB + 2];
+                                const int xbr = pr[1], x1r = pr[O_R1 - O_RB];
+                                const int xa = pa[0], xb10 = pb[10], xb18 = pb[18], xb26 = pb[26], xc = pc[0];
+                                int g = xa + cA;
+                                g = __viaddmin_s32(xb10, cB10, g);
+                                int g2 = xb18 + cB18;
+                                g2 = __viaddmin_s32(xb26, cB26, g2);
+                                g = __viaddmin_s32(xc, cC, g);
+                                const int aB = min(xbl, xbr) + cSB, a1 = min(x1l, x1r) + cS1;
+                                int v = min(g, g2) + eI;
+                                v = __viaddmin_s32(a1, e1, v);
+                                v = __viaddmin_s32(aB, eB, v);
+                                v = __reduce_min_sync(full, v);
+                                if (lane == 0) qP[i] = (short)v;   // <= INF16 + size and mismatch terms: fits
+                            }
+                        }
+                        c -= n;
                     }
                 }
             }
             __syncthreads();
-            // =================== phase 2: lists of the next diagonal pair (two warps) ===========================
-            if (warp >= NW - 2) build_list(warp - (NW - 2), d0 + 2 + warp - (NW - 2));
-            // ---- C and the derived rows of diagonals d0, d0+1 (25 row elements per warp pass)
-            {
-                const int nseg0 = (W - d0 + SEG - 1) / SEG, nseg = nseg0 + (nd == 2 ? (W - d0 - 1 + SEG - 1) / SEG : 0);
-                for (int un = NW - 1 - warp; un < nseg; un += NW) {
-                    const int ds = un >= nseg0 ? 1 : 0, sg = ds ? un - nseg0 : un;
-                    const int d = d0 + ds, ncells = W - d;
-                    const int x = sg * SEG - 7 + lane;
-                    const bool valid = x >= 0 && x < ncells;
-                    const int i = valid ? x : 0, j = i + d;
-                    const int t = valid ? tb.ptype[sx[i + 1] * 6 + sx[j + 1]] : 0;
-                    int e = INF16;
-                    if (t) {
-                        e = min((int)sm.part[ds * PR + i], (int)sm.part[(2 + ds) * PR + i]);
-                        if (e >= FIN16) e = INF16;
-                    }
-                    int vg = INF16, v1 = INF16, vb = INF16;
-                    const int t2 = tb.rtype[t];
-                    if (t && i > 0 && j < W - 1 && e < FIN16) {
-                        const int m2 = (t2 * 5 + sx[j + 2]) * 5 + sx[i];
-                        vg = e + tb.mmI[m2];
-                        v1 = e + tb.mm1n[m2];
-                        vb = e + tb.tAU[t2];
-                    }
-                    const int g1 = __shfl_up_sync(full, vg, 1), g2 = __shfl_up_sync(full, vg, 2);
-                    const int g3 = __shfl_up_sync(full, vg, 3), g4 = __shfl_up_sync(full, vg, 4);
-                    const int ne = min(g2, min(min(g1, g3) + tb.w2, min(vg, g4) + tb.w4));
-                    const int no = min(min(g1, g2) + tb.w1, min(vg, g3) + tb.w3);
-                    int m8 = min(vg, g1);
-                    m8 = min(m8, __shfl_up_sync(full, m8, 2));
-                    m8 = min(m8, __shfl_up_sync(full, m8, 4));
-                    if (valid && lane >= 7) {
-                        minv = min(minv, e);
-                        const int o16 = (d & (R16 - 1)) * PR + i, o32 = (d & (R32 - 1)) * PR + i;
-                        sm.rc[o16] = (short)e;
-                        sm.ctx[o16] = (unsigned char)t2;
-                        sm.g[o16] = (short)vg;
-                        sm.r1[o32] = (short)v1;
-                        sm.rb[o32] = (short)vb;
-                        sm.ne[o32] = (short)ne;
-                        sm.no[o32] = (short)no;
-                        sm.m8[o32] = (short)m8;
-                        gC[tri4(d, W) + i] = (short)(e < FIN16 ? e + tb.ext[t * 36 + sx[i] * 6 + sx[j + 2]] : INF16);
-                    }
-                }
-            }
-            // ---- multiloop matrix of both diagonals: 31 cells per warp, the neighbour on d0 comes by shuffle
+            // =================== phase Y: multiloop matrix of diagonals d0, d0+1 (31 cells per warp, the neighbour
+            //                     on d0 comes by shuffle) and the remaining terms of diagonals d0+2, d0+3 ===========
             {
                 const int nc0 = W - d0, nc1 = nd == 2 ? W - d0 - 1 : 0;
                 if (warp * 31 < nc0) {
                     const int x = warp * 31 + lane;
                     const bool v0 = x < nc0;
                     const int xx = v0 ? x : nc0 - 1;
-                    // split minimum of cell (xx, d): which tile diagonal produced it decides how many partials exist
-                    auto decof = [&](int d, int xi) {
-                        if (d < 2 * TURN + 3) return INF16;
-                        const int Dsrc = (d & 1) ? ((xi & 1) ? d + 1 : d - 1) : d;
-                        const int ks = ksplit(Dsrc);
-                        int v = sm.decp[(d & 7) * PR + xi];
-                        for (int kp = 1; kp < ks; kp++) v = min(v, (int)sm.decp[(kp * 8 + (d & 7)) * PR + xi]);
-                        return v;
-                    };
-                    auto stemof = [&](int ds, int d, int xi) {
-                        const int j = xi + d;
-                        const int t = tb.ptype[sx[xi + 1] * 6 + sx[j + 1]];
-                        if (!t) return INF16;
-                        const int e = min((int)sm.part[ds * PR + xi], (int)sm.part[(2 + ds) * PR + xi]);
-                        return e < FIN16 ? e + tb.mlstem[t * 36 + sx[xi] * 6 + sx[j + 2]] : INF16;
+                    auto stemof = [&](int d, int xi) {
+                        const int o16 = (d & (R16 - 1)) * PR + xi;
+                        const int e = sm.rc[o16];
+                        const int t = tb.rtype[sm.ctx[o16]];
+                        return e < FIN16 ? e + tb.mlstem[t * 36 + sx[xi] * 6 + sx[xi + d + 2]] : INF16;
                     };
                     const int dec0 = decof(d0, xx);
-                    int m0 = min(dec0, stemof(0, d0, xx));
+                    int m0 = min(dec0, stemof(d0, xx));
                     if (d0 - 1 > TURN)
                         m0 = min(m0, min((int)sm.fm[(xx + 1) * P + xx + d0], (int)sm.fm[xx * P + xx + d0 - 1]) + tb.MLbase);
                     if (m0 >= FIN16) m0 = INF16;
                     if (v0) {
                         minv = min(minv, m0);
-                        sm.dml[(d0 & 3) * PR + x] = (short)dec0;
                         sm.fm[x * P + x + d0] = (short)m0;
                         sm.fm[(x + d0) * P + x] = (short)m0;
                     }
                     const int m0n = __shfl_down_sync(full, m0, 1);
                     if (lane < 31 && x < nc1) {
                         const int d = d0 + 1;
-                        const int dec1 = decof(d, x);
-                        int m1 = min(dec1, stemof(1, d, x));
+                        int m1 = min(decof(d, x), stemof(d, x));
                         m1 = min(m1, min(m0, m0n) + tb.MLbase);
                         if (m1 >= FIN16) m1 = INF16;
                         minv = min(minv, m1);
-                        sm.dml[(d & 3) * PR + x] = (short)dec1;
                         sm.fm[x * P + x + d] = (short)m1;
                         sm.fm[(x + d) * P + x] = (short)m1;
                     }
                 }
+                const int n2 = d0 + 2 < W ? sm.cnt[(d0 + 2) & 3] : 0, n3 = d0 + 3 < W ? sm.cnt[(d0 + 3) & 3] : 0;
+                const int nch2 = (n2 + 31) >> 5, nch = nch2 + ((n3 + 31) >> 5);
+                for (int it = NW - 1 - warp; it < nch; it += NW)
+                    do_special(it < nch2 ? d0 + 2 : d0 + 3, it < nch2 ? it : it - nch2);
             }
             __syncthreads();
         }
@@ -567,6 +594,10 @@ void launch_mfe3(const MfeLaunch &L, const MfeTables *d_tab, int n_sm, cudaStrea
         launch_mfe3_t<64, 4, 4>(L, d_tab, n_sm, stream);
     else if (nw == 4)
         launch_mfe3_t<120, 4, 2>(L, d_tab, n_sm, stream);
+    else if (nw == 12)
+        launch_mfe3_t<120, 12, 2>(L, d_tab, n_sm, stream);
+    else if (nw == 16)
+        launch_mfe3_t<120, 16, 2>(L, d_tab, n_sm, stream);
     else
         launch_mfe3_t<120, 8, 2>(L, d_tab, n_sm, stream);
     if (n_launches) (*n_launches)++;
