@@ -86,6 +86,7 @@ void ensure_pf_tables(double temperature) {
     make_pf_tables(g_ctx.hp, temperature, host_pf);
     if (!g_ctx.d_pf) CK(cudaMalloc(&g_ctx.d_pf, sizeof(PfTables)));
     CK(cudaMemcpy(g_ctx.d_pf, &host_pf, sizeof(PfTables), cudaMemcpyHostToDevice));
+    pf2_upload_tables(host_pf);
     g_ctx.pf_temperature = temperature;
 }
 

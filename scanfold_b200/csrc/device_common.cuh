@@ -110,6 +110,12 @@ int mfe_grid_size(int W, int n_sm, int n_fold);
 void launch_pf(const PfLaunch &L, const MfeTables *d_mfe, const PfTables *d_pf, int n_sm, cudaStream_t stream,
                int *n_launches);
 size_t pf_scratch_doubles_per_cta(int W);
+// second-generation partition function (pf2.cu): unconstrained windows up to 120 nt, shared-memory resident
+bool pf2_supports(const PfLaunch &L);
+size_t pf2_scratch_doubles_per_cta();
+void pf2_upload_tables(const PfTables &q);
+void launch_pf2(const PfLaunch &L, const MfeTables *d_mfe, const PfTables *d_pf, int n_sm, cudaStream_t stream,
+                int *n_launches);
 int pf_grid_size(int W, int n_sm, int n_fold);
 
 constexpr int SHUFFLE_MONO = 0, SHUFFLE_DI = 1;

@@ -575,7 +575,10 @@ size_t pf_smem_bytes(int W) {
 
 }  // namespace
 
-size_t pf_scratch_doubles_per_cta(int W) { return 7 * ((size_t)W * (W + 1) / 2) + 3 * (size_t)PRING * W; }
+size_t pf_scratch_doubles_per_cta(int W) {
+    const size_t a = 7 * ((size_t)W * (W + 1) / 2) + 3 * (size_t)PRING * W, b = pf2_scratch_doubles_per_cta();
+    return a > b ? a : b;
+}
 
 int pf_grid_size(int W, int n_sm, int n_fold) {
     long long g = (long long)n_sm * 4;
@@ -586,6 +589,10 @@ int pf_grid_size(int W, int n_sm, int n_fold) {
 void launch_pf(const PfLaunch &L, const MfeTables *d_mfe, const PfTables *d_pf, int n_sm, cudaStream_t stream,
                int *n_launches) {
     if (L.n_fold <= 0) return;
+    if (pf2_supports(L)) {   // unconstrained windows up to 120 nt: shared-memory kernel (pf2.cu)
+        launch_pf2(L, d_mfe, d_pf, n_sm, stream, n_launches);
+        return;
+    }
     size_t smem = pf_smem_bytes(L.W);
     static bool configured = false;
     if (!configured) {
