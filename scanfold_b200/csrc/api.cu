@@ -126,8 +126,8 @@ struct FoldWork {  // device scratch for one MFE launch
     }
     // energy-only unconstrained folds: int16 warp-per-fold kernel, then the int32 kernel on whatever it flagged
     void launch_energy_only(MfeLaunch L, cudaStream_t st, int *n_launch) const {
-        const bool use3 = engine() == 3 && mfe3_supports(L.W), use2 = engine() != 1 && mfe2_supports(L.W);
-        if ((use3 || use2) && !L.hc && !L.sc && L.max_span <= 0 && !L.pair_tbl) {
+        const bool use3 = engine() == 3 && mfe3_supports(L.W), use2 = engine() != 1 && mfe2_supports(L.W) && !L.pair_tbl;
+        if ((use3 || use2) && !L.hc && !L.sc && L.max_span <= 0) {   // mfe3 also traces the structure back
             MfeLaunch L2 = L;
             L2.gscratch = scratch2.p;
             L2.gscratch_per_cta = (long long)per_warp2;
@@ -553,8 +553,7 @@ int sfb_scan_plan_run(sfb_scan_plan *P, float *ms_total, float *ms_mfe, int32_t 
                 L.max_span = 0;
                 L.e_out = P->nat_unc.p + c0;
                 L.pair_tbl = need_unc ? nullptr : P->pair_tbl.p + (size_t)c0 * W;
-                P->fw.fill(L);
-                launch_mfe(L, g_ctx.d_mfe, g_ctx.n_sm, st, &n_launch);
+                P->fw.launch_energy_only(L, st, &n_launch);
             }
             // native fold with md / hc / sc and structure (ScanFold.py:494-497,512-513,534-541)
             if (need_unc && cn_regular > 0) {

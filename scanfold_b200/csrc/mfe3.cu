@@ -86,6 +86,7 @@ struct Smem3 {
     int ctr[2];
     int minv[32];
     int fbest[32];
+    int tbstk[3 * (P + 8)];   // traceback stack (natives only)
 };
 
 __host__ __device__ __forceinline__ int tri4(int d, int W) {  // first cell of diagonal d in the d >= 4 triangle
@@ -123,6 +124,182 @@ __device__ int hairpin_special3(const MfeTables *T, const Tab3 &tb, const unsign
         return e + tb.tAU[type];
     }
     return e + tb.mmH[(type * 5 + sx[i + 2]) * 5 + sx[j]];
+}
+
+
+// full interior-loop energy, all classes (traceback only)
+__device__ int e_intloop3(const MfeTables *T, int n1, int n2, int type, int t2, int si1, int sj1, int sp1, int sq1) {
+    const int nl = max(n1, n2), ns = min(n1, n2);
+    const int au = T->TerminalAU;
+    if (nl == 0) return T->stack[type][t2];
+    if (ns == 0) {
+        int e = T->bulge[nl];
+        if (nl == 1)
+            e += T->stack[type][t2];
+        else
+            e += (type > 2 ? au : 0) + (t2 > 2 ? au : 0);
+        return e;
+    }
+    if (ns == 1) {
+        if (nl == 1) return T->int11[type][t2][si1][sj1];
+        if (nl == 2) return n1 == 1 ? T->int21[type][t2][si1][sq1][sj1] : T->int21[t2][type][sq1][si1][sp1];
+        return T->internal_loop[nl + 1] + min(T->max_ninio, (nl - ns) * T->ninio) + T->mismatch1nI[type][si1][sj1] +
+               T->mismatch1nI[t2][sq1][sp1];
+    }
+    if (ns == 2) {
+        if (nl == 2) return T->int22[type][t2][si1][sp1][sq1][sj1];
+        if (nl == 3) return T->internal_loop[5] + T->ninio + T->mismatch23I[type][si1][sj1] + T->mismatch23I[t2][sq1][sp1];
+    }
+    return T->internal_loop[nl + ns] + min(T->max_ninio, (nl - ns) * T->ninio) + T->mismatchI[type][si1][sj1] +
+           T->mismatchI[t2][sq1][sp1];
+}
+
+// Traceback by one warp in the candidate order of SURVEY A.4 (the same order as mfe.cu's serial traceback): the
+// control flow is warp-uniform, every candidate search is spread over the lanes and the first match in order wins.
+// cx: C + exterior stem term by diagonal (the F5 staging area); pt: 1-based partner, 0 = unpaired.
+template <int P>
+__device__ bool traceback3(Smem3<P> &sm, const MfeTables *T, const short *cx, short *pt, int W, int lane) {
+    const Tab3 &tb = sm.tb;
+    const unsigned char *sx = sm.sx;
+    const unsigned full = 0xffffffffu;
+    int *stk = sm.tbstk;
+    auto ptype = [&](int a, int b) { return (int)tb.ptype[sx[a + 1] * 6 + sx[b + 1]]; };
+    auto CC = [&](int i, int j) {
+        const int v = cx[tri4(j - i, W) + i];
+        return v >= FIN16 ? INF : v - tb.ext[ptype(i, j) * 36 + sx[i] * 6 + sx[j + 2]];
+    };
+    auto MM = [&](int i, int j) {
+        if (j - i <= TURN) return INF;
+        const int v = sm.fm[i * P + j];
+        return v >= FIN16 ? INF : v;
+    };
+    for (int k = lane; k < W; k += 32) pt[k] = 0;
+    int sp = 1;
+    if (lane == 0) {
+        stk[0] = 0;
+        stk[1] = W - 1;
+        stk[2] = 0;
+    }
+    __syncwarp();
+    while (sp > 0) {
+        sp--;
+        int i = stk[3 * sp], j = stk[3 * sp + 1];
+        const int ml = stk[3 * sp + 2];
+        __syncwarp();
+        bool have_pair = false;
+        if (j < i + TURN + 1) continue;
+        const int fij = ml ? MM(i, j) : (int)sm.f5[j + 1];
+        const int mij1 = MM(i, j - 1);
+        const int fi = ml ? (mij1 < INF ? mij1 + tb.MLbase : INF) : (int)sm.f5[j];
+        auto push = [&](int a, int b, int c) {
+            if (lane == 0) {
+                stk[3 * sp] = a;
+                stk[3 * sp + 1] = b;
+                stk[3 * sp + 2] = c;
+            }
+            sp++;
+        };
+        if (fij == fi) {
+            push(i, j - 1, ml);
+            __syncwarp();
+            continue;
+        }
+        if (ml == 0) {
+            int kf = -1;
+            for (int k0 = j - TURN - 1; k0 >= 0 && kf < 0; k0 -= 32) {
+                const int k = k0 - lane;
+                bool hit = false;
+                if (k >= 0) {
+                    const int ckj = CC(k, j);
+                    hit = ckj < INF && fij == tb.ext[ptype(k, j) * 36 + sx[k] * 6 + sx[j + 2]] + ckj + sm.f5[k];
+                }
+                const unsigned m = __ballot_sync(full, hit);
+                if (m) kf = k0 - (__ffs(m) - 1);
+            }
+            if (kf < 0) return false;
+            push(0, kf - 1, 0);
+            i = kf;
+            have_pair = true;
+        } else {
+            const int mi1j = MM(i + 1, j);
+            if (mi1j < INF && mi1j + tb.MLbase == fij) {
+                push(i + 1, j, 1);
+                __syncwarp();
+                continue;
+            }
+            const int cij = CC(i, j);
+            if (cij < INF && fij == cij + tb.mlstem[ptype(i, j) * 36 + sx[i] * 6 + sx[j + 2]]) {
+                have_pair = true;
+            } else {
+                int kf = -1;
+                for (int k0 = i + 1 + TURN; k0 <= j - 2 - TURN && kf < 0; k0 += 32) {
+                    const int k = k0 + lane;
+                    bool hit = false;
+                    if (k <= j - 2 - TURN) {
+                        const int a = MM(i, k), b = MM(k + 1, j);
+                        hit = a < INF && b < INF && fij == a + b;
+                    }
+                    const unsigned m = __ballot_sync(full, hit);
+                    if (m) kf = k0 + __ffs(m) - 1;
+                }
+                if (kf < 0) return false;
+                push(i, kf, 1);
+                push(kf + 1, j, 1);
+                __syncwarp();
+                continue;
+            }
+        }
+        while (have_pair) {
+            if (lane == 0) {
+                pt[i] = (short)(j + 1);
+                pt[j] = (short)(i + 1);
+            }
+            const int type = ptype(i, j);
+            const int cij = CC(i, j);
+            if (cij == hairpin_special3(T, tb, sx, i, j, type)) break;
+            bool traced = false;
+            const int pmax = min(j - 2 - TURN, i + MAXLOOP + 1);
+            for (int p = i + 1; p <= pmax && !traced; p++) {
+                int minq = j - i + p - MAXLOOP - 2;
+                if (minq < p + 1 + TURN) minq = p + 1 + TURN;
+                const int q = j - 1 - lane;   // at most 31 candidates per p
+                bool hit = false;
+                if (q >= minq) {
+                    const int cpq = CC(p, q);
+                    if (cpq < INF) {
+                        const int t2 = tb.rtype[ptype(p, q)];
+                        const int e = e_intloop3(T, p - i - 1, j - q - 1, type, t2, sx[i + 2], sx[j], sx[p], sx[q + 2]);
+                        hit = cij == e + cpq;
+                    }
+                }
+                const unsigned m = __ballot_sync(full, hit);
+                if (m) {
+                    j = j - 1 - (__ffs(m) - 1);
+                    i = p;
+                    traced = true;
+                }
+            }
+            if (traced) continue;
+            const int en = cij - tb.mlclose[(tb.rtype[type] * 5 + sx[j]) * 5 + sx[i + 2]];
+            int kf = -1;
+            for (int k0 = i + 2 + TURN; k0 < j - 2 - TURN && kf < 0; k0 += 32) {
+                const int k = k0 + lane;
+                bool hit = false;
+                if (k < j - 2 - TURN) {
+                    const int a = MM(i + 1, k), b = MM(k + 1, j - 1);
+                    hit = a < INF && b < INF && en == a + b;
+                }
+                const unsigned m = __ballot_sync(full, hit);
+                if (m) kf = k0 + __ffs(m) - 1;
+            }
+            if (kf < 0) return false;
+            push(i + 1, kf, 1);
+            push(kf + 1, j - 1, 1);
+            break;
+        }
+        __syncwarp();
+    }
+    return true;
 }
 
 template <int P, int NW, int OCC>
@@ -491,10 +668,17 @@ mfe3_kernel(MfeLaunch L, const MfeTables *__restrict__ T, const Tab3 *__restrict
                 }
                 __syncthreads();
             }
-            if (tid == 0) {
-                int mv = sm.minv[0];
-                for (int q = 1; q < NW; q++) mv = min(mv, sm.minv[q]);
-                L.e_out[fold] = mv < LOW16 ? MFE_REDO : (int)sm.f5[W];
+            int mv = sm.minv[0];
+            for (int q = 1; q < NW; q++) mv = min(mv, sm.minv[q]);
+            if (tid == 0) L.e_out[fold] = mv < LOW16 ? MFE_REDO : (int)sm.f5[W];
+            if (L.pair_tbl && mv >= LOW16) {   // native folds: structure (CTA-uniform branch)
+                short *pt = sm.partc;
+                if (warp == 0) {
+                    const bool ok = traceback3<P>(sm, T, cx, pt, W, lane);
+                    if (!ok && lane == 0) L.e_out[fold] = MFE_REDO;   // the int32 kernel folds it again
+                }
+                __syncthreads();
+                for (int k = tid; k < W; k += NT) L.pair_tbl[(size_t)fold * W + k] = pt[k];
             }
         }
     }
