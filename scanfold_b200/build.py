@@ -7,7 +7,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libscanfold_b200.so")
 SOURCES = ["params.cpp", "mfe.cu", "mfe2.cu", "mfe3.cu", "pf.cu", "pf2.cu", "shuffle.cu", "accumulate.cu", "microbench.cu", "api.cu"]
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+EXTRA = os.environ.get("SFB_NVCC_EXTRA", "").split()
+NVCC_FLAGS = EXTRA + ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
 
 

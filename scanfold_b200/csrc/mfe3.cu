@@ -23,6 +23,7 @@
 // int16 storage is exact as long as no stored energy drops below LOW16; a fold that does is flagged and redone
 // by the int32 kernel (mfe.cu) in the same stream, so results never depend on which kernel ran.
 #include <cstddef>
+#include <cstdio>
 #include <cstdlib>
 
 #include "device_common.cuh"
@@ -87,6 +88,7 @@ struct Smem3 {
     int minv[32];
     int fbest[32];
     int tbstk[3 * (P + 8)];   // traceback stack (natives only)
+    alignas(16) int stepinfo[(P / 2 + 2) * 4];   // per diagonal pair: unit counts of the two phases (fold independent)
 };
 
 __host__ __device__ __forceinline__ int tri4(int d, int W) {  // first cell of diagonal d in the d >= 4 triangle
@@ -320,6 +322,17 @@ mfe3_kernel(MfeLaunch L, const MfeTables *__restrict__ T, const Tab3 *__restrict
     const Tab3 &tb = sm.tb;
     const unsigned char *sx = sm.sx;
     const int W = L.W;
+    for (int st = tid; TURN + 1 + 2 * st < W; st += NT) {
+        const int d0 = TURN + 1 + 2 * st, nd = d0 + 1 < W ? 2 : 1;
+        const int nseg0 = (W - d0 + SEG - 1) / SEG, nS = nseg0 + (nd == 2 ? (W - d0 - 1 + SEG - 1) / SEG : 0);
+        const int D = d0 + 2;
+        const int ntile = D <= W - 1 ? (W - 1 - D) / 2 + 1 : 0;
+        const int KS = ksplit(D, W), ksh = KS >> 1 /* log2 of 1, 2, 4 */;
+        const int kwsh = ntile > 16 ? 0 : (ntile > 8 ? 1 : 2), TPW = 32 >> kwsh;   // k parts inside a warp
+        const int nT = ((ntile + TPW - 1) >> (5 - kwsh)) << ksh;
+        reinterpret_cast<int4 *>(sm.stepinfo)[st] =
+            make_int4(nseg0 | (nS << 8), ntile | (ksh << 8) | (kwsh << 12), nT, (W - d0 + 30) / 31);
+    }
     short *gC = reinterpret_cast<short *>(L.gscratch) + (size_t)blockIdx.x * L.gscratch_per_cta;
     const short *smb = sm.ne;   // every tap address below is an offset (in shorts) from here
     constexpr int O_NE = 0, O_NO = R32 * PR, O_M8 = 2 * R32 * PR, O_R1 = 3 * R32 * PR, O_RB = 4 * R32 * PR,
@@ -382,29 +395,32 @@ mfe3_kernel(MfeLaunch L, const MfeTables *__restrict__ T, const Tab3 *__restrict
             sq1 = sx[q + 2];   // S[q+1]
         };
         int cc, t2, sp1, sq1;
-        inner(0, 0, cc, t2, sp1, sq1);
-        aT = min(aT, cc + tb.stack[type * 8 + t2]);
-        inner(0, 1, cc, t2, sp1, sq1);
-        aT = min(aT, cc + tb.bulge1 + tb.stack[type * 8 + t2]);
-        inner(1, 0, cc, t2, sp1, sq1);
-        aT = min(aT, cc + tb.bulge1 + tb.stack[type * 8 + t2]);
-        inner(1, 1, cc, t2, sp1, sq1);
-        aT = min(aT, cc + __ldg(&T->int11[type][t2][si1][sj1]));
-        inner(1, 2, cc, t2, sp1, sq1);
-        aT = min(aT, cc + __ldg(&T->int21[type][t2][si1][sq1][sj1]));
-        inner(2, 1, cc, t2, sp1, sq1);
-        aT = min(aT, cc + __ldg(&T->int21[t2][type][sq1][si1][sp1]));
-        inner(2, 2, cc, t2, sp1, sq1);
-        aT = min(aT, cc + __ldg(&T->int22[type][t2][si1][sp1][sq1][sj1]));
-        inner(2, 3, cc, t2, sp1, sq1);
-        aT = min(aT, cc + tb.il5_ninio + tb.mm23[mi] + tb.mm23[(t2 * 5 + sq1) * 5 + sp1]);
-        inner(3, 2, cc, t2, sp1, sq1);
-        aT = min(aT, cc + tb.il5_ninio + tb.mm23[mi] + tb.mm23[(t2 * 5 + sq1) * 5 + sp1]);
-        int eh = __ldg(&T->hairpin_len[d - 1]) + tb.mmH[mi];
-        if (d <= 7 && active) eh = hairpin_special3(T, tb, sx, i, j, type);
-        const int dm = decof(d - 2, i + 1);
-        const int res = min(min(aT, eh), dm + tb.mlclose[(tb.rtype[type] * 5 + sj1) * 5 + si1]);
-        if (active) sm.parts[slot * PR + i] = (short)min(res, INF16);
+        {
+            inner(0, 0, cc, t2, sp1, sq1);
+            aT = min(aT, cc + tb.stack[type * 8 + t2]);
+            inner(0, 1, cc, t2, sp1, sq1);
+            aT = min(aT, cc + tb.bulge1 + tb.stack[type * 8 + t2]);
+            inner(1, 0, cc, t2, sp1, sq1);
+            aT = min(aT, cc + tb.bulge1 + tb.stack[type * 8 + t2]);
+            inner(1, 1, cc, t2, sp1, sq1);
+            aT = min(aT, cc + __ldg(&T->int11[type][t2][si1][sj1]));
+            int eh = __ldg(&T->hairpin_len[d - 1]) + tb.mmH[mi];
+            if (d <= 7 && active) eh = hairpin_special3(T, tb, sx, i, j, type);
+            aT = min(aT, eh);
+            inner(1, 2, cc, t2, sp1, sq1);
+            aT = min(aT, cc + __ldg(&T->int21[type][t2][si1][sq1][sj1]));
+            inner(2, 1, cc, t2, sp1, sq1);
+            aT = min(aT, cc + __ldg(&T->int21[t2][type][sq1][si1][sp1]));
+            inner(2, 2, cc, t2, sp1, sq1);
+            aT = min(aT, cc + __ldg(&T->int22[type][t2][si1][sp1][sq1][sj1]));
+            inner(2, 3, cc, t2, sp1, sq1);
+            aT = min(aT, cc + tb.il5_ninio + tb.mm23[mi] + tb.mm23[(t2 * 5 + sq1) * 5 + sp1]);
+            inner(3, 2, cc, t2, sp1, sq1);
+            aT = min(aT, cc + tb.il5_ninio + tb.mm23[mi] + tb.mm23[(t2 * 5 + sq1) * 5 + sp1]);
+            const int dm = decof(d - 2, i + 1);
+            aT = min(aT, dm + tb.mlclose[(tb.rtype[type] * 5 + sj1) * 5 + si1]);
+        }
+        if (active) sm.parts[slot * PR + i] = (short)min(aT, INF16);
     };
 
     for (int fold = blockIdx.x; fold < L.n_fold; fold += gridDim.x) {
@@ -430,22 +446,24 @@ mfe3_kernel(MfeLaunch L, const MfeTables *__restrict__ T, const Tab3 *__restrict
         }
         __syncthreads();
 
+#ifdef SFB_TIMING
+        long long tX = 0, tXb = 0, tY = 0, tYb = 0, tc = clock64(), t0 = tc;
+#define TICK(acc) { long long tn = clock64(); acc += tn - tc; tc = tn; }
+#else
+#define TICK(acc)
+#endif
         for (int d0 = TURN + 1; d0 < W; d0 += 2) {
             const int nd = d0 + 1 < W ? 2 : 1;
             // =================== phase X: statically balanced work units ================================
             //   S  C and the derived rows of diagonals d0, d0+1 (25 row elements per unit)
             //   T  split minima of tile diagonal d0+2 (2x2 tiles, packed)
             //   L  lists of diagonals d0+4, d0+5
-            //   C  interior loops of size >= 2 of the pairable cells of diagonals d0+2, d0+3 (two cells per unit)
             {
-                const int nseg0 = (W - d0 + SEG - 1) / SEG, nS = nseg0 + (nd == 2 ? (W - d0 - 1 + SEG - 1) / SEG : 0);
-                const int D = d0 + 2;
-                const int ntile = D <= W - 1 ? (W - 1 - D) / 2 + 1 : 0;
-                const int KS = ksplit(D, W), ksh = KS >> 1 /* log2 of 1, 2, 4 */;
-                const int kwsh = ntile > 16 ? 0 : (ntile > 8 ? 1 : 2), TPW = 32 >> kwsh;   // k parts inside a warp
-                const int nT = ((ntile + TPW - 1) >> (5 - kwsh)) << ksh;
-                const int n2 = d0 + 2 < W ? sm.cnt[(d0 + 2) & 3] : 0, n3 = d0 + 3 < W ? sm.cnt[(d0 + 3) & 3] : 0;
-                const int uT = nS, uL = uT + nT, nH = uL + 2;   // heavy units: S, T, L (about three cells' worth each)
+                const int4 si = reinterpret_cast<const int4 *>(sm.stepinfo)[(d0 - TURN - 1) >> 1];
+                const int nseg0 = si.x & 255, nS = si.x >> 8, D = d0 + 2;
+                const int ntile = si.y & 255, ksh = (si.y >> 8) & 15, kwsh = si.y >> 12, KS = 1 << ksh, TPW = 32 >> kwsh;
+                const int nT = si.z;
+                const int uT = nS, uL = uT + nT, nH = uL + 2;
                 for (int u = warp; u < nH; u += NW) {
                     if (u < uT) {
                         // ---- S
@@ -538,14 +556,64 @@ mfe3_kernel(MfeLaunch L, const MfeTables *__restrict__ T, const Tab3 *__restrict
                         build_list(d0 + 4 + (u - uL));
                     }
                 }
+            }
+            TICK(tX)
+            __syncthreads();
+            TICK(tXb)
+            // =================== phase Y: multiloop matrix of diagonals d0, d0+1 (31 cells per unit, the neighbour
+            //   on d0 comes by shuffle), the table-driven terms of diagonals d0+2, d0+3 (one list chunk per unit) and
+            //   the interior loops of size >= 2 of diagonals d0+4, d0+5 (they only need rows <= d0+1) =============
+            {
+                const int nc0 = W - d0, nc1 = nd == 2 ? W - d0 - 1 : 0;
+                const int nfin = sm.stepinfo[((d0 - TURN - 1) >> 1) * 4 + 3];
+                const int n2 = d0 + 2 < W ? sm.cnt[(d0 + 2) & 3] : 0, n3 = d0 + 3 < W ? sm.cnt[(d0 + 3) & 3] : 0;
+                const int n4 = d0 + 4 < W ? sm.cnt[(d0 + 4) & 3] : 0, n5 = d0 + 5 < W ? sm.cnt[(d0 + 5) & 3] : 0;
+                const int nch2 = (n2 + 31) >> 5, nch = nch2 + ((n3 + 31) >> 5);
+                const int nHy = nfin + nch;
+                for (int u = warp; u < nHy; u += NW) {
+                    if (u < nfin) {
+                        const int x = u * 31 + lane;
+                        const bool v0 = x < nc0;
+                        const int xx = v0 ? x : nc0 - 1;
+                        auto stemof = [&](int d, int xi) {
+                            const int o16 = (d & (R16 - 1)) * PR + xi;
+                            const int e = sm.rc[o16];
+                            const int t = tb.rtype[sm.ctx[o16]];
+                            return e < FIN16 ? e + tb.mlstem[t * 36 + sx[xi] * 6 + sx[xi + d + 2]] : INF16;
+                        };
+                        const int dec0 = decof(d0, xx);
+                        int m0 = min(dec0, stemof(d0, xx));
+                        if (d0 - 1 > TURN)
+                            m0 = min(m0, min((int)sm.fm[(xx + 1) * P + xx + d0], (int)sm.fm[xx * P + xx + d0 - 1]) + tb.MLbase);
+                        if (m0 >= FIN16) m0 = INF16;
+                        if (v0) {
+                            minv = min(minv, m0);
+                            sm.fm[x * P + x + d0] = (short)m0;
+                            sm.fm[(x + d0) * P + x] = (short)m0;
+                        }
+                        const int m0n = __shfl_down_sync(full, m0, 1);
+                        if (lane < 31 && x < nc1) {
+                            const int d = d0 + 1;
+                            int m1 = min(decof(d, x), stemof(d, x));
+                            m1 = min(m1, min(m0, m0n) + tb.MLbase);
+                            if (m1 >= FIN16) m1 = INF16;
+                            minv = min(minv, m1);
+                            sm.fm[x * P + x + d] = (short)m1;
+                            sm.fm[(x + d) * P + x] = (short)m1;
+                        }
+                    } else {
+                        const int it = u - nfin;
+                        do_special(it < nch2 ? d0 + 2 : d0 + 3, it < nch2 ? it : it - nch2);
+                    }
+                }
                 // ---- C: one pairable cell per pass; lane = loop size U with its nine taps (see the header).
-                // The cells continue the round robin of the heavy units, so the warps that got one unit fewer start.
+                // The cells continue the round robin of the heavy units (multiloop rows, list chunks) of this phase.
                 {
-                    int c = warp - nH % NW;
+                    int c = warp - nHy % NW;
                     if (c < 0) c += NW;
 #pragma unroll 1
                     for (int ds = 0; ds < 2; ds++) {
-                        const int d = d0 + 2 + ds, n = ds ? n3 : n2;
+                        const int d = d0 + 4 + ds, n = ds ? n5 : n4;
                         if (c < n) {
                             const int s32 = ((d - 2 - U) & (R32 - 1)) * PR, s16 = ((d - 2 - U) & (R16 - 1)) * PR;
                             int oA = O_PAD, oB = O_PAD, oC = O_PAD;
@@ -586,7 +654,15 @@ mfe3_kernel(MfeLaunch L, const MfeTables *__restrict__ T, const Tab3 *__restrict
                                 int v = min(g, g2) + eI;
                                 v = __viaddmin_s32(a1, e1, v);
                                 v = __viaddmin_s32(aB, eB, v);
+#ifdef SFB_SHFL_REDUCE
+                                v = min(v, __shfl_xor_sync(full, v, 16));
+                                v = min(v, __shfl_xor_sync(full, v, 8));
+                                v = min(v, __shfl_xor_sync(full, v, 4));
+                                v = min(v, __shfl_xor_sync(full, v, 2));
+                                v = min(v, __shfl_xor_sync(full, v, 1));
+#else
                                 v = __reduce_min_sync(full, v);
+#endif
                                 if (lane == 0) qP[i] = (short)v;   // <= INF16 + size and mismatch terms: fits
                             }
                         }
@@ -594,49 +670,14 @@ mfe3_kernel(MfeLaunch L, const MfeTables *__restrict__ T, const Tab3 *__restrict
                     }
                 }
             }
+            TICK(tY)
             __syncthreads();
-            // =================== phase Y: multiloop matrix of diagonals d0, d0+1 (31 cells per warp, the neighbour
-            //                     on d0 comes by shuffle) and the remaining terms of diagonals d0+2, d0+3 ===========
-            {
-                const int nc0 = W - d0, nc1 = nd == 2 ? W - d0 - 1 : 0;
-                if (warp * 31 < nc0) {
-                    const int x = warp * 31 + lane;
-                    const bool v0 = x < nc0;
-                    const int xx = v0 ? x : nc0 - 1;
-                    auto stemof = [&](int d, int xi) {
-                        const int o16 = (d & (R16 - 1)) * PR + xi;
-                        const int e = sm.rc[o16];
-                        const int t = tb.rtype[sm.ctx[o16]];
-                        return e < FIN16 ? e + tb.mlstem[t * 36 + sx[xi] * 6 + sx[xi + d + 2]] : INF16;
-                    };
-                    const int dec0 = decof(d0, xx);
-                    int m0 = min(dec0, stemof(d0, xx));
-                    if (d0 - 1 > TURN)
-                        m0 = min(m0, min((int)sm.fm[(xx + 1) * P + xx + d0], (int)sm.fm[xx * P + xx + d0 - 1]) + tb.MLbase);
-                    if (m0 >= FIN16) m0 = INF16;
-                    if (v0) {
-                        minv = min(minv, m0);
-                        sm.fm[x * P + x + d0] = (short)m0;
-                        sm.fm[(x + d0) * P + x] = (short)m0;
-                    }
-                    const int m0n = __shfl_down_sync(full, m0, 1);
-                    if (lane < 31 && x < nc1) {
-                        const int d = d0 + 1;
-                        int m1 = min(decof(d, x), stemof(d, x));
-                        m1 = min(m1, min(m0, m0n) + tb.MLbase);
-                        if (m1 >= FIN16) m1 = INF16;
-                        minv = min(minv, m1);
-                        sm.fm[x * P + x + d] = (short)m1;
-                        sm.fm[(x + d) * P + x] = (short)m1;
-                    }
-                }
-                const int n2 = d0 + 2 < W ? sm.cnt[(d0 + 2) & 3] : 0, n3 = d0 + 3 < W ? sm.cnt[(d0 + 3) & 3] : 0;
-                const int nch2 = (n2 + 31) >> 5, nch = nch2 + ((n3 + 31) >> 5);
-                for (int it = NW - 1 - warp; it < nch; it += NW)
-                    do_special(it < nch2 ? d0 + 2 : d0 + 3, it < nch2 ? it : it - nch2);
-            }
-            __syncthreads();
+            TICK(tYb)
         }
+#ifdef SFB_TIMING
+        if (blockIdx.x == 0 && lane == 0 && fold == 0)
+            printf("warp %d: X %lld  Xbar %lld  Y %lld  Ybar %lld  loop %lld\n", warp, tX, tXb, tY, tYb, clock64() - t0);
+#endif
 
         // ---- exterior loop: stage C (+ stem term) back from the scratch row, then F5 sequentially (warp 0)
         {

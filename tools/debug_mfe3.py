@@ -1,10 +1,11 @@
-"""GPU check of the energy-only kernel selected by SFB_MFE_ENGINE against the int32 CTA kernel (structure=True path)."""
+"""GPU check of the energy-only kernel selected by SFB_MFE_ENGINE against the CPU oracle."""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from scanfold_b200 import engine
 sys.path.insert(0, "tests")
 from util import rand_seqs
+from oracle import oracle as O
 engine.init(0)
 Ws = [int(a) for a in sys.argv[1:]] or [16, 17, 20, 24, 31, 40, 64, 65, 80, 100, 119, 120]
 for W in Ws:
@@ -14,7 +15,7 @@ for W in Ws:
     except Exception as ex:
         print("W", W, "energy-only failed:", ex)
         continue
-    e1, _ = engine.fold_batch(seqs, structure=True)
+    e1 = np.asarray(O.fold_batch(np.frombuffer("".join(seqs).encode(), dtype=np.uint8).reshape(len(seqs), W), n_threads=16))
     bad = np.nonzero(e1 != e2)[0]
     print("W", W, "mismatch", len(bad), "of", len(seqs), "redo", int((e2 == 0x7fffff00).sum()))
     for k in bad[:4]:
