@@ -47,6 +47,11 @@ const char *sfb_last_error(void);
 /* Launch everything on the caller's CUDA stream (a cudaStream_t, e.g. torch.cuda.current_stream().cuda_stream)
  * so that the caller's events bracket the library's work; NULL = back to the library's own stream. */
 int sfb_set_stream(void *cuda_stream_or_null);
+/* Kernel selection for tests and tuning (results never depend on it): mfe_engine 1 = int32 CTA kernel (mfe.cu),
+ * 2 = + int16 warp-team kernel (mfe2.cu), 3 = + int16 CTA kernel with stencil / range-minimum loops (mfe3.cu,
+ * default); pf_engine 1 = global-memory kernel (pf.cu), 2 = + shared-memory kernel (pf2.cu, default).
+ * A value <= 0 leaves that setting unchanged. */
+int sfb_set_engines(int mfe_engine, int pf_engine);
 /* 1 if the loaded table is the built-in best-effort stand-in (parity with ViennaRNA unpinned) */
 int sfb_params_besteffort(void);
 

@@ -120,8 +120,8 @@ struct FoldWork {  // device scratch for one MFE launch
             if (need2 > scratch2.n) scratch2.alloc(need2);
         }
     }
-    static int engine() {  // SFB_MFE_ENGINE=2 selects the second-generation kernel (tuning / debugging knob)
-        static const int e = getenv("SFB_MFE_ENGINE") ? atoi(getenv("SFB_MFE_ENGINE")) : 3;
+    static int &engine() {  // sfb_set_engines / SFB_MFE_ENGINE: which energy-only kernel generation may run
+        static int e = getenv("SFB_MFE_ENGINE") ? atoi(getenv("SFB_MFE_ENGINE")) : 3;
         return e;
     }
     // energy-only unconstrained folds: int16 warp-per-fold kernel, then the int32 kernel on whatever it flagged
@@ -240,6 +240,14 @@ void sfb_shutdown(void) {
     if (g_ctx.d_pf) cudaFree(g_ctx.d_pf);
     if (g_ctx.own_stream) cudaStreamDestroy(g_ctx.own_stream);
     g_ctx = Context();
+}
+
+int sfb_set_engines(int mfe_engine, int pf_engine) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (mfe_engine > 3 || pf_engine > 2) return fail(SFB_E_ARG, "sfb_set_engines: unknown engine");
+    if (mfe_engine > 0) FoldWork::engine() = mfe_engine;
+    if (pf_engine > 0) pf2_set_enabled(pf_engine >= 2);
+    return 0;
 }
 
 int sfb_set_stream(void *cuda_stream_or_null) {

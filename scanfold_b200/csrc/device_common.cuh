@@ -112,6 +112,7 @@ void launch_pf(const PfLaunch &L, const MfeTables *d_mfe, const PfTables *d_pf, 
 size_t pf_scratch_doubles_per_cta(int W);
 // second-generation partition function (pf2.cu): unconstrained windows up to 120 nt, shared-memory resident
 bool pf2_supports(const PfLaunch &L);
+void pf2_set_enabled(bool on);
 size_t pf2_scratch_doubles_per_cta();
 void pf2_upload_tables(const PfTables &q);
 void launch_pf2(const PfLaunch &L, const MfeTables *d_mfe, const PfTables *d_pf, int n_sm, cudaStream_t stream,

@@ -516,9 +516,14 @@ pf2_kernel(PfLaunch L, const MfeTables *__restrict__ MT, const PfTables *__restr
 
 }  // namespace
 
+static bool &pf2_enabled() {
+    static bool on = !(getenv("SFB_PF_ENGINE") && atoi(getenv("SFB_PF_ENGINE")) == 1);
+    return on;
+}
+void pf2_set_enabled(bool on) { pf2_enabled() = on; }
+
 bool pf2_supports(const PfLaunch &L) {
-    static const bool off = getenv("SFB_PF_ENGINE") && atoi(getenv("SFB_PF_ENGINE")) == 1;   // debugging knob
-    return !off && !L.hc && !L.sc && L.max_span <= 0 && L.W >= 2 * TURN + 4 && L.W <= P2;
+    return pf2_enabled() && !L.hc && !L.sc && L.max_span <= 0 && L.W >= 2 * TURN + 4 && L.W <= P2;
 }
 
 size_t pf2_scratch_doubles_per_cta() { return 2 * (size_t)P2 * P2; }

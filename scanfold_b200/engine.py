@@ -22,7 +22,7 @@ EXPORTS = ["sfb_version", "sfb_init", "sfb_shutdown", "sfb_last_error", "sfb_par
            "sfb_pf_batch", "sfb_deigan", "sfb_scan", "sfb_scan_plan_create", "sfb_scan_plan_keep_shuffles",
            "sfb_scan_plan_run", "sfb_scan_plan_fetch", "sfb_scan_plan_destroy", "sfb_accumulate_begin",
            "sfb_accumulate_geometry", "sfb_accumulate_export", "sfb_accumulate_merge", "sfb_accumulate_compact",
-           "sfb_accumulate_fetch", "sfb_accumulate_launches", "sfb_accumulate_free", "sfb_microbench", "sfb_set_stream"]
+           "sfb_accumulate_fetch", "sfb_accumulate_launches", "sfb_accumulate_free", "sfb_microbench", "sfb_set_stream", "sfb_set_engines"]
 
 
 class EngineError(RuntimeError):
@@ -93,6 +93,7 @@ def load_library():
         L.sfb_accumulate_free.restype = None
         L.sfb_shutdown.restype = None
         L.sfb_set_stream.argtypes = [C.c_void_p]
+        L.sfb_set_engines.argtypes = [C.c_int, C.c_int]
         L.sfb_microbench.argtypes = [C.c_int, C.POINTER(C.c_double)]
         _lib = L
     return _lib
@@ -398,3 +399,10 @@ def set_stream(cuda_stream):
     """Route every launch and copy of the library to `cuda_stream` (int handle, e.g. torch's current stream)."""
     ensure_init()
     _check(load_library().sfb_set_stream(C.c_void_p(int(cuda_stream)) if cuda_stream else None))
+
+
+def set_engines(mfe=0, pf=0):
+    """Kernel generations allowed to run (tests / tuning; results never depend on it): mfe 1 = int32 CTA kernel,
+    2 = + int16 warp-team kernel, 3 = + int16 CTA kernel with stencil / range-minimum loops (default);
+    pf 1 = global-memory kernel, 2 = + shared-memory kernel (default).  0 leaves a setting unchanged."""
+    _check(load_library().sfb_set_engines(int(mfe), int(pf)))

@@ -270,16 +270,51 @@ def test_scan_shape_mode(engine, oracle):
             assert res.mfe_dcal[nwin] == eo
 
 
-@pytest.mark.parametrize("W", [16, 17, 33, 40, 64, 65, 97, 120, 127, 128])
-def test_warp_per_fold_kernel_matches_int32_kernel(engine, oracle, W):
-    """energy-only folds take the int16 warp-per-fold kernel (mfe2.cu); with structure they take the int32 CTA
-    kernel (mfe.cu).  Same energies, bit for bit, including sequences that overflow int16 and get redone."""
+@pytest.mark.parametrize("W", [16, 17, 33, 40, 64, 65, 97, 119, 120, 127, 128])
+def test_fold_kernels_agree(engine, oracle, W):
+    """The three MFE kernel generations -- int32 CTA kernel (mfe.cu), int16 warp teams (mfe2.cu), int16 CTA kernel
+    with stencil / range-minimum interior loops and on-device traceback (mfe3.cu) -- give the same energies and
+    structures, bit for bit, including sequences that overflow int16 and get redone, and equal the oracle."""
     seqs = rand_seqs(7000 + W, 600, W, gc_rich=True)
     seqs += ["G" * (W // 2) + "C" * (W - W // 2), ("GC" * W)[:W], "A" * W, ("GGGGAAAACCCC" * W)[:W], ("AU" * W)[:W],
              ("GGGGGCCCCC" * W)[:W], ("CUUCGG" * W)[:W], "N" * W, ("ACGUN" * W)[:W]]
-    e_fast, _ = engine.fold_batch(seqs, structure=False)
-    e_ref, _ = engine.fold_batch(seqs, structure=True)
-    bad = np.nonzero(e_fast != e_ref)[0]
-    assert len(bad) == 0, (W, [(int(k), seqs[k], int(e_fast[k]), int(e_ref[k])) for k in bad[:5]])
+    try:
+        engine.set_engines(mfe=1)
+        e_ref, pt_ref = engine.fold_batch(seqs, structure=True)
+        engine.set_engines(mfe=2)
+        e2, _ = engine.fold_batch(seqs, structure=False)
+        engine.set_engines(mfe=3)
+        e3, _ = engine.fold_batch(seqs, structure=False)
+        e3s, pt3 = engine.fold_batch(seqs, structure=True)
+    finally:
+        engine.set_engines(mfe=3)
+    for name, e in (("mfe2", e2), ("mfe3", e3), ("mfe3+traceback", e3s)):
+        bad = np.nonzero(e != e_ref)[0]
+        assert len(bad) == 0, (name, W, [(int(k), seqs[k], int(e[k]), int(e_ref[k])) for k in bad[:5]])
+    bad = np.nonzero((pt3 != pt_ref).any(axis=1))[0]
+    assert len(bad) == 0, (W, [(int(k), seqs[k]) for k in bad[:5]])
     for k in list(range(0, 40)) + list(range(len(seqs) - 9, len(seqs))):
-        assert e_fast[k] == oracle.mfe(seqs[k], structure=False)[0], (W, k, seqs[k])
+        eo, so = oracle.mfe(seqs[k])
+        assert e3[k] == eo and db_from_pt(pt3[k]) == so, (W, k, seqs[k])
+
+
+@pytest.mark.parametrize("W", [10, 31, 64, 97, 120])
+def test_partition_function_kernels_agree(engine, oracle, W):
+    """Shared-memory PF kernel (pf2.cu) against the global-memory one (pf.cu) and the oracle."""
+    seqs = rand_seqs(4100 + W, 40, W, gc_rich=True) + ["A" * W, ("GC" * W)[:W], ("GGGGAAAACCCC" * W)[:W]]
+    try:
+        engine.set_engines(pf=1)
+        r1 = engine.pf_batch(seqs, want_bpp=True)
+        engine.set_engines(pf=2)
+        r2 = engine.pf_batch(seqs, want_bpp=True)
+    finally:
+        engine.set_engines(pf=2)
+    for key in ("dG", "ed"):
+        assert np.allclose(r1[key], r2[key], rtol=1e-9, atol=1e-9), key
+    assert np.abs(r1["bpp"] - r2["bpp"]).max() < 1e-10
+    assert np.array_equal(r1["centroid"], r2["centroid"])
+    for k in range(0, len(seqs), 7):
+        o = oracle.pf(seqs[k], want_bpp=True)
+        assert abs(r2["dG"][k] - o["dG"]) <= 1e-6 * max(1.0, abs(o["dG"]))
+        assert abs(r2["ed"][k] - o["ed"]) <= 1e-6 * max(1.0, abs(o["ed"]))
+        assert np.abs(r2["bpp"][k] - o["bpp"]).max() < 1e-9
