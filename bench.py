@@ -283,7 +283,7 @@ def run_ours(args):
             "e2e": {"value": e2e, "unit": "windows/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps},
             "gpu_launches": int(total_launches), "gpu_launches_e2e_per_step": int(t.n_launches + launches_e2e[0]),
-            "roofline": {"bound": "int_alu", "kernel": "mfe_fold_kernel", "achieved": achieved / 1e9,
+            "roofline": {"bound": "int_alu", "kernel": "mfe3_kernel (+ int32 mfe_fold_kernel redo of flagged folds)", "achieved": achieved / 1e9,
                          "peak": peak_addmin / 1e9, "unit": "G add-min/s", "frac": achieved / peak_addmin,
                          "peak_source": "sfb_microbench VIADDMNMX rate measured in this run (MEASURED_PEAKS.json "
                                         "has no integer peak; HBM is not the bound)",

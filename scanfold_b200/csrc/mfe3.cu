@@ -739,7 +739,8 @@ void launch_mfe3_t(const MfeLaunch &L, const MfeTables *d_tab, int n_sm, cudaStr
 
 }  // namespace
 
-bool mfe3_supports(int W) { return g_mfe3_ok && W >= 16 && W <= 120; }
+static_assert(sizeof(Smem3<200>) <= 227 * 1024, "the 200-nt configuration must fit one SM");
+bool mfe3_supports(int W) { return g_mfe3_ok && W >= 16 && W <= 200; }
 
 // scratch rows (one per resident CTA, the most any configuration launches)
 int mfe3_max_ctas(int n_sm) { return n_sm * 6; }
@@ -817,6 +818,8 @@ void launch_mfe3(const MfeLaunch &L, const MfeTables *d_tab, int n_sm, cudaStrea
     static const int nw = getenv("SFB_MFE3_WARPS") ? atoi(getenv("SFB_MFE3_WARPS")) : 8;  // tuning knob
     if (L.W <= 64)
         launch_mfe3_t<64, 4, 4>(L, d_tab, n_sm, stream);
+    else if (L.W > 120)
+        launch_mfe3_t<200, 16, 1>(L, d_tab, n_sm, stream);
     else if (nw == 4)
         launch_mfe3_t<120, 4, 2>(L, d_tab, n_sm, stream);
     else if (nw == 12)
