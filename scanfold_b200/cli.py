@@ -5,8 +5,12 @@ file names (ScanFold.py:310-388,1484-1500), same file contents.  Additive flags 
 the device shuffles), --parity_shuffles (host-provided shuffles, for bit-exact comparison with a reference
 run), --params (ViennaRNA .par file), --gpu (device ordinal).
 
-Not carried over (out of scope): --lri, --algo rnastructure, --by_ed, -c 0, --global_refold and the
-motif extraction that follows the hot path; selecting one of the first five is an error, not a silent no-op.
+The structure-extraction step that follows the ScanFold-Fold outputs (motif .dbn / .ct files and
+ExtractedStructures.gff3, ScanFold.py:1557-1781) runs too, every motif as one single-window scan; only its
+PostScript plots are not written.
+
+Not carried over (out of scope): --lri, --algo rnastructure, --by_ed, -c 0, --global_refold; selecting
+one of them is an error, not a silent no-op.
 """
 import argparse
 import os
@@ -18,7 +22,7 @@ from datetime import datetime
 
 import numpy as np
 
-from . import pipeline, scan
+from . import motifs, pipeline, scan
 
 
 def build_parser():
@@ -207,6 +211,13 @@ def run_record(args, record_name, raw_seq, original_directory, dist=None):
         print("Elapsed time: %ss" % round(time.time() - t0, 2))
         print("Determining best base pairs...")
         pipeline.write_fold_outputs(seq, ptable, names, minz, step)
+        # structure extraction: refold every top-level helix of the Zavg < -2 structure (ScanFold.py:1557-1781)
+        parity_npz = None
+        if args.parity_shuffles:
+            parity_npz = np.load(args.parity_shuffles if os.path.isabs(args.parity_shuffles)
+                                 else os.path.join(original_directory, args.parity_shuffles))
+        motifs.run(seq, names.dbn3 + ".dbn", args.name, args.structure_extract_file, shuffle_type=str(args.type),
+                   temperature=float(args.t), seed=args.seed, parity=parity_npz)
         print("Total runtime: %ss" % round(time.time() - t0, 2))
         print("ScanFold-Fold analysis complete! Output found in folder named: " + folder)
     finally:

@@ -815,7 +815,7 @@ void mfe3_upload_tables(const MfeTables &M) {
 
 void launch_mfe3(const MfeLaunch &L, const MfeTables *d_tab, int n_sm, cudaStream_t stream, int *n_launches) {
     if (L.n_fold <= 0) return;
-    static const int nw = getenv("SFB_MFE3_WARPS") ? atoi(getenv("SFB_MFE3_WARPS")) : 8;  // tuning knob
+    static const int nw = getenv("SFB_MFE3_WARPS") ? atoi(getenv("SFB_MFE3_WARPS")) : 12;  // tuning knob
     if (L.W <= 64)
         launch_mfe3_t<64, 4, 4>(L, d_tab, n_sm, stream);
     else if (L.W > 120)

@@ -14,7 +14,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libscanfold_b200.so")
+LIB_PATH = os.environ.get("SFB_LIB") or os.path.join(_HERE, "libscanfold_b200.so")   # SFB_LIB: debug builds only
 INF = 10000000
 SHUFFLE_MONO, SHUFFLE_DI = 0, 1
 

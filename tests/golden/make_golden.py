@@ -10,7 +10,8 @@ Each case directory holds:
   case.json      command line, window geometry
   input.fa       (+ constraints.dbn / react.shape)
   trace.npz      per-window engine inputs/outputs recovered from the fold trace: the shuffled sequences the
-                 reference drew (parity shuffles), energies, structures, ED, centroids
+                 reference drew (parity shuffles), energies, structures, ED, centroids; motif_shuffles_<n> = the
+                 100 shuffles drawn for motif n by the structure-extraction step
   expected/      every output file the reference wrote (motif .ps placeholders dropped)
 
 Run here (needs /root/reference):  python tests/golden/make_golden.py
@@ -54,6 +55,9 @@ CASES = {
     "step7_w40": dict(L=150, seed=14, args=["-w", "40", "-r", "10", "-s", "7"]),
     "hc_w40": dict(L=150, seed=15, args=["-w", "40", "-r", "10"], hc=True),
     "shape_w40": dict(L=150, seed=16, args=["-w", "40", "-r", "10", "--shapeD"], react=True),
+    "motifs_w50": dict(L=0, seed=18, args=["-w", "50", "-r", "10"],
+                       seq="AAUAC" + "GGGGCGCUUCGGCGCCCC" + "AUAAUUAAUA" + "GCCGGAUCGAAAGAUCCGGC" + "AAUAUAAUAAAUUA" +
+                           "GGCACGGCUUUUGCCGUGCC" + "UUAUAAUAUA" + "CCGCGGAGAAAUCCGCGG" + "AUUAAUAUAAUAUUAAAUUAAUAAUAUUAAUA"),
     "dna_name_w30": dict(L=100, seed=17, alpha="ACGT", args=["-w", "30", "-r", "8", "--name", "chrTest"],
                          header="rec17|extra|fields"),
 }
@@ -61,7 +65,7 @@ CASES = {
 
 def make_case(name, spec):
     rng = random.Random(spec["seed"])
-    seq = rand_seq(rng, spec["L"], spec.get("alpha", "ACGU"))
+    seq = spec.get("seq") or rand_seq(rng, spec["L"], spec.get("alpha", "ACGU"))
     header = spec.get("header", name)
     work = tempfile.mkdtemp(prefix="golden_")
     fasta = os.path.join(work, "input.fa")
@@ -106,6 +110,7 @@ def make_case(name, spec):
     r = int(args[args.index("-r") + 1])
     step = int(args[args.index("-s") + 1]) if "-s" in args else 1
     L = len(seq)
+    spec = dict(spec, L=L)
     nwin = (L - W) // step + 1
     n = nwin + 1
     shuf = np.zeros((n, r, W), dtype=np.uint8)
@@ -131,6 +136,16 @@ def make_case(name, spec):
         for k in range(r):
             she[w, k] = grp[3 + k]["e"]
             shuf[w, k] = np.frombuffer(grp[3 + k]["seq"].encode(), dtype=np.uint8)
+    # ---- motif step (ScanFold.py:1724-1750): per motif pf (hc), pf (RNA.pf_fold), mfe (hc), then native + 100 shuffles
+    motif_shuffles = {}
+    k_motif = 0
+    while pos < len(trace):
+        grp = trace[pos:pos + 104]
+        pos += 104
+        assert [g["op"] for g in grp] == ["pf", "pf", "mfe"] + ["mfe"] * 101, (name, "motif trace")
+        k_motif += 1
+        motif_shuffles["motif_shuffles_%d" % k_motif] = np.stack(
+            [np.frombuffer(g["seq"].encode(), dtype=np.uint8) for g in grp[4:104]])
     dst = os.path.join(HERE, name)
     if os.path.exists(dst):
         shutil.rmtree(dst)
@@ -139,7 +154,7 @@ def make_case(name, spec):
     for fn, path in aux.items():
         shutil.copy(path, os.path.join(dst, fn))
     np.savez_compressed(os.path.join(dst, "trace.npz"), shuffles=shuf, mfe_dcal=mfe, native_unconstrained_dcal=nat,
-                        shuffle_dcal=she, pair_tbl=pair_tbl, centroid_tbl=cen_tbl, ed=ed, ensemble_dG=dG)
+                        shuffle_dcal=she, pair_tbl=pair_tbl, centroid_tbl=cen_tbl, ed=ed, ensemble_dG=dG, **motif_shuffles)
     kept = []
     for fn in sorted(os.listdir(outdir)):
         if fn.endswith(".ps"):
@@ -154,7 +169,59 @@ def make_case(name, spec):
     print("%-14s windows=%d files=%d" % (name, nwin, len(kept)))
 
 
+def make_motif_vectors():
+    """Known-answer vectors for motifs.extract_motifs: the reference's own extraction block (ScanFold.py, from
+    `structure_raw = filter2constraints` to the ExtractedStructure list) executed on synthetic dot-bracket lines,
+    including pseudoknot characters, an opener at index 0 and nested helices."""
+    import textwrap
+    import types
+    sys.path.insert(0, os.path.join(HERE, "stubs"))
+    sys.path.insert(0, REF)
+    import ScanFoldFunctions as SFF
+    src = open(os.path.join(REF, "ScanFold.py")).read().split("\n")
+    a = next(k for k, ln in enumerate(src) if ln.strip() == "structure_raw = filter2constraints")
+    b = next(k for k, ln in enumerate(src) if "extracted_structure_list.append(" in ln)
+    block = textwrap.dedent("\n".join(src[a:b + 2]))
+    rng = random.Random(77)
+    lines = ["..((((....))))..((...))..", "((((....))))..((...))", "..((..((...))..((...))..))..(((...)))",
+             "..((..<<..))..>>..((...))..", "..<<<...>>>..{{..}}..((...))", ".((.{.)).}.((...)).", "....", "",
+             "((...))", ".(((...)))(((...))).", "..((..<..))..>..", "..(((...)))<<<...>>>"]
+    for _ in range(20):          # random balanced structures with a few pseudoknot characters sprinkled in
+        n = rng.randint(20, 70)
+        st, depth = [], 0
+        for k in range(n):
+            c = rng.choice("..((()))..<>{}" if k % 7 == 3 else "...(())")
+            if c == ")" and depth == 0:
+                c = "."
+            if c == "(":
+                depth += 1
+            if c == ")":
+                depth -= 1
+            st.append(c)
+        st += [")"] * depth
+        lines.append("".join(st))
+    vectors = []
+    for st in lines:
+        seq = "".join(rng.choice("ACGU") for _ in st) + "ACG"
+        nuc_dict = {k + 1: SFF.NucZscore(ch, k + 1) for k, ch in enumerate(seq)}
+        ns = {"filter2constraints": st + "\n", "seq": seq, "cur_record": types.SimpleNamespace(seq=seq),
+              "nuc_dict": nuc_dict, "NucStructure": SFF.NucStructure, "ExtractedStructure": SFF.ExtractedStructure,
+              "bond_order": [], "bond_count": 0, "print": lambda *a, **k: None}
+        try:
+            exec(block, ns)
+            out = [[es.i, es.j, es.sequence, es.structure] for es in ns["extracted_structure_list"]]
+            err = None
+        except Exception as ex:          # unbalanced openers / closers crash the reference (IndexError)
+            out, err = None, type(ex).__name__
+        vectors.append({"structure": st, "seq": seq, "motifs": out, "error": err})
+    json.dump(vectors, open(os.path.join(HERE, "motif_extract_vectors.json"), "w"), indent=0)
+    print("motif extraction vectors: %d (%d raise)" % (len(vectors), sum(v["error"] is not None for v in vectors)))
+
+
 if __name__ == "__main__":
-    sel = sys.argv[1:] or sorted(CASES)
+    sel = sys.argv[1:] or sorted(CASES) + ["motif_vectors"]
     for nm in sel:
-        make_case(nm, CASES[nm])
+        if nm == "motif_vectors":
+            make_motif_vectors()
+        else:
+            make_case(nm, CASES[nm])

@@ -7,7 +7,7 @@ import shutil
 import numpy as np
 import pytest
 
-from test_host_pipeline import CASES, GOLDEN, NEXT_ROW_FILES
+from test_host_pipeline import CASES, GOLDEN
 
 pytestmark = pytest.mark.gpu
 
@@ -25,7 +25,7 @@ def test_cli_outputs_byte_identical(name, tmp_path, monkeypatch, engine):
     cli.main(["input.fa"] + args + ["--parity_shuffles", "trace.npz"])
     out = tmp_path / case["record"]
     exp_dir = os.path.join(d, "expected")
-    exp = sorted(f for f in os.listdir(exp_dir) if f not in NEXT_ROW_FILES and "_motif_" not in f)
+    exp = sorted(os.listdir(exp_dir))          # scan, ScanFold-Fold and structure-extraction outputs
     assert sorted(os.listdir(out)) == exp
     for f in exp:
         assert open(out / f).read() == open(os.path.join(exp_dir, f)).read(), "%s differs in case %s" % (f, name)

@@ -14,7 +14,7 @@ from util import accumulate_numpy
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 CASES = sorted(d for d in os.listdir(GOLDEN) if os.path.exists(os.path.join(GOLDEN, d, "case.json")))
-# written by the motif-extraction step that follows the hot path
+# written by the structure-extraction step that follows the hot path: compared separately below
 NEXT_ROW_FILES = ("ExtractedStructures.gff3",)
 
 
@@ -81,3 +81,52 @@ def test_stats_match_golden_out_rows():
         for k, row in enumerate(rows):
             f = row.split("\t")
             assert f[4] == str(float(z[k])) and f[5] == str(float(p[k])), (name, k)
+
+
+def test_motif_extraction_vectors():
+    """motifs.extract_motifs against known-answer vectors produced by EXECUTING the reference's own extraction block
+    (ScanFold.py:1582-1716, see make_golden.py make_motif_vectors): pseudoknot characters, the lost opener at index 0,
+    empty motifs from mismatched start / end lists, and the IndexError the reference raises when closers run out."""
+    from scanfold_b200 import motifs
+    vectors = json.load(open(os.path.join(GOLDEN, "motif_extract_vectors.json")))
+    assert len(vectors) >= 30
+    for v in vectors:
+        if v["error"]:
+            with pytest.raises(IndexError):
+                motifs.extract_motifs(v["structure"] + "\n", v["seq"], log=lambda *a: None)
+            continue
+        got = motifs.extract_motifs(v["structure"] + "\n", v["seq"], log=lambda *a: None)
+        assert [[m.i, m.j, m.sequence, m.structure] for m in got] == v["motifs"], v["structure"]
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_motif_outputs_byte_identical(name, tmp_path, monkeypatch):
+    """Structure-extraction outputs (motif .dbn / .ct, ExtractedStructures.gff3) of the host code against the golden
+    files of the unmodified reference; the per-motif fold results come from the CPU oracle here (the checker), from
+    the CUDA engine in tests/test_gpu_cli.py."""
+    from oracle import oracle as O
+    from scanfold_b200 import motifs, scan, stats
+    case = load_case(name)
+    exp_dir = os.path.join(case["dir"], "expected")
+    args = case["args"]
+    chrom = args[args.index("--name") + 1] if "--name" in args else "UserInput"
+    monkeypatch.chdir(tmp_path)
+    found = motifs.extract_motifs(open(os.path.join(exp_dir, "Zavg_-2_pairs.dbn")).readlines()[2], case["seq"],
+                                  log=lambda *a: None)
+    results = []
+    for m in found:
+        sh = case["trace"]["motif_shuffles_%d" % m.number]
+        e, s = O.mfe(m.sequence, hc=m.structure)
+        pf = O.pf(m.sequence, hc=m.structure)
+        nat = O.mfe(m.sequence, structure=False)[0]
+        she = [O.mfe(bytes(row).decode(), structure=False)[0] for row in sh]
+        z, p = stats.zscore_pvalue(np.array([nat]), np.array([she]))
+        results.append({"structure": s, "mfe": float(stats.round_energy([e])[0]), "z": float(z[0]), "p": float(p[0]),
+                        "ed": float(scan.round_ed([pf["ed"]])[0])})
+    motifs.write_motif_outputs(found, results, chrom, "ExtractedStructures.gff3")
+    exp = {f: open(os.path.join(exp_dir, f)).read() for f in os.listdir(exp_dir)
+           if f in NEXT_ROW_FILES or "_motif_" in f}
+    got = {f: open(os.path.join(tmp_path, f)).read() for f in os.listdir(tmp_path)}
+    assert sorted(got) == sorted(exp)
+    for f in sorted(exp):
+        assert got[f] == exp[f], "%s differs in case %s" % (f, name)
