@@ -12,7 +12,12 @@
 // capped asymmetry term, so it only needs a range minimum of G over the row -- including the near ones in that
 // range is harmless because the cap is an upper bound of their true term.  Per finished diagonal row the kernel
 // stores the two stencils (NE, NO) and a sliding 8-minimum (M8); a cell then needs 1 + (1..4) loads per u
-// instead of u-3.  Bulge and 1xn loops keep one load per candidate (rows RB, R1).
+// instead of u-3.  Bulge and 1xn loops keep one load per candidate side: the bulge value (C + TerminalAU) and the 1xn
+// value (C + mismatch1nI) of neighbouring cells share a 32-bit word, once in a copy indexed by the 5' end (loops
+// with the unpaired bases on the 3' side) and once in a copy indexed by the 3' end (5' side), so that both loads have a
+// lane-independent position.  With an odd word pitch / a row pitch of 31 (mod 32) words and the taps of disabled
+// lanes redirected to the address of an enabled lane, every tap of the loop is one shared-memory wavefront (r01h: 16
+// wavefronts for 9 loads, r01j: 7 for 7).
 //
 // Work split: the CTA walks the anti-diagonals two at a time.  Phase C: the pairable cells of both diagonals
 // are compacted into lists and every (list chunk, candidate class) pair is an independent work item for one
@@ -69,25 +74,27 @@ struct Smem3 {
     // ring pitch in shorts: PR/2 words = 31 (mod 32), so lane U reading row (c-U) at offset a*U (a = 0, 1/2, 1) lands in
     // bank (1+a/2)*U: the 32 taps of one warp load hit 32 different banks
     static constexpr int PR = P <= 64 ? P + 2 : ((P + 2 + 63) / 64) * 64 - 2;   // small windows: shared memory first
+    static constexpr int PRW = (P + 3) | 1;   // pitch (32-bit words) of the paired bulge / 1xn rows: odd
     Tab3 tb;
     // ring rows and the square FML matrix, INF-initialised per fold; ne.. doubles as the staging area of C for
     // the exterior loop
-    short ne[R32 * PR], no[R32 * PR], m8[R32 * PR], r1[R32 * PR], rb[R32 * PR];
+    short ne[R32 * PR], no[R32 * PR], m8[R32 * PR];
+    unsigned rpa[R32 * PRW];  // [row][p]: lo = C + TerminalAU of cell (p, p+dd), hi = C + mismatch1nI of cell (p+1, ..)
+    unsigned rpq[R32 * PRW];  // [row][q]: lo = C + TerminalAU of cell (q-dd, q), hi = C + mismatch1nI of cell (.., q-1)
     short g[R16 * PR];
     short rc[R16 * PR];
-    short padrow[PR + 38];
     short fm[P * P];          // fm[a][b]: FML[a,b] for b > a (row = 5' end), FML[b,a] for b < a (row = 3' end)
     short decp[KSMAX * 8 * PR];
     short partc[4 * PR], parts[4 * PR];   // partial minima by diagonal & 3: loops of size >= 2 / everything else
     short f5[P + 8];
-    alignas(16) int list[(4 * PR + 32) * 4];     // per pairable cell: i, mismatchI / mismatch1nI / TerminalAU term of the closing pair
+    alignas(16) short list[(4 * PR + 32) * 4];   // per pairable cell: i, mismatchI / mismatch1nI / TerminalAU term of the
+                                                 // closing pair; the traceback stack of the natives reuses it
     unsigned char ctx[R16 * PR];
     unsigned char sx[P + 8];   // sx[k+1] = code of nucleotide k, sx[0] = sx[W+1] = 5
     int cnt[4];
     int ctr[2];
     int minv[32];
     int fbest[32];
-    int tbstk[3 * (P + 8)];   // traceback stack (natives only)
     alignas(16) int stepinfo[(P / 2 + 2) * 4];   // per diagonal pair: unit counts of the two phases (fold independent)
 };
 
@@ -164,7 +171,8 @@ __device__ bool traceback3(Smem3<P> &sm, const MfeTables *T, const short *cx, sh
     const Tab3 &tb = sm.tb;
     const unsigned char *sx = sm.sx;
     const unsigned full = 0xffffffffu;
-    int *stk = sm.tbstk;
+    static_assert(sizeof(sm.list) >= 3 * (P + 8) * sizeof(int), "the traceback stack lives in the list area");
+    int *stk = reinterpret_cast<int *>(sm.list);
     auto ptype = [&](int a, int b) { return (int)tb.ptype[sx[a + 1] * 6 + sx[b + 1]]; };
     auto CC = [&](int i, int j) {
         const int v = cx[tri4(j - i, W) + i];
@@ -335,19 +343,26 @@ mfe3_kernel(MfeLaunch L, const MfeTables *__restrict__ T, const Tab3 *__restrict
     }
     short *gC = reinterpret_cast<short *>(L.gscratch) + (size_t)blockIdx.x * L.gscratch_per_cta;
     const short *smb = sm.ne;   // every tap address below is an offset (in shorts) from here
-    constexpr int O_NE = 0, O_NO = R32 * PR, O_M8 = 2 * R32 * PR, O_R1 = 3 * R32 * PR, O_RB = 4 * R32 * PR,
-                  O_G = 5 * R32 * PR, O_PAD = 5 * R32 * PR + 2 * R16 * PR;
+    constexpr int PRW = SM::PRW;
+    constexpr int O_NE = 0, O_NO = R32 * PR, O_M8 = 2 * R32 * PR;   // in shorts from smb
+    static_assert(offsetof(SM, no) - offsetof(SM, ne) == 2 * O_NO && offsetof(SM, m8) - offsetof(SM, ne) == 2 * O_M8,
+                  "tap offsets follow the member order");
 
     // ---- per-lane loop size U = lane: size terms of its nine taps (see the header); BIG disables a tap
     const int U = lane;
     const bool uok = U <= MAXLOOP;
     const int cSB = (uok && U >= 2) ? c3_sizeB[U] : BIG;
     const int cS1 = (uok && U >= 4) ? c3_size1[U] : BIG;
-    const int cA = !uok ? BIG : (U == 6 ? c3_sG6[0] : (U >= 7 ? c3_il[U] : BIG));
-    const int cB10 = !uok ? BIG : (U == 6 ? c3_sG6[1] : (U >= 9 ? c3_cap[U] : BIG));
+    const int cA = (uok && U >= 7) ? c3_il[U] : BIG;        // generic loops of size 6 and the two end candidates of
+    const int cB10 = (uok && U >= 11) ? c3_cap[U] : BIG;    // sizes 9, 10 are table-driven terms (do_special)
     const int cB18 = (uok && U > 19) ? c3_cap[U] : BIG;
     const int cB26 = (uok && U > 27) ? c3_cap[U] : BIG;
-    const int cC = !uok ? BIG : (U == 6 ? c3_sG6[2] : ((U == 9 || U == 10 || U > 11) ? c3_cap[U] : BIG));
+    const int cC = (uok && U > 11) ? c3_cap[U] : BIG;
+    // a disabled tap reads the address of an enabled lane (same word: a broadcast, never a bank conflict)
+    const int UA = U < 7 ? U + 8 : (U > MAXLOOP ? MAXLOOP - 1 : U);
+    const int UC = U < 12 ? U + 12 : (U > MAXLOOP ? MAXLOOP : U);
+    const int kA = ((UA & 1) ? O_NO : O_NE) + 3 + (UA >> 1), kC = O_M8 + UC - 1;
+    const int g6a = c3_sG6[0], g6b = c3_sG6[1], g6c = c3_sG6[2], g9 = c3_cap[9], g10 = c3_cap[10];
 
     // compacted list of the pairable cells of diagonal d with the closing-pair terms (one warp) -> slot d & 3
     auto build_list = [&](int d) {
@@ -359,8 +374,8 @@ mfe3_kernel(MfeLaunch L, const MfeTables *__restrict__ T, const Tab3 *__restrict
             const unsigned m = __ballot_sync(full, t != 0);
             if (t) {
                 const int mi = (t * 5 + sx[i + 2]) * 5 + sx[i + d];
-                int4 en = make_int4(i, tb.mmI[mi], tb.mm1n[mi], tb.tAU[t]);
-                reinterpret_cast<int4 *>(sm.list)[slot * PR + nl + __popc(m & ((1u << lane) - 1))] = en;
+                const short4 en = make_short4((short)i, tb.mmI[mi], tb.mm1n[mi], tb.tAU[t]);
+                reinterpret_cast<short4 *>(sm.list)[slot * PR + nl + __popc(m & ((1u << lane) - 1))] = en;
             }
             nl += __popc(m);
         }
@@ -419,6 +434,12 @@ mfe3_kernel(MfeLaunch L, const MfeTables *__restrict__ T, const Tab3 *__restrict
             aT = min(aT, cc + tb.il5_ninio + tb.mm23[mi] + tb.mm23[(t2 * 5 + sq1) * 5 + sp1]);
             const int dm = decof(d - 2, i + 1);
             aT = min(aT, dm + tb.mlclose[(tb.rtype[type] * 5 + sj1) * 5 + si1]);
+            // generic loops the stencil / range rows do not cover: 2x4 3x3 4x2 and the two ends of sizes 9, 10
+            auto grow = [&](int dd, int p) { return dd > TURN ? (int)sm.g[(dd & (R16 - 1)) * PR + p] : INF16; };
+            int aG = min(grow(d - 8, i + 3) + g6a, min(grow(d - 8, i + 4) + g6b, grow(d - 8, i + 5) + g6c));
+            aG = min(aG, min(grow(d - 11, i + 3), grow(d - 11, i + 8)) + g9);
+            aG = min(aG, min(grow(d - 12, i + 3), grow(d - 12, i + 9)) + g10);
+            aT = min(aT, aG + tb.mmI[mi]);
         }
         if (active) sm.parts[slot * PR + i] = (short)min(aT, INF16);
     };
@@ -499,8 +520,14 @@ mfe3_kernel(MfeLaunch L, const MfeTables *__restrict__ T, const Tab3 *__restrict
                             sm.rc[o16] = (short)e;
                             sm.ctx[o16] = (unsigned char)t2;
                             sm.g[o16] = (short)vg;
-                            sm.r1[o32] = (short)v1;
-                            sm.rb[o32] = (short)vb;
+                            {   // bulge | 1xn pairs: 16-bit halves of the 5'-indexed and the 3'-indexed copy
+                                short *wa = reinterpret_cast<short *>(sm.rpa) + 2 * ((d & (R32 - 1)) * PRW + i);
+                                short *wq = reinterpret_cast<short *>(sm.rpq) + 2 * ((d & (R32 - 1)) * PRW + j);
+                                wa[0] = (short)vb;
+                                if (i > 0) wa[-1] = (short)v1;
+                                wq[0] = (short)vb;
+                                wq[3] = (short)v1;
+                            }
                             sm.ne[o32] = (short)ne;
                             sm.no[o32] = (short)no;
                             sm.m8[o32] = (short)m8;
@@ -615,42 +642,29 @@ mfe3_kernel(MfeLaunch L, const MfeTables *__restrict__ T, const Tab3 *__restrict
                     for (int ds = 0; ds < 2; ds++) {
                         const int d = d0 + 4 + ds, n = ds ? n5 : n4;
                         if (c < n) {
-                            const int s32 = ((d - 2 - U) & (R32 - 1)) * PR, s16 = ((d - 2 - U) & (R16 - 1)) * PR;
-                            int oA = O_PAD, oB = O_PAD, oC = O_PAD;
-                            if (uok) {
-                                if (U == 6) {
-                                    oA = O_G + s16 + 3;
-                                    oB = O_G + s16 + 4 - 10;
-                                    oC = O_G + s16 + 5;
-                                } else if (U >= 7) {
-                                    oA = ((U & 1) ? O_NO : O_NE) + s32 + 3 + (U >> 1);
-                                    if (U == 9 || U == 10) {
-                                        oB = O_G + s16 + 3 - 10;
-                                        oC = O_G + s16 + U - 1;
-                                    } else if (U >= 11) {
-                                        oB = O_M8 + s32;
-                                        oC = O_M8 + s32 + (U > 11 ? U - 1 : 10);
-                                    }
-                                }
-                            }
-                            const short *qL = smb + O_RB + s32, *qR = smb + O_RB + s32 + U;
-                            const short *qA = smb + oA, *qB = smb + oB, *qC = smb + oC;
+                            const int slot = (d - 2 - U) & (R32 - 1);
+                            const short *qA = smb + kA + ((d - 2 - UA) & (R32 - 1)) * PR;
+                            const short *qB = smb + O_M8 + slot * PR;
+                            const short *qC = smb + kC + ((d - 2 - UC) & (R32 - 1)) * PR;
+                            const unsigned *qR = sm.rpa + slot * PRW + 1;        // inner pair (i+1, j-1-U) and 1xn neighbour
+                            const unsigned *qL = sm.rpq + slot * PRW + d - 1;    // inner pair (i+1+U, j-1) and 1xn neighbour
                             short *qP = sm.partc + (d & 3) * PR;
-                            const int4 *lst = reinterpret_cast<const int4 *>(sm.list) + (d & 3) * PR;
-                            int4 en = lst[c];
+                            const short4 *lst = reinterpret_cast<const short4 *>(sm.list) + (d & 3) * PR;
+                            short4 en = lst[c];
                             for (; c < n; c += NW) {
                                 const int i = en.x, eI = en.y, e1 = en.z, eB = en.w;
                                 en = lst[c + NW];   // next entry (at most NW past the list end: still inside sm.list)
-                                const short *pl = qL + i, *pr = qR + i, *pa = qA + i, *pb = qB + i, *pc = qC + i;
-                                const int xbl = pl[1], x1l = pl[O_R1 - O_RB + 2];
-                                const int xbr = pr[1], x1r = pr[O_R1 - O_RB];
+                                const unsigned wr = qR[i], wl = qL[i];
+                                const short *pa = qA + i, *pb = qB + i, *pc = qC + i;
                                 const int xa = pa[0], xb10 = pb[10], xb18 = pb[18], xb26 = pb[26], xc = pc[0];
+                                const unsigned wm = __vmins2(wr, wl);
+                                const int xb = (int)(short)(wm & 0xffffu), x1 = (int)wm >> 16;
                                 int g = xa + cA;
                                 g = __viaddmin_s32(xb10, cB10, g);
                                 int g2 = xb18 + cB18;
                                 g2 = __viaddmin_s32(xb26, cB26, g2);
                                 g = __viaddmin_s32(xc, cC, g);
-                                const int aB = min(xbl, xbr) + cSB, a1 = min(x1l, x1r) + cS1;
+                                const int aB = xb + cSB, a1 = x1 + cS1;
                                 int v = min(g, g2) + eI;
                                 v = __viaddmin_s32(a1, e1, v);
                                 v = __viaddmin_s32(aB, eB, v);
