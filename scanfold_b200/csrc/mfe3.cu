@@ -84,14 +84,14 @@ struct Smem3 {
     short g[R16 * PR];
     short rc[R16 * PR];
     short fm[P * P];          // fm[a][b]: FML[a,b] for b > a (row = 5' end), FML[b,a] for b < a (row = 3' end)
-    short decp[KSMAX * 8 * PR];
+    short decp[KSMAX * 4 * PR];   // split minima of the last 4 diagonals, one copy per k part
     short partc[4 * PR], parts[4 * PR];   // partial minima by diagonal & 3: loops of size >= 2 / everything else
     short f5[P + 8];
-    alignas(16) short list[(4 * PR + 32) * 4];   // per pairable cell: i, mismatchI / mismatch1nI / TerminalAU term of the
+    alignas(16) int list[(4 * PR + 32) * 4];     // per pairable cell: i, mismatchI / mismatch1nI / TerminalAU term of the
                                                  // closing pair; the traceback stack of the natives reuses it
     unsigned char ctx[R16 * PR];
     unsigned char sx[P + 8];   // sx[k+1] = code of nucleotide k, sx[0] = sx[W+1] = 5
-    int cnt[4];
+    alignas(16) int cnt[4];   // pairable cells of the diagonals d with d & 3 = slot (0 beyond the last diagonal)
     int ctr[2];
     int minv[32];
     int fbest[32];
@@ -374,8 +374,8 @@ mfe3_kernel(MfeLaunch L, const MfeTables *__restrict__ T, const Tab3 *__restrict
             const unsigned m = __ballot_sync(full, t != 0);
             if (t) {
                 const int mi = (t * 5 + sx[i + 2]) * 5 + sx[i + d];
-                const short4 en = make_short4((short)i, tb.mmI[mi], tb.mm1n[mi], tb.tAU[t]);
-                reinterpret_cast<short4 *>(sm.list)[slot * PR + nl + __popc(m & ((1u << lane) - 1))] = en;
+                const int4 en = make_int4(i, tb.mmI[mi], tb.mm1n[mi], tb.tAU[t]);
+                reinterpret_cast<int4 *>(sm.list)[slot * PR + nl + __popc(m & ((1u << lane) - 1))] = en;
             }
             nl += __popc(m);
         }
@@ -386,8 +386,8 @@ mfe3_kernel(MfeLaunch L, const MfeTables *__restrict__ T, const Tab3 *__restrict
         if (d < 2 * TURN + 3) return INF16;
         const int Dsrc = (d & 1) ? ((xi & 1) ? d + 1 : d - 1) : d;
         const int ks = ksplit(Dsrc, W);
-        int v = sm.decp[(d & 7) * PR + xi];
-        for (int kp = 1; kp < ks; kp++) v = min(v, (int)sm.decp[(kp * 8 + (d & 7)) * PR + xi]);
+        int v = sm.decp[(d & 3) * PR + xi];
+        for (int kp = 1; kp < ks; kp++) v = min(v, (int)sm.decp[(kp * 4 + (d & 3)) * PR + xi]);
         return v;
     };
     // table-driven shapes, hairpin and multiloop closing of the pairable cells of diagonal d, list chunk c (lane = cell)
@@ -479,8 +479,8 @@ mfe3_kernel(MfeLaunch L, const MfeTables *__restrict__ T, const Tab3 *__restrict
             //   S  C and the derived rows of diagonals d0, d0+1 (25 row elements per unit)
             //   T  split minima of tile diagonal d0+2 (2x2 tiles, packed)
             //   L  lists of diagonals d0+4, d0+5
+            const int4 si = reinterpret_cast<const int4 *>(sm.stepinfo)[(d0 - TURN - 1) >> 1];
             {
-                const int4 si = reinterpret_cast<const int4 *>(sm.stepinfo)[(d0 - TURN - 1) >> 1];
                 const int nseg0 = si.x & 255, nS = si.x >> 8, D = d0 + 2;
                 const int ntile = si.y & 255, ksh = (si.y >> 8) & 15, kwsh = si.y >> 12, KS = 1 << ksh, TPW = 32 >> kwsh;
                 const int nT = si.z;
@@ -571,12 +571,12 @@ mfe3_kernel(MfeLaunch L, const MfeTables *__restrict__ T, const Tab3 *__restrict
                         }
                         if (valid && kq == 0) {
                             auto fin = [](int v) { return (short)(v >= FIN16 ? INF16 : v); };
-                            short *dp = sm.decp + kp * 8 * PR;
-                            dp[(D & 7) * PR + i] = fin((short)(acc0 & 0xffffu));
-                            dp[((D - 1) & 7) * PR + i + 1] = fin((int)acc0 >> 16);
+                            short *dp = sm.decp + kp * 4 * PR;
+                            dp[(D & 3) * PR + i] = fin((short)(acc0 & 0xffffu));
+                            dp[((D - 1) & 3) * PR + i + 1] = fin((int)acc0 >> 16);
                             if (j + 1 < W) {
-                                dp[((D + 1) & 7) * PR + i] = fin((short)(acc1 & 0xffffu));
-                                dp[(D & 7) * PR + i + 1] = fin((int)acc1 >> 16);
+                                dp[((D + 1) & 3) * PR + i] = fin((short)(acc1 & 0xffffu));
+                                dp[(D & 3) * PR + i + 1] = fin((int)acc1 >> 16);
                             }
                         }
                     } else {
@@ -592,9 +592,10 @@ mfe3_kernel(MfeLaunch L, const MfeTables *__restrict__ T, const Tab3 *__restrict
             //   the interior loops of size >= 2 of diagonals d0+4, d0+5 (they only need rows <= d0+1) =============
             {
                 const int nc0 = W - d0, nc1 = nd == 2 ? W - d0 - 1 : 0;
-                const int nfin = sm.stepinfo[((d0 - TURN - 1) >> 1) * 4 + 3];
-                const int n2 = d0 + 2 < W ? sm.cnt[(d0 + 2) & 3] : 0, n3 = d0 + 3 < W ? sm.cnt[(d0 + 3) & 3] : 0;
-                const int n4 = d0 + 4 < W ? sm.cnt[(d0 + 4) & 3] : 0, n5 = d0 + 5 < W ? sm.cnt[(d0 + 5) & 3] : 0;
+                const int nfin = si.w;
+                const int4 cn = *reinterpret_cast<const int4 *>(sm.cnt);   // d0 is even: slots (d0 & 2) .. hold d0+4, d0+5
+                const bool up = (d0 & 2) != 0;
+                const int n4 = up ? cn.z : cn.x, n5 = up ? cn.w : cn.y, n2 = up ? cn.x : cn.z, n3 = up ? cn.y : cn.w;
                 const int nch2 = (n2 + 31) >> 5, nch = nch2 + ((n3 + 31) >> 5);
                 const int nHy = nfin + nch;
                 for (int u = warp; u < nHy; u += NW) {
@@ -649,8 +650,8 @@ mfe3_kernel(MfeLaunch L, const MfeTables *__restrict__ T, const Tab3 *__restrict
                             const unsigned *qR = sm.rpa + slot * PRW + 1;        // inner pair (i+1, j-1-U) and 1xn neighbour
                             const unsigned *qL = sm.rpq + slot * PRW + d - 1;    // inner pair (i+1+U, j-1) and 1xn neighbour
                             short *qP = sm.partc + (d & 3) * PR;
-                            const short4 *lst = reinterpret_cast<const short4 *>(sm.list) + (d & 3) * PR;
-                            short4 en = lst[c];
+                            const int4 *lst = reinterpret_cast<const int4 *>(sm.list) + (d & 3) * PR;
+                            int4 en = lst[c];
                             for (; c < n; c += NW) {
                                 const int i = en.x, eI = en.y, e1 = en.z, eB = en.w;
                                 en = lst[c + NW];   // next entry (at most NW past the list end: still inside sm.list)
