@@ -30,7 +30,16 @@ __constant__ double c2_G[32 * 32];  // [u1 * 32 + u2]: expinternal[u] * expninio
 __constant__ double c2_1[32];       // 1xn loops of total size u
 __constant__ double c2_B[32];       // bulges of size u
 
+// the small Boltzmann-factor tables the narrow column phases look up (same member names as PfTables): a shared-memory
+// copy per CTA, so those phases wait for an LDS instead of an L1-missing global load
+struct PfHead {
+    double expmismatchI[8][5][5], expmismatch1nI[8][5][5], expmismatchM[8][5][5], expmismatchExt[8][5][5];
+    double expdangle5[8][5], expdangle3[8][5];
+    double expMLintern, expTermAU;
+};
+
 struct Smem2 {
+    PfHead th;
     double ring[3][32][RP];     // generic | 1xn | bulge copies
     double ringq[8][P2];        // raw qb (inside) / raw P (outside) of the last columns: table-driven shapes
     double qm[QROWS * PQ];      // folded: row = 3' end k', entries i <= k'-4
@@ -41,6 +50,8 @@ struct Smem2 {
     double ecol[P2 + 8];
     double x1[P2 + 8], x2[P2 + 8], x12[P2 + 8], g1[P2 + 8];
     double q5[P2 + 8], q3[P2 + 8];
+    double qcol[P2 + 8];        // outside: qb of the current column (read from L2 once, in the wide phase)
+    double pmcol[P2 + 8];       // outside: PM of the previous column
     double scale[P2 + 40], emlb[P2 + 8], ainv[P2 + 8];
     double red[32];
     short cen[P2 + 8];
@@ -133,7 +144,8 @@ __device__ __forceinline__ double shape2(const PfTables *T, int u1, int u2, int 
     return T->expinternal[5] * T->expmismatch23I[type][si1][sj1] * T->expmismatch23I[t2][sq1][sp1] * T->expninio[1];
 }
 
-__device__ __forceinline__ double mlstem2(const PfTables *T, int type, int si1, int sj1) {
+template <class TT>
+__device__ __forceinline__ double mlstem2(const TT *T, int type, int si1, int sj1) {
     double z = 1.;
     if (si1 >= 0 && sj1 >= 0)
         z = T->expmismatchM[type][si1][sj1];
@@ -145,7 +157,8 @@ __device__ __forceinline__ double mlstem2(const PfTables *T, int type, int si1, 
     return z * T->expMLintern;
 }
 
-__device__ __forceinline__ double extloop2(const PfTables *T, int type, int si1, int sj1) {
+template <class TT>
+__device__ __forceinline__ double extloop2(const TT *T, int type, int si1, int sj1) {
     double z = 1.;
     if (si1 >= 0 && sj1 >= 0)
         z = T->expmismatchExt[type][si1][sj1];
@@ -163,8 +176,53 @@ __device__ __forceinline__ double warp_sum(double v) {
 }
 
 // the nine shapes as (u1, u2) nibbles: (0,0) (0,1) (1,0) (1,1) (1,2) (2,1) (2,2) (2,3) (3,2)
-__device__ __forceinline__ int shape_u1(int z) { return (int)((0x322211100ull >> (4 * z)) & 15); }
-__device__ __forceinline__ int shape_u2(int z) { return (int)((0x232121010ull >> (4 * z)) & 15); }
+__host__ __device__ constexpr int shape_u1(int z) { return (int)((0x322211100ull >> (4 * z)) & 15); }
+__host__ __device__ constexpr int shape_u2(int z) { return (int)((0x232121010ull >> (4 * z)) & 15); }
+
+// Table-driven shapes with u2 = S4 (u2 <= 3, so u2 mod 4 = u2) closed by (i,j): they ride with the separable
+// candidates of the same u2 group in phase A, where all 16 warps work, instead of the 5-warp column phase.
+template <int S4>
+__device__ __forceinline__ double shapes_inside(const Smem2 &sm, const PfTables *T, int i, int j, int t) {
+    const unsigned char *S = sm.S;
+    const int si1 = S[i + 1], sj1 = S[j - 1];
+    double acc = 0.;
+    sfor2<0, 8>([&](auto Z) {
+        constexpr int z = decltype(Z)::value, u1 = shape_u1(z), u2 = shape_u2(z);
+        if constexpr (u2 == S4) {
+            const int p = i + 1 + u1, q = j - 1 - u2;
+            if (q - p > TURN) {
+                const double qpq = sm.ringq[q & 7][p];
+                if (qpq != 0.) {
+                    const int t2 = rtype_of(pair_type(S[p], S[q]));
+                    acc += qpq * shape2(T, u1, u2, t, t2, si1, sj1, S[p - 1], S[q + 1]) * sm.scale[u1 + u2 + 2];
+                }
+            }
+        }
+    });
+    return acc;
+}
+
+// the same for the outside pass: (k,l) is the inner pair, (i,j) = (k-1-u1, l+1+u2) the closing one
+template <int S4>
+__device__ __forceinline__ double shapes_outside(const Smem2 &sm, const PfTables *T, int k, int l, int t2, int W) {
+    const unsigned char *S = sm.S;
+    const int sp1 = S[k - 1], sq1 = S[l + 1];
+    double acc = 0.;
+    sfor2<0, 8>([&](auto Z) {
+        constexpr int z = decltype(Z)::value, u1 = shape_u1(z), u2 = shape_u2(z);
+        if constexpr (u2 == S4) {
+            const int i = k - 1 - u1, j = l + 1 + u2;
+            if (i >= 0 && j <= W - 1) {
+                const double pij = sm.ringq[j & 7][i];
+                if (pij > 0.) {
+                    const int tij = pair_type(S[i], S[j]);
+                    acc += pij * shape2(T, u1, u2, tij, t2, S[i + 1], S[j - 1], sp1, sq1) * sm.scale[u1 + u2 + 2];
+                }
+            }
+        }
+    });
+    return acc;
+}
 
 __global__ void __launch_bounds__(NT2, 1)
 pf2_kernel(PfLaunch L, const MfeTables *__restrict__ MT, const PfTables *__restrict__ T) {
@@ -179,6 +237,21 @@ pf2_kernel(PfLaunch L, const MfeTables *__restrict__ MT, const PfTables *__restr
     auto qmidx = [&](int kk, int i) { return kk <= HF ? kk * PQ + i : (W + 3 - kk) * PQ + (W - kk) + i; };
     const double *ringp = &sm.ring[0][0][0];
 
+    for (int k = tid; k < 200; k += NT2) {
+        (&sm.th.expmismatchI[0][0][0])[k] = (&T->expmismatchI[0][0][0])[k];
+        (&sm.th.expmismatch1nI[0][0][0])[k] = (&T->expmismatch1nI[0][0][0])[k];
+        (&sm.th.expmismatchM[0][0][0])[k] = (&T->expmismatchM[0][0][0])[k];
+        (&sm.th.expmismatchExt[0][0][0])[k] = (&T->expmismatchExt[0][0][0])[k];
+        if (k < 40) {
+            (&sm.th.expdangle5[0][0])[k] = (&T->expdangle5[0][0])[k];
+            (&sm.th.expdangle3[0][0])[k] = (&T->expdangle3[0][0])[k];
+        }
+    }
+    if (tid == 0) {
+        sm.th.expMLintern = T->expMLintern;
+        sm.th.expTermAU = T->expTermAU;
+    }
+    const PfHead *TH = &sm.th;
     if (tid == 0) {
         sm.scale[0] = 1.;
         sm.emlb[0] = 1.;
@@ -229,17 +302,17 @@ pf2_kernel(PfLaunch L, const MfeTables *__restrict__ MT, const PfTables *__restr
                 if (s == 0 && i < P2) sm.ty[i] = (unsigned char)t;
                 if (__any_sync(full, t != 0)) {
                     if (t) {
-                        double aG = 0., a1 = 0., aB = 0.;
+                        double aG = 0., a1 = 0., aB = 0., aS = 0.;
                         const int u2max = j - 5;
                         switch (s) {
-                            case 0: cand_group<0, false>(ringp, j - 1, i + 1, u2max, aG, a1, aB); break;
-                            case 1: cand_group<1, false>(ringp, j - 1, i + 1, u2max, aG, a1, aB); break;
-                            case 2: cand_group<2, false>(ringp, j - 1, i + 1, u2max, aG, a1, aB); break;
-                            default: cand_group<3, false>(ringp, j - 1, i + 1, u2max, aG, a1, aB); break;
+                            case 0: cand_group<0, false>(ringp, j - 1, i + 1, u2max, aG, a1, aB); aS = shapes_inside<0>(sm, T, i, j, t); break;
+                            case 1: cand_group<1, false>(ringp, j - 1, i + 1, u2max, aG, a1, aB); aS = shapes_inside<1>(sm, T, i, j, t); break;
+                            case 2: cand_group<2, false>(ringp, j - 1, i + 1, u2max, aG, a1, aB); aS = shapes_inside<2>(sm, T, i, j, t); break;
+                            default: cand_group<3, false>(ringp, j - 1, i + 1, u2max, aG, a1, aB); aS = shapes_inside<3>(sm, T, i, j, t) + hairpin2(c, i, j, t) * sm.scale[j - i + 1]; break;
                         }
                         const int si1 = S[i + 1], sj1 = S[j - 1];
-                        sm.partA[s][i] = aG * T->expmismatchI[t][si1][sj1] + a1 * T->expmismatch1nI[t][si1][sj1] +
-                                         aB * (t > 2 ? tAU : 1.);
+                        sm.partA[s][i] = aG * TH->expmismatchI[t][si1][sj1] + a1 * TH->expmismatch1nI[t][si1][sj1] +
+                                         aB * (t > 2 ? tAU : 1.) + aS;
                     }
                 }
             }
@@ -252,24 +325,11 @@ pf2_kernel(PfLaunch L, const MfeTables *__restrict__ MT, const PfTables *__restr
                 if (t) {
                     const int si1 = S[i + 1], sj1 = S[j - 1];
                     qv = sm.partA[0][i] + sm.partA[1][i] + sm.partA[2][i] + sm.partA[3][i];
-#pragma unroll
-                    for (int z = 0; z < 9; z++) {
-                        const int u1 = shape_u1(z), u2 = shape_u2(z);
-                        const int p = i + 1 + u1, q = j - 1 - u2;
-                        if (q - p > TURN) {
-                            const double qpq = sm.ringq[q & 7][p];
-                            if (qpq != 0.) {
-                                const int t2 = rtype_of(pair_type(S[p], S[q]));
-                                qv += qpq * shape2(T, u1, u2, t, t2, si1, sj1, S[p - 1], S[q + 1]) * sm.scale[u1 + u2 + 2];
-                            }
-                        }
-                    }
-                    qv += hairpin2(c, i, j, t) * sm.scale[j - i + 1];
-                    qv += sm.qqcol[i + 1] * closing * mlstem2(T, rtype_of(t), sj1, si1) * sc2;
+                    qv += sm.qqcol[i + 1] * closing * mlstem2(TH, rtype_of(t), sj1, si1) * sc2;
                     if (i > 0 && j < W - 1) {   // (i,j) as the inner pair of an enclosing loop
                         const int t2 = rtype_of(t), a = S[j + 1], b = S[i - 1];
-                        vG = qv * T->expmismatchI[t2][a][b];
-                        v1 = qv * T->expmismatch1nI[t2][a][b];
+                        vG = qv * TH->expmismatchI[t2][a][b];
+                        v1 = qv * TH->expmismatch1nI[t2][a][b];
                         vB = t2 > 2 ? qv * tAU : qv;
                     }
                 }
@@ -283,7 +343,7 @@ pf2_kernel(PfLaunch L, const MfeTables *__restrict__ MT, const PfTables *__restr
                     double m1 = 0.;
                     if (i <= j - TURN - 1) {
                         if (j - 1 - i > TURN) m1 = sm.qm1[(j - 1) & 1][i] * eml1;
-                        if (t) m1 += qv * mlstem2(T, t, nb(i - 1), nb(j + 1));
+                        if (t) m1 += qv * mlstem2(TH, t, nb(i - 1), nb(j + 1));
                     }
                     sm.qm1[j & 1][i] = m1;
                 }
@@ -327,7 +387,7 @@ pf2_kernel(PfLaunch L, const MfeTables *__restrict__ MT, const PfTables *__restr
                 double acc = 0.;
                 for (int i = lane; i <= j - TURN - 1; i += 32) {
                     const int t = sm.ty[i];
-                    if (t) acc += sm.q5[i] * sm.ringq[j & 7][i] * extloop2(T, t, nb(i - 1), nb(j + 1));
+                    if (t) acc += sm.q5[i] * sm.ringq[j & 7][i] * extloop2(TH, t, nb(i - 1), nb(j + 1));
                 }
                 acc = warp_sum(acc);
                 if (lane == 0) sm.q5[j + 1] = sm.q5[j] * sc1 + acc;
@@ -361,19 +421,20 @@ pf2_kernel(PfLaunch L, const MfeTables *__restrict__ MT, const PfTables *__restr
                 const int kblk = warp & 3, s = warp >> 2, k = kblk * 32 + lane;
                 const double qkl = k <= l - TURN - 1 ? qbG[l * P2 + k] : 0.;
                 const bool act = qkl != 0. && k >= 1 && l <= W - 2;
+                if (s == 0 && k < P2) sm.qcol[k] = qkl;
                 if (__any_sync(full, act)) {
                     if (act) {
-                        double aG = 0., a1 = 0., aB = 0.;
+                        double aG = 0., a1 = 0., aB = 0., aS = 0.;
                         const int u2max = W - 2 - l;
-                        switch (s) {
-                            case 0: cand_group<0, true>(ringp, l + 1, 32 + k - 1, u2max, aG, a1, aB); break;
-                            case 1: cand_group<1, true>(ringp, l + 1, 32 + k - 1, u2max, aG, a1, aB); break;
-                            case 2: cand_group<2, true>(ringp, l + 1, 32 + k - 1, u2max, aG, a1, aB); break;
-                            default: cand_group<3, true>(ringp, l + 1, 32 + k - 1, u2max, aG, a1, aB); break;
-                        }
                         const int t2 = rtype_of(pair_type(S[k], S[l])), a = S[l + 1], b = S[k - 1];
-                        sm.partA[s][k] = aG * T->expmismatchI[t2][a][b] + a1 * T->expmismatch1nI[t2][a][b] +
-                                         aB * (t2 > 2 ? tAU : 1.);
+                        switch (s) {
+                            case 0: cand_group<0, true>(ringp, l + 1, 32 + k - 1, u2max, aG, a1, aB); aS = shapes_outside<0>(sm, T, k, l, t2, W); break;
+                            case 1: cand_group<1, true>(ringp, l + 1, 32 + k - 1, u2max, aG, a1, aB); aS = shapes_outside<1>(sm, T, k, l, t2, W); break;
+                            case 2: cand_group<2, true>(ringp, l + 1, 32 + k - 1, u2max, aG, a1, aB); aS = shapes_outside<2>(sm, T, k, l, t2, W); break;
+                            default: cand_group<3, true>(ringp, l + 1, 32 + k - 1, u2max, aG, a1, aB); aS = shapes_outside<3>(sm, T, k, l, t2, W); break;
+                        }
+                        sm.partA[s][k] = aG * TH->expmismatchI[t2][a][b] + a1 * TH->expmismatch1nI[t2][a][b] +
+                                         aB * (t2 > 2 ? tAU : 1.) + aS;
                     }
                 }
                 // X1[i,l] = sum_{j >= l+6} PM[i,j] qm[l+1,j-1], the j range cut in four
@@ -388,7 +449,7 @@ pf2_kernel(PfLaunch L, const MfeTables *__restrict__ MT, const PfTables *__restr
                     double a3 = 0.;
                     for (int j = l + TURN + 1 + lane; j < W; j += 32) {
                         const double q = qbG[j * P2 + l];
-                        if (q != 0.) a3 += q * sm.q3[j + 1] * extloop2(T, pair_type(S[l], S[j]), nb(l - 1), nb(j + 1));
+                        if (q != 0.) a3 += q * sm.q3[j + 1] * extloop2(TH, pair_type(S[l], S[j]), nb(l - 1), nb(j + 1));
                     }
                     a3 = warp_sum(a3);
                     if (lane == 0) sm.q3[l] = sm.q3[l + 1] * sc1 + a3;
@@ -401,7 +462,7 @@ pf2_kernel(PfLaunch L, const MfeTables *__restrict__ MT, const PfTables *__restr
                 double x1 = 0., x2 = 0.;
                 if (i <= l - TURN - 1) {
                     x1 = sm.partC[0][i] + sm.partC[1][i] + sm.partC[2][i] + sm.partC[3][i];
-                    if (l + 1 < W) x2 = sm.x2[i] * eml1 + (i <= l - TURN ? pmG[(l + 1) * P2 + i] : 0.);
+                    if (l + 1 < W) x2 = sm.x2[i] * eml1 + (i <= l - TURN ? sm.pmcol[i] : 0.);
                 }
                 sm.x1[i] = x1;
                 sm.x2[i] = x2;
@@ -451,36 +512,23 @@ pf2_kernel(PfLaunch L, const MfeTables *__restrict__ MT, const PfTables *__restr
                 const int k = tid;
                 double Pv = 0., vG = 0., v1 = 0., vB = 0., pm = 0.;
                 if (k <= l - TURN - 1) {
-                    const double qkl = qbG[l * P2 + k];
+                    const double qkl = sm.qcol[k];
                     if (qkl != 0.) {
                         const int t = pair_type(S[k], S[l]);
                         if (k >= 1 && l <= W - 2) {
                             const int t2 = rtype_of(t), sp1 = S[k - 1], sq1 = S[l + 1];
                             Pv = sm.partA[0][k] + sm.partA[1][k] + sm.partA[2][k] + sm.partA[3][k];
-#pragma unroll
-                            for (int z = 0; z < 9; z++) {
-                                const int u1 = shape_u1(z), u2 = shape_u2(z);
-                                const int i = k - 1 - u1, j = l + 1 + u2;
-                                if (i >= 0 && j <= W - 1) {
-                                    const double pij = sm.ringq[j & 7][i];
-                                    if (pij > 0.) {
-                                        const int tij = pair_type(S[i], S[j]);
-                                        Pv += pij * shape2(T, u1, u2, tij, t2, S[i + 1], S[j - 1], sp1, sq1) *
-                                              sm.scale[u1 + u2 + 2];
-                                    }
-                                }
-                            }
                             const double ml = sm.g1[k] + sm.partC[0][k] + sm.partC[1][k] + sm.partC[2][k];
-                            Pv += ml * mlstem2(T, t, sp1, sq1) * sc2;
+                            Pv += ml * mlstem2(TH, t, sp1, sq1) * sc2;
                         }
-                        Pv += sm.q5[k] * sm.q3[l + 1] / Z * extloop2(T, t, nb(k - 1), nb(l + 1));
+                        Pv += sm.q5[k] * sm.q3[l + 1] / Z * extloop2(TH, t, nb(k - 1), nb(l + 1));
                         if (Pv != 0.) {
                             const int a = S[k + 1], b = S[l - 1];
-                            vG = Pv * T->expmismatchI[t][a][b];
-                            v1 = Pv * T->expmismatch1nI[t][a][b];
+                            vG = Pv * TH->expmismatchI[t][a][b];
+                            v1 = Pv * TH->expmismatch1nI[t][a][b];
                             vB = t > 2 ? Pv * tAU : Pv;
                         }
-                        pm = Pv * closing * mlstem2(T, rtype_of(t), S[l - 1], S[k + 1]);
+                        pm = Pv * closing * mlstem2(TH, rtype_of(t), S[l - 1], S[k + 1]);
                         const double p = Pv * qkl;
                         ed_local += p * (1. - p);
                         if (p > 0.5) {
@@ -490,6 +538,7 @@ pf2_kernel(PfLaunch L, const MfeTables *__restrict__ MT, const PfTables *__restr
                         if (L.bpp) L.bpp[((long long)fold * W + k) * W + l] = p;
                     }
                     pmG[l * P2 + k] = pm;
+                    sm.pmcol[k] = pm;
                 }
                 const int slot = l & 31;
                 sm.ring[0][slot][32 + k] = vG;
