@@ -19,12 +19,19 @@
 // lanes redirected to the address of an enabled lane, every tap of the loop is one shared-memory wavefront (r01h: 16
 // wavefronts for 9 loads, r01j: 7 for 7).
 //
-// Work split: the CTA walks the anti-diagonals two at a time.  Phase C: the pairable cells of both diagonals
-// are compacted into lists and every (list chunk, candidate class) pair is an independent work item for one
-// warp (classes: generic / table-driven shapes + hairpin + multiloop closing / left bulge + 1xn / right bulge +
-// 1xn); each item leaves a partial minimum per cell.  Phase S: per row element the partial minima are combined
-// into C and the derived rows G, R1, RB, NE, NO, M8 are written (warp shuffles along the row).  Phase M: the
-// multiloop matrix FML of both diagonals, sharing the left operand of the split loop.
+// Work split: the CTA walks the anti-diagonals two at a time (pairs d0, d0+1 with d0 odd) with ONE barrier per pair.
+// Phase k (pair d0 = 5 + 2k) runs these mutually independent work units, each for one warp:
+//   S   finalises C of the pair: the partial minima left by earlier phases plus the terms that need the previous
+//       pair (stack, bulge of one, multiloop closing), then the derived rows G, NE, NO, M8, the bulge / 1xn words
+//   F   the multiloop matrix FML of the PREVIOUS pair (d0-2, d0-1): it needs that pair's finished C rows
+//   T   split minima of tile diagonal d0+1 (2x2 tiles; they only read FML of diagonals <= d0-3)
+//   P   table-driven terms of the NEXT pair (d0+2, d0+3) that only read rows <= d0-1 (1x1, 2x1, 2x2, 2x3, hairpin,
+//       generic 2x4 / 3x3 / 4x2 and the ends of sizes 9, 10): lane = pairable cell of a compacted list chunk
+//   C   interior loops of size >= 2 of the next pair: one warp pass per pairable cell, lane = loop size
+//   L   lists of the pairable cells of diagonals d0+4, d0+5
+// so the only chain from pair to pair is S -> barrier -> S; everything else has a phase of slack.  (The first version
+// had two barrier-separated phases per pair; late diagonals, which have fewer units than warps, paid two latency
+// floors per pair.)
 // int16 storage is exact as long as no stored energy drops below LOW16; a fold that does is flagged and redone
 // by the int32 kernel (mfe.cu) in the same stream, so results never depend on which kernel ran.
 #include <cstddef>
@@ -84,10 +91,11 @@ struct Smem3 {
     short g[R16 * PR];
     short rc[R16 * PR];
     short fm[P * P];          // fm[a][b]: FML[a,b] for b > a (row = 5' end), FML[b,a] for b < a (row = 3' end)
-    short decp[KSMAX * 4 * PR];   // split minima of the last 4 diagonals, one copy per k part
+    short decp[KSMAX * 8 * PR];   // split minima of the last 8 diagonals, one copy per k part
     short partc[4 * PR], parts[4 * PR];   // partial minima by diagonal & 3: loops of size >= 2 / everything else
     short f5[P + 8];
-    alignas(16) int list[(4 * PR + 32) * 4];     // per pairable cell: i, mismatchI / mismatch1nI / TerminalAU term of the
+    static constexpr int LP = P;              // list pitch (entries): a diagonal has fewer than P cells
+    alignas(16) int list[(4 * LP + 32) * 4];     // per pairable cell: i, mismatchI / mismatch1nI / TerminalAU term of the
                                                  // closing pair; the traceback stack of the natives reuses it
     unsigned char ctx[R16 * PR];
     unsigned char sx[P + 8];   // sx[k+1] = code of nucleotide k, sx[0] = sx[W+1] = 5
@@ -95,7 +103,7 @@ struct Smem3 {
     int ctr[2];
     int minv[32];
     int fbest[32];
-    alignas(16) int stepinfo[(P / 2 + 2) * 4];   // per diagonal pair: unit counts of the two phases (fold independent)
+    alignas(8) int stepinfo[(P / 2 + 4) * 2];    // per diagonal pair: unit counts of the phase (fold independent)
 };
 
 __host__ __device__ __forceinline__ int tri4(int d, int W) {  // first cell of diagonal d in the d >= 4 triangle
@@ -330,16 +338,19 @@ mfe3_kernel(MfeLaunch L, const MfeTables *__restrict__ T, const Tab3 *__restrict
     const Tab3 &tb = sm.tb;
     const unsigned char *sx = sm.sx;
     const int W = L.W;
-    for (int st = tid; TURN + 1 + 2 * st < W; st += NT) {
-        const int d0 = TURN + 1 + 2 * st, nd = d0 + 1 < W ? 2 : 1;
-        const int nseg0 = (W - d0 + SEG - 1) / SEG, nS = nseg0 + (nd == 2 ? (W - d0 - 1 + SEG - 1) / SEG : 0);
-        const int D = d0 + 2;
+    constexpr int LP = SM::LP;
+    const int npairs = (W - TURN) / 2 + 1;   // phases: pairs d0 = 5, 7, .. while d0 - 2 < W (F runs one pair behind)
+    for (int st = tid; st < npairs; st += NT) {
+        const int d0 = TURN + 2 + 2 * st;
+        const int nseg0 = d0 < W ? (W - d0 + SEG - 1) / SEG : 0, nseg1 = d0 + 1 < W ? (W - d0 - 1 + SEG - 1) / SEG : 0;
+        const int nF = d0 - 2 < W ? (W - (d0 - 2) + 30) / 31 : 0;
+        const int D = d0 + 1;
         const int ntile = D <= W - 1 ? (W - 1 - D) / 2 + 1 : 0;
         const int KS = ksplit(D, W), ksh = KS >> 1 /* log2 of 1, 2, 4 */;
         const int kwsh = ntile > 16 ? 0 : (ntile > 8 ? 1 : 2), TPW = 32 >> kwsh;   // k parts inside a warp
         const int nT = ((ntile + TPW - 1) >> (5 - kwsh)) << ksh;
-        reinterpret_cast<int4 *>(sm.stepinfo)[st] =
-            make_int4(nseg0 | (nS << 8), ntile | (ksh << 8) | (kwsh << 12), nT, (W - d0 + 30) / 31);
+        reinterpret_cast<int2 *>(sm.stepinfo)[st] =
+            make_int2(nseg0 | ((nseg0 + nseg1) << 8) | (nF << 16), ntile | (ksh << 8) | (kwsh << 12) | (nT << 16));
     }
     short *gC = reinterpret_cast<short *>(L.gscratch) + (size_t)blockIdx.x * L.gscratch_per_cta;
     const short *smb = sm.ne;   // every tap address below is an offset (in shorts) from here
@@ -375,7 +386,7 @@ mfe3_kernel(MfeLaunch L, const MfeTables *__restrict__ T, const Tab3 *__restrict
             if (t) {
                 const int mi = (t * 5 + sx[i + 2]) * 5 + sx[i + d];
                 const int4 en = make_int4(i, tb.mmI[mi], tb.mm1n[mi], tb.tAU[t]);
-                reinterpret_cast<int4 *>(sm.list)[slot * PR + nl + __popc(m & ((1u << lane) - 1))] = en;
+                reinterpret_cast<int4 *>(sm.list)[slot * LP + nl + __popc(m & ((1u << lane) - 1))] = en;
             }
             nl += __popc(m);
         }
@@ -386,16 +397,17 @@ mfe3_kernel(MfeLaunch L, const MfeTables *__restrict__ T, const Tab3 *__restrict
         if (d < 2 * TURN + 3) return INF16;
         const int Dsrc = (d & 1) ? ((xi & 1) ? d + 1 : d - 1) : d;
         const int ks = ksplit(Dsrc, W);
-        int v = sm.decp[(d & 3) * PR + xi];
-        for (int kp = 1; kp < ks; kp++) v = min(v, (int)sm.decp[(kp * 4 + (d & 3)) * PR + xi]);
+        int v = sm.decp[(d & 7) * PR + xi];
+        for (int kp = 1; kp < ks; kp++) v = min(v, (int)sm.decp[(kp * 8 + (d & 7)) * PR + xi]);
         return v;
     };
-    // table-driven shapes, hairpin and multiloop closing of the pairable cells of diagonal d, list chunk c (lane = cell)
-    auto do_special = [&](int d, int c) {
+    // unit P: table-driven terms of the pairable cells of diagonal d, list chunk c (lane = cell), that only read rows
+    // <= d-4; stack, bulge of one and multiloop closing are added when the cell is finalised (unit S)
+    auto unit_P = [&](int d, int c) {
         const int slot = d & 3, n = sm.cnt[slot];
         const int idx = c * 32 + lane;
         const bool active = idx < n;
-        const int i = active ? sm.list[(slot * PR + idx) * 4] : 0;
+        const int i = active ? sm.list[(slot * LP + idx) * 4] : 0;
         const int j = i + d;
         const int type = tb.ptype[sx[i + 1] * 6 + sx[j + 1]];
         const int si1 = sx[i + 2], sj1 = sx[j];
@@ -411,12 +423,6 @@ mfe3_kernel(MfeLaunch L, const MfeTables *__restrict__ T, const Tab3 *__restrict
         };
         int cc, t2, sp1, sq1;
         {
-            inner(0, 0, cc, t2, sp1, sq1);
-            aT = min(aT, cc + tb.stack[type * 8 + t2]);
-            inner(0, 1, cc, t2, sp1, sq1);
-            aT = min(aT, cc + tb.bulge1 + tb.stack[type * 8 + t2]);
-            inner(1, 0, cc, t2, sp1, sq1);
-            aT = min(aT, cc + tb.bulge1 + tb.stack[type * 8 + t2]);
             inner(1, 1, cc, t2, sp1, sq1);
             aT = min(aT, cc + __ldg(&T->int11[type][t2][si1][sj1]));
             int eh = __ldg(&T->hairpin_len[d - 1]) + tb.mmH[mi];
@@ -432,8 +438,6 @@ mfe3_kernel(MfeLaunch L, const MfeTables *__restrict__ T, const Tab3 *__restrict
             aT = min(aT, cc + tb.il5_ninio + tb.mm23[mi] + tb.mm23[(t2 * 5 + sq1) * 5 + sp1]);
             inner(3, 2, cc, t2, sp1, sq1);
             aT = min(aT, cc + tb.il5_ninio + tb.mm23[mi] + tb.mm23[(t2 * 5 + sq1) * 5 + sp1]);
-            const int dm = decof(d - 2, i + 1);
-            aT = min(aT, dm + tb.mlclose[(tb.rtype[type] * 5 + sj1) * 5 + si1]);
             // generic loops the stencil / range rows do not cover: 2x4 3x3 4x2 and the two ends of sizes 9, 10
             auto grow = [&](int dd, int p) { return dd > TURN ? (int)sm.g[(dd & (R16 - 1)) * PR + p] : INF16; };
             int aG = min(grow(d - 8, i + 3) + g6a, min(grow(d - 8, i + 4) + g6b, grow(d - 8, i + 5) + g6c));
@@ -442,6 +446,153 @@ mfe3_kernel(MfeLaunch L, const MfeTables *__restrict__ T, const Tab3 *__restrict
             aT = min(aT, aG + tb.mmI[mi]);
         }
         if (active) sm.parts[slot * PR + i] = (short)min(aT, INF16);
+    };
+
+    int minv = 0;   // smallest stored energy of the fold (int16 range check)
+
+    // unit S: 25 row elements of diagonal d -- C from the partial minima and the terms that need the previous pair,
+    // then the derived rows (warp shuffles along the row; lanes 0..6 are the halo of the sliding minimum)
+    auto unit_S = [&](int d, int sg) {
+        const int ncells = W - d;
+        const int x = sg * SEG - 7 + lane;
+        const bool valid = x >= 0 && x < ncells;
+        const int i = valid ? x : 0, j = i + d;
+        const int t = valid ? tb.ptype[sx[i + 1] * 6 + sx[j + 1]] : 0;
+        int e = INF16;
+        if (t) {
+            e = min((int)sm.partc[(d & 3) * PR + i], (int)sm.parts[(d & 3) * PR + i]);
+            if (d - 2 > TURN) {   // stack: inner pair (i+1, j-1)
+                const int o = ((d - 2) & (R16 - 1)) * PR + i + 1;
+                e = min(e, sm.rc[o] + tb.stack[t * 8 + sm.ctx[o]]);
+            }
+            if (d - 3 > TURN) {   // bulge of one: inner pairs (i+1, j-2) and (i+2, j-1)
+                const int o = ((d - 3) & (R16 - 1)) * PR + i + 1;
+                const int b0 = sm.rc[o] + tb.stack[t * 8 + sm.ctx[o]], b1 = sm.rc[o + 1] + tb.stack[t * 8 + sm.ctx[o + 1]];
+                e = min(e, min(b0, b1) + tb.bulge1);
+            }
+            const int dm = decof(d - 2, i + 1);   // multiloop closed by (i,j)
+            e = min(e, dm + tb.mlclose[(tb.rtype[t] * 5 + sx[j]) * 5 + sx[i + 2]]);
+            if (e >= FIN16) e = INF16;
+        }
+        int vg = INF16, v1 = INF16, vb = INF16;
+        const int t2 = tb.rtype[t];
+        if (t && i > 0 && j < W - 1 && e < FIN16) {
+            const int m2 = (t2 * 5 + sx[j + 2]) * 5 + sx[i];
+            vg = e + tb.mmI[m2];
+            v1 = e + tb.mm1n[m2];
+            vb = e + tb.tAU[t2];
+        }
+        const int g1 = __shfl_up_sync(full, vg, 1), g2 = __shfl_up_sync(full, vg, 2);
+        const int g3 = __shfl_up_sync(full, vg, 3), g4 = __shfl_up_sync(full, vg, 4);
+        const int ne = min(g2, min(min(g1, g3) + tb.w2, min(vg, g4) + tb.w4));
+        const int no = min(min(g1, g2) + tb.w1, min(vg, g3) + tb.w3);
+        int m8 = min(vg, g1);
+        m8 = min(m8, __shfl_up_sync(full, m8, 2));
+        m8 = min(m8, __shfl_up_sync(full, m8, 4));
+        if (valid && lane >= 7) {
+            minv = min(minv, e);
+            const int o16 = (d & (R16 - 1)) * PR + i, o32 = (d & (R32 - 1)) * PR + i;
+            sm.rc[o16] = (short)e;
+            sm.ctx[o16] = (unsigned char)t2;
+            sm.g[o16] = (short)vg;
+            {   // bulge | 1xn pairs: 16-bit halves of the 5'-indexed and the 3'-indexed copy
+                short *wa = reinterpret_cast<short *>(sm.rpa) + 2 * ((d & (R32 - 1)) * PRW + i);
+                short *wq = reinterpret_cast<short *>(sm.rpq) + 2 * ((d & (R32 - 1)) * PRW + j);
+                wa[0] = (short)vb;
+                if (i > 0) wa[-1] = (short)v1;
+                wq[0] = (short)vb;
+                wq[3] = (short)v1;
+            }
+            sm.ne[o32] = (short)ne;
+            sm.no[o32] = (short)no;
+            sm.m8[o32] = (short)m8;
+            gC[tri4(d, W) + i] = (short)(e < FIN16 ? e + tb.ext[t * 36 + sx[i] * 6 + sx[j + 2]] : INF16);
+        }
+    };
+
+    // unit F: 31 cells of the multiloop matrix of diagonals dA, dA+1 (the neighbour on dA comes by shuffle)
+    auto unit_F = [&](int dA, int u) {
+        const int nc0 = dA > TURN ? W - dA : 0, nc1 = dA + 1 < W ? W - dA - 1 : 0;
+        const int x = u * 31 + lane;
+        const bool v0 = x < nc0;
+        const int xx = v0 ? x : max(nc0 - 1, 0);
+        auto stemof = [&](int d, int xi) {
+            const int o16 = (d & (R16 - 1)) * PR + xi;
+            const int e = sm.rc[o16];
+            const int t = tb.rtype[sm.ctx[o16]];
+            return e < FIN16 ? e + tb.mlstem[t * 36 + sx[xi] * 6 + sx[xi + d + 2]] : INF16;
+        };
+        int m0 = INF16;
+        if (nc0 > 0) {
+            m0 = min(decof(dA, xx), stemof(dA, xx));
+            if (dA - 1 > TURN)
+                m0 = min(m0, min((int)sm.fm[(xx + 1) * P + xx + dA], (int)sm.fm[xx * P + xx + dA - 1]) + tb.MLbase);
+            if (m0 >= FIN16) m0 = INF16;
+            if (v0) {
+                minv = min(minv, m0);
+                sm.fm[x * P + x + dA] = (short)m0;
+                sm.fm[(x + dA) * P + x] = (short)m0;
+            }
+        }
+        const int m0n = __shfl_down_sync(full, m0, 1);
+        if (lane < 31 && x < nc1) {
+            const int d = dA + 1;
+            int m1 = min(decof(d, x), stemof(d, x));
+            m1 = min(m1, min(m0, m0n) + tb.MLbase);
+            if (m1 >= FIN16) m1 = INF16;
+            minv = min(minv, m1);
+            sm.fm[x * P + x + d] = (short)m1;
+            sm.fm[(x + d) * P + x] = (short)m1;
+        }
+    };
+
+    // unit T: 2x2 tiles (i, i+1) x (j, j+1), i and j even, j - i = D: all four split minima share their operands; both
+    // operand pairs are one aligned 32-bit load from the square matrix.  Lanes = tiles x k parts; further k parts are
+    // separate units (partials in decp).  k = i+4 .. j-4 only touches FML of diagonals <= D-4.
+    auto unit_T = [&](int D, int q, int ntile, int ksh, int kwsh) {
+        const int KS = 1 << ksh, TPW = 32 >> kwsh;
+        const int grp = q >> ksh, kp = q & (KS - 1);
+        const int tl = grp * TPW + (lane & (TPW - 1)), kq = lane >> (5 - kwsh);
+        const bool valid = tl < ntile;
+        const int i = 2 * min(tl, ntile - 1), j = i + D;
+        const int cntk = max(D - 7, 0);
+        const int pidx = (kp << kwsh) + kq, psh = ksh + kwsh;
+        const int k0 = i + 4 + ((cntk * pidx) >> psh), k1 = i + 4 + ((cntk * (pidx + 1)) >> psh);
+        const unsigned *pa = reinterpret_cast<const unsigned *>(sm.fm + k0 * P + i);
+        const unsigned *pb = reinterpret_cast<const unsigned *>(sm.fm + (k0 + 1) * P + j);
+        unsigned acc0 = INF16 * 65537u, acc1 = INF16 * 65537u;
+        int k = k0;
+        for (; k + 3 < k1; k += 4, pa += 2 * P, pb += 2 * P) {
+#pragma unroll
+            for (int z = 0; z < 4; z++) {
+                const unsigned a = pa[z * (P / 2)], b = pb[z * (P / 2)];
+                acc0 = __viaddmin_s16x2(a, __byte_perm(b, 0, 0x1010), acc0);
+                acc1 = __viaddmin_s16x2(a, __byte_perm(b, 0, 0x3232), acc1);
+            }
+        }
+        for (; k < k1; k++, pa += P / 2, pb += P / 2) {
+            const unsigned a = pa[0], b = pb[0];
+            acc0 = __viaddmin_s16x2(a, __byte_perm(b, 0, 0x1010), acc0);
+            acc1 = __viaddmin_s16x2(a, __byte_perm(b, 0, 0x3232), acc1);
+        }
+        if (kwsh >= 1) {
+            acc0 = __vmins2(acc0, __shfl_xor_sync(full, acc0, 16));
+            acc1 = __vmins2(acc1, __shfl_xor_sync(full, acc1, 16));
+        }
+        if (kwsh == 2) {
+            acc0 = __vmins2(acc0, __shfl_xor_sync(full, acc0, 8));
+            acc1 = __vmins2(acc1, __shfl_xor_sync(full, acc1, 8));
+        }
+        if (valid && kq == 0) {
+            auto fin = [](int v) { return (short)(v >= FIN16 ? INF16 : v); };
+            short *dp = sm.decp + kp * 8 * PR;
+            dp[(D & 7) * PR + i] = fin((short)(acc0 & 0xffffu));
+            dp[((D - 1) & 7) * PR + i + 1] = fin((int)acc0 >> 16);
+            if (j + 1 < W) {
+                dp[((D + 1) & 7) * PR + i] = fin((short)(acc1 & 0xffffu));
+                dp[(D & 7) * PR + i + 1] = fin((int)acc1 >> 16);
+            }
+        }
     };
 
     for (int fold = blockIdx.x; fold < L.n_fold; fold += gridDim.x) {
@@ -454,245 +605,94 @@ mfe3_kernel(MfeLaunch L, const MfeTables *__restrict__ T, const Tab3 *__restrict
             int4 *p = reinterpret_cast<int4 *>(sm.ne);
             constexpr int n16 = (int)((offsetof(SM, decp) - offsetof(SM, ne) + 15) / 16);   // a ragged tail spills
             for (int k = tid; k < n16; k += NT) p[k] = inf4;                                 // into decp (rewritten before use)
-            for (int k = tid; k < 4 * PR; k += NT) sm.partc[k] = INF16;   // diagonals 4, 5 have no interior loops
-            if (tid < 2) sm.ctr[tid] = 0;
+            for (int k = tid; k < 4 * PR; k += NT) sm.partc[k] = INF16;   // diagonals 4 .. 7 have no interior loops of size >= 2
         }
-        int minv = 0;
+        minv = 0;
         __syncthreads();
-        if (warp < 4) build_list(TURN + 1 + warp);
+        // diagonals 4 .. 6: lists, hairpins (all they can close), then the rows of diagonal 4 and the lists of 7, 8
+        if (warp < 3) build_list(TURN + 1 + warp);
         __syncthreads();
-        for (int it = warp; it < 8; it += NW) {   // the other terms of diagonals 4, 5 (at most 4 chunks each)
+        for (int it = warp; it < 12; it += NW) {   // at most 4 list chunks per diagonal
             const int d = TURN + 1 + (it >> 2), c = it & 3;
-            if (d < W && c * 32 < sm.cnt[d & 3]) do_special(d, c);
+            if (d < W && c * 32 < sm.cnt[d & 3]) unit_P(d, c);
+        }
+        __syncthreads();
+        for (int u = warp; u < (W - TURN - 1 + SEG - 1) / SEG + 2; u += NW) {
+            if (u < 2)
+                build_list(TURN + 4 + u);   // slots 3 and 0: the list of diagonal 4 is no longer needed
+            else
+                unit_S(TURN + 1, u - 2);
         }
         __syncthreads();
 
-#ifdef SFB_TIMING
-        long long tX = 0, tXb = 0, tY = 0, tYb = 0, tc = clock64(), t0 = tc;
-#define TICK(acc) { long long tn = clock64(); acc += tn - tc; tc = tn; }
-#else
-#define TICK(acc)
-#endif
-        for (int d0 = TURN + 1; d0 < W; d0 += 2) {
-            const int nd = d0 + 1 < W ? 2 : 1;
-            // =================== phase X: statically balanced work units ================================
-            //   S  C and the derived rows of diagonals d0, d0+1 (25 row elements per unit)
-            //   T  split minima of tile diagonal d0+2 (2x2 tiles, packed)
-            //   L  lists of diagonals d0+4, d0+5
-            const int4 si = reinterpret_cast<const int4 *>(sm.stepinfo)[(d0 - TURN - 1) >> 1];
-            {
-                const int nseg0 = si.x & 255, nS = si.x >> 8, D = d0 + 2;
-                const int ntile = si.y & 255, ksh = (si.y >> 8) & 15, kwsh = si.y >> 12, KS = 1 << ksh, TPW = 32 >> kwsh;
-                const int nT = si.z;
-                const int uT = nS, uL = uT + nT, nH = uL + 2;
-                for (int u = warp; u < nH; u += NW) {
-                    if (u < uT) {
-                        // ---- S
-                        const int ds = u >= nseg0 ? 1 : 0, sg = ds ? u - nseg0 : u;
-                        const int d = d0 + ds, ncells = W - d;
-                        const int x = sg * SEG - 7 + lane;
-                        const bool valid = x >= 0 && x < ncells;
-                        const int i = valid ? x : 0, j = i + d;
-                        const int t = valid ? tb.ptype[sx[i + 1] * 6 + sx[j + 1]] : 0;
-                        int e = INF16;
-                        if (t) {
-                            e = min((int)sm.partc[(d & 3) * PR + i], (int)sm.parts[(d & 3) * PR + i]);
-                            if (e >= FIN16) e = INF16;
-                        }
-                        int vg = INF16, v1 = INF16, vb = INF16;
-                        const int t2 = tb.rtype[t];
-                        if (t && i > 0 && j < W - 1 && e < FIN16) {
-                            const int m2 = (t2 * 5 + sx[j + 2]) * 5 + sx[i];
-                            vg = e + tb.mmI[m2];
-                            v1 = e + tb.mm1n[m2];
-                            vb = e + tb.tAU[t2];
-                        }
-                        const int g1 = __shfl_up_sync(full, vg, 1), g2 = __shfl_up_sync(full, vg, 2);
-                        const int g3 = __shfl_up_sync(full, vg, 3), g4 = __shfl_up_sync(full, vg, 4);
-                        const int ne = min(g2, min(min(g1, g3) + tb.w2, min(vg, g4) + tb.w4));
-                        const int no = min(min(g1, g2) + tb.w1, min(vg, g3) + tb.w3);
-                        int m8 = min(vg, g1);
-                        m8 = min(m8, __shfl_up_sync(full, m8, 2));
-                        m8 = min(m8, __shfl_up_sync(full, m8, 4));
-                        if (valid && lane >= 7) {
-                            minv = min(minv, e);
-                            const int o16 = (d & (R16 - 1)) * PR + i, o32 = (d & (R32 - 1)) * PR + i;
-                            sm.rc[o16] = (short)e;
-                            sm.ctx[o16] = (unsigned char)t2;
-                            sm.g[o16] = (short)vg;
-                            {   // bulge | 1xn pairs: 16-bit halves of the 5'-indexed and the 3'-indexed copy
-                                short *wa = reinterpret_cast<short *>(sm.rpa) + 2 * ((d & (R32 - 1)) * PRW + i);
-                                short *wq = reinterpret_cast<short *>(sm.rpq) + 2 * ((d & (R32 - 1)) * PRW + j);
-                                wa[0] = (short)vb;
-                                if (i > 0) wa[-1] = (short)v1;
-                                wq[0] = (short)vb;
-                                wq[3] = (short)v1;
-                            }
-                            sm.ne[o32] = (short)ne;
-                            sm.no[o32] = (short)no;
-                            sm.m8[o32] = (short)m8;
-                            gC[tri4(d, W) + i] = (short)(e < FIN16 ? e + tb.ext[t * 36 + sx[i] * 6 + sx[j + 2]] : INF16);
-                        }
-                    } else if (u < uL) {
-                        // ---- T: 2x2 tile (i, i+1) x (j, j+1), i and j even, j - i = D: all four split minima share
-                        // their operands; both operand pairs are one aligned 32-bit load from the square matrix.
-                        // Lanes = tiles x k parts; further k parts are separate units (partials in decp).
-                        const int q = u - uT, grp = q >> ksh, kp = q & (KS - 1);
-                        const int tl = grp * TPW + (lane & (TPW - 1)), kq = lane >> (5 - kwsh);
-                        const bool valid = tl < ntile;
-                        const int i = 2 * min(tl, ntile - 1), j = i + D;
-                        const int cntk = D - 7;   // k = i+4 .. j-4; the band |a-b| < 4 of fm stays INF
-                        const int pidx = (kp << kwsh) + kq, psh = ksh + kwsh;
-                        const int k0 = i + 4 + ((cntk * pidx) >> psh), k1 = i + 4 + ((cntk * (pidx + 1)) >> psh);
-                        const unsigned *pa = reinterpret_cast<const unsigned *>(sm.fm + k0 * P + i);
-                        const unsigned *pb = reinterpret_cast<const unsigned *>(sm.fm + (k0 + 1) * P + j);
-                        unsigned acc0 = INF16 * 65537u, acc1 = INF16 * 65537u;
-                        int k = k0;
-                        for (; k + 3 < k1; k += 4, pa += 2 * P, pb += 2 * P) {
-#pragma unroll
-                            for (int z = 0; z < 4; z++) {
-                                const unsigned a = pa[z * (P / 2)], b = pb[z * (P / 2)];
-                                acc0 = __viaddmin_s16x2(a, __byte_perm(b, 0, 0x1010), acc0);
-                                acc1 = __viaddmin_s16x2(a, __byte_perm(b, 0, 0x3232), acc1);
-                            }
-                        }
-                        for (; k < k1; k++, pa += P / 2, pb += P / 2) {
-                            const unsigned a = pa[0], b = pb[0];
-                            acc0 = __viaddmin_s16x2(a, __byte_perm(b, 0, 0x1010), acc0);
-                            acc1 = __viaddmin_s16x2(a, __byte_perm(b, 0, 0x3232), acc1);
-                        }
-                        if (kwsh >= 1) {
-                            acc0 = __vmins2(acc0, __shfl_xor_sync(full, acc0, 16));
-                            acc1 = __vmins2(acc1, __shfl_xor_sync(full, acc1, 16));
-                        }
-                        if (kwsh == 2) {
-                            acc0 = __vmins2(acc0, __shfl_xor_sync(full, acc0, 8));
-                            acc1 = __vmins2(acc1, __shfl_xor_sync(full, acc1, 8));
-                        }
-                        if (valid && kq == 0) {
-                            auto fin = [](int v) { return (short)(v >= FIN16 ? INF16 : v); };
-                            short *dp = sm.decp + kp * 4 * PR;
-                            dp[(D & 3) * PR + i] = fin((short)(acc0 & 0xffffu));
-                            dp[((D - 1) & 3) * PR + i + 1] = fin((int)acc0 >> 16);
-                            if (j + 1 < W) {
-                                dp[((D + 1) & 3) * PR + i] = fin((short)(acc1 & 0xffffu));
-                                dp[(D & 3) * PR + i + 1] = fin((int)acc1 >> 16);
-                            }
-                        }
-                    } else {
-                        build_list(d0 + 4 + (u - uL));
-                    }
+        for (int d0 = TURN + 2; d0 - 2 < W; d0 += 2) {
+            const int2 si = reinterpret_cast<const int2 *>(sm.stepinfo)[(d0 - TURN - 2) >> 1];
+            const int nseg0 = si.x & 255, nS = (si.x >> 8) & 255, nF = si.x >> 16;
+            const int ntile = si.y & 255, ksh = (si.y >> 8) & 15, kwsh = (si.y >> 12) & 15, nT = si.y >> 16;
+            const int4 cn = *reinterpret_cast<const int4 *>(sm.cnt);   // d0 is odd: d0+2, d0+3 sit in slots (d0+2) & 3, +1
+            const bool up = ((d0 + 2) & 2) != 0;                       // (d0 + 2) & 3 is 3 or 1
+            const int n2 = up ? cn.w : cn.y, n3 = up ? cn.x : cn.z;
+            const int nch2 = (n2 + 31) >> 5, nP = nch2 + ((n3 + 31) >> 5);
+            const int uP = nS, uT = uP + nP, uF = uT + nT, uL = uF + nF, nH = uL + 2;
+            for (int u = warp; u < nH; u += NW) {
+                if (u < uP) {
+                    unit_S(u >= nseg0 ? d0 + 1 : d0, u >= nseg0 ? u - nseg0 : u);
+                } else if (u < uT) {
+                    const int it = u - uP;
+                    unit_P(it < nch2 ? d0 + 2 : d0 + 3, it < nch2 ? it : it - nch2);
+                } else if (u < uF) {
+                    unit_T(d0 + 1, u - uT, ntile, ksh, kwsh);
+                } else if (u < uL) {
+                    unit_F(d0 - 2, u - uF);
+                } else {
+                    build_list(d0 + 4 + (u - uL));
                 }
             }
-            TICK(tX)
-            __syncthreads();
-            TICK(tXb)
-            // =================== phase Y: multiloop matrix of diagonals d0, d0+1 (31 cells per unit, the neighbour
-            //   on d0 comes by shuffle), the table-driven terms of diagonals d0+2, d0+3 (one list chunk per unit) and
-            //   the interior loops of size >= 2 of diagonals d0+4, d0+5 (they only need rows <= d0+1) =============
+            // ---- C: interior loops of size >= 2 of the pairable cells of diagonals d0+2, d0+3 (rows <= d0-1): one
+            // cell per pass, lane = loop size U with its seven taps (see the header).  The cells continue the round
+            // robin of the units above.
             {
-                const int nc0 = W - d0, nc1 = nd == 2 ? W - d0 - 1 : 0;
-                const int nfin = si.w;
-                const int4 cn = *reinterpret_cast<const int4 *>(sm.cnt);   // d0 is even: slots (d0 & 2) .. hold d0+4, d0+5
-                const bool up = (d0 & 2) != 0;
-                const int n4 = up ? cn.z : cn.x, n5 = up ? cn.w : cn.y, n2 = up ? cn.x : cn.z, n3 = up ? cn.y : cn.w;
-                const int nch2 = (n2 + 31) >> 5, nch = nch2 + ((n3 + 31) >> 5);
-                const int nHy = nfin + nch;
-                for (int u = warp; u < nHy; u += NW) {
-                    if (u < nfin) {
-                        const int x = u * 31 + lane;
-                        const bool v0 = x < nc0;
-                        const int xx = v0 ? x : nc0 - 1;
-                        auto stemof = [&](int d, int xi) {
-                            const int o16 = (d & (R16 - 1)) * PR + xi;
-                            const int e = sm.rc[o16];
-                            const int t = tb.rtype[sm.ctx[o16]];
-                            return e < FIN16 ? e + tb.mlstem[t * 36 + sx[xi] * 6 + sx[xi + d + 2]] : INF16;
-                        };
-                        const int dec0 = decof(d0, xx);
-                        int m0 = min(dec0, stemof(d0, xx));
-                        if (d0 - 1 > TURN)
-                            m0 = min(m0, min((int)sm.fm[(xx + 1) * P + xx + d0], (int)sm.fm[xx * P + xx + d0 - 1]) + tb.MLbase);
-                        if (m0 >= FIN16) m0 = INF16;
-                        if (v0) {
-                            minv = min(minv, m0);
-                            sm.fm[x * P + x + d0] = (short)m0;
-                            sm.fm[(x + d0) * P + x] = (short)m0;
-                        }
-                        const int m0n = __shfl_down_sync(full, m0, 1);
-                        if (lane < 31 && x < nc1) {
-                            const int d = d0 + 1;
-                            int m1 = min(decof(d, x), stemof(d, x));
-                            m1 = min(m1, min(m0, m0n) + tb.MLbase);
-                            if (m1 >= FIN16) m1 = INF16;
-                            minv = min(minv, m1);
-                            sm.fm[x * P + x + d] = (short)m1;
-                            sm.fm[(x + d) * P + x] = (short)m1;
-                        }
-                    } else {
-                        const int it = u - nfin;
-                        do_special(it < nch2 ? d0 + 2 : d0 + 3, it < nch2 ? it : it - nch2);
-                    }
-                }
-                // ---- C: one pairable cell per pass; lane = loop size U with its nine taps (see the header).
-                // The cells continue the round robin of the heavy units (multiloop rows, list chunks) of this phase.
-                {
-                    int c = warp - nHy % NW;
-                    if (c < 0) c += NW;
+                int c = warp - nH % NW;
+                if (c < 0) c += NW;
 #pragma unroll 1
-                    for (int ds = 0; ds < 2; ds++) {
-                        const int d = d0 + 4 + ds, n = ds ? n5 : n4;
-                        if (c < n) {
-                            const int slot = (d - 2 - U) & (R32 - 1);
-                            const short *qA = smb + kA + ((d - 2 - UA) & (R32 - 1)) * PR;
-                            const short *qB = smb + O_M8 + slot * PR;
-                            const short *qC = smb + kC + ((d - 2 - UC) & (R32 - 1)) * PR;
-                            const unsigned *qR = sm.rpa + slot * PRW + 1;        // inner pair (i+1, j-1-U) and 1xn neighbour
-                            const unsigned *qL = sm.rpq + slot * PRW + d - 1;    // inner pair (i+1+U, j-1) and 1xn neighbour
-                            short *qP = sm.partc + (d & 3) * PR;
-                            const int4 *lst = reinterpret_cast<const int4 *>(sm.list) + (d & 3) * PR;
-                            int4 en = lst[c];
-                            for (; c < n; c += NW) {
-                                const int i = en.x, eI = en.y, e1 = en.z, eB = en.w;
-                                en = lst[c + NW];   // next entry (at most NW past the list end: still inside sm.list)
-                                const unsigned wr = qR[i], wl = qL[i];
-                                const short *pa = qA + i, *pb = qB + i, *pc = qC + i;
-                                const int xa = pa[0], xb10 = pb[10], xb18 = pb[18], xb26 = pb[26], xc = pc[0];
-                                const unsigned wm = __vmins2(wr, wl);
-                                const int xb = (int)(short)(wm & 0xffffu), x1 = (int)wm >> 16;
-                                int g = xa + cA;
-                                g = __viaddmin_s32(xb10, cB10, g);
-                                int g2 = xb18 + cB18;
-                                g2 = __viaddmin_s32(xb26, cB26, g2);
-                                g = __viaddmin_s32(xc, cC, g);
-                                const int aB = xb + cSB, a1 = x1 + cS1;
-                                int v = min(g, g2) + eI;
-                                v = __viaddmin_s32(a1, e1, v);
-                                v = __viaddmin_s32(aB, eB, v);
-#ifdef SFB_SHFL_REDUCE
-                                v = min(v, __shfl_xor_sync(full, v, 16));
-                                v = min(v, __shfl_xor_sync(full, v, 8));
-                                v = min(v, __shfl_xor_sync(full, v, 4));
-                                v = min(v, __shfl_xor_sync(full, v, 2));
-                                v = min(v, __shfl_xor_sync(full, v, 1));
-#else
-                                v = __reduce_min_sync(full, v);
-#endif
-                                if (lane == 0) qP[i] = (short)v;   // <= INF16 + size and mismatch terms: fits
-                            }
+                for (int ds = 0; ds < 2; ds++) {
+                    const int d = d0 + 2 + ds, n = ds ? n3 : n2;
+                    if (c < n) {
+                        const int slot = (d - 2 - U) & (R32 - 1);
+                        const short *qA = smb + kA + ((d - 2 - UA) & (R32 - 1)) * PR;
+                        const short *qB = smb + O_M8 + slot * PR;
+                        const short *qC = smb + kC + ((d - 2 - UC) & (R32 - 1)) * PR;
+                        const unsigned *qR = sm.rpa + slot * PRW + 1;        // inner pair (i+1, j-1-U) and 1xn neighbour
+                        const unsigned *qL = sm.rpq + slot * PRW + d - 1;    // inner pair (i+1+U, j-1) and 1xn neighbour
+                        short *qP = sm.partc + (d & 3) * PR;
+                        const int4 *lst = reinterpret_cast<const int4 *>(sm.list) + (d & 3) * LP;
+                        int4 en = lst[c];
+                        for (; c < n; c += NW) {
+                            const int i = en.x, eI = en.y, e1 = en.z, eB = en.w;
+                            en = lst[c + NW];   // next entry (at most NW past the list end: still inside sm.list)
+                            const unsigned wr = qR[i], wl = qL[i];
+                            const short *pa = qA + i, *pb = qB + i, *pc = qC + i;
+                            const int xa = pa[0], xb10 = pb[10], xb18 = pb[18], xb26 = pb[26], xc = pc[0];
+                            const unsigned wm = __vmins2(wr, wl);
+                            const int xb = (int)(short)(wm & 0xffffu), x1 = (int)wm >> 16;
+                            int g = xa + cA;
+                            g = __viaddmin_s32(xb10, cB10, g);
+                            int g2 = xb18 + cB18;
+                            g2 = __viaddmin_s32(xb26, cB26, g2);
+                            g = __viaddmin_s32(xc, cC, g);
+                            const int aB = xb + cSB, a1 = x1 + cS1;
+                            int v = min(g, g2) + eI;
+                            v = __viaddmin_s32(a1, e1, v);
+                            v = __viaddmin_s32(aB, eB, v);
+                            v = __reduce_min_sync(full, v);
+                            if (lane == 0) qP[i] = (short)v;   // <= INF16 + size and mismatch terms: fits
                         }
-                        c -= n;
                     }
+                    c -= n;
                 }
             }
-            TICK(tY)
             __syncthreads();
-            TICK(tYb)
         }
-#ifdef SFB_TIMING
-        if (blockIdx.x == 0 && lane == 0 && fold == 0)
-            printf("warp %d: X %lld  Xbar %lld  Y %lld  Ybar %lld  loop %lld\n", warp, tX, tXb, tY, tYb, clock64() - t0);
-#endif
 
         // ---- exterior loop: stage C (+ stem term) back from the scratch row, then F5 sequentially (warp 0)
         {
@@ -700,8 +700,8 @@ mfe3_kernel(MfeLaunch L, const MfeTables *__restrict__ T, const Tab3 *__restrict
             const int ntri = tri4(W, W);
             for (int k = tid; k < ntri; k += NT) cx[k] = __ldcg(gC + k);
             for (int k = tid; k <= min(W, TURN + 1); k += NT) sm.f5[k] = 0;
-            minv = __reduce_min_sync(full, minv);
-            if (lane == 0) sm.minv[warp] = minv;
+            const int minw = __reduce_min_sync(full, minv);
+            if (lane == 0) sm.minv[warp] = minw;
             __syncthreads();
             // F5[len] only needs F5[i] for i <= len - 5, so four consecutive lengths are independent: one (or two)
             // warps per length, then the running minimum along the block
