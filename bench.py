@@ -221,9 +221,13 @@ def run_ours(args):
     plan.close()
 
     # ---------------- end-to-end arm through the public API with host buffers: `e2e`
+    trace = os.environ.get("SFB_BENCH_TRACE")
+
     def e2e_step():
+        tt = [time.perf_counter()]
         t = scan.scan_record(seq, W, step, r, shuffle_type=stype, seed=42, first_window=w0, n_windows=nwin,
                              final_window=final)
+        tt.append(time.perf_counter())
         z100, mfe100, ed100 = pipeline.fold_inputs(t)
         acc = engine.Accumulator(L, W, step, w0, t.pair_tbl, z100, mfe100, ed100)
         try:        # halo rows go to the right neighbour over NCCL; rank 0 gathers the compact partner lists
@@ -232,7 +236,12 @@ def run_ours(args):
             launches_e2e[0] = acc.n_launches
         finally:
             acc.close()
+        tt.append(time.perf_counter())
         whole = multigpu.gather_tables(ptable, rank, world, dist if world > 1 else None)
+        tt.append(time.perf_counter())
+        if trace and rank == 0:
+            sys.stderr.write("e2e step: scan_record %.1f ms (device %.1f), accumulate %.1f ms, gather %.1f ms\n" % (
+                (tt[1] - tt[0]) * 1e3, t.ms_total, (tt[2] - tt[1]) * 1e3, (tt[3] - tt[2]) * 1e3))
         return t, ptable, whole
 
     launches_e2e = [0]

@@ -49,10 +49,47 @@ struct CudaError : std::runtime_error {
             throw CudaError(std::string(#expr) + ": " + cudaGetErrorString(e__));                        \
     } while (0)
 
+// Device-memory cache: a scan plan needs several hundred MB of scratch (shuffles, energies) and callers create one
+// plan per record, so freed blocks are kept (up to POOL_CAP bytes) and handed out again instead of going through
+// cudaFree / cudaMalloc, which cost tens to hundreds of milliseconds at these sizes.
+struct DevPool {
+    static constexpr size_t POOL_CAP = (size_t)3 << 30;
+    std::mutex mu;
+    std::vector<std::pair<size_t, void *>> blocks;   // (bytes, pointer) of cached blocks
+    size_t cached = 0;
+    void *take(size_t bytes) {
+        std::lock_guard<std::mutex> lk(mu);
+        int best = -1;
+        for (int k = 0; k < (int)blocks.size(); k++)
+            if (blocks[k].first >= bytes && blocks[k].first <= 2 * bytes + 4096 &&
+                (best < 0 || blocks[k].first < blocks[best].first))
+                best = k;
+        if (best < 0) return nullptr;
+        void *p = blocks[best].second;
+        cached -= blocks[best].first;
+        blocks.erase(blocks.begin() + best);
+        return p;
+    }
+    bool give(size_t bytes, void *p) {
+        std::lock_guard<std::mutex> lk(mu);
+        if (cached + bytes > POOL_CAP) return false;
+        blocks.emplace_back(bytes, p);
+        cached += bytes;
+        return true;
+    }
+    void clear() {
+        std::lock_guard<std::mutex> lk(mu);
+        for (auto &b : blocks) cudaFree(b.second);
+        blocks.clear();
+        cached = 0;
+    }
+};
+DevPool &g_pool = *new DevPool;   // never destroyed: buffers may be released during interpreter shutdown
+
 template <typename T>
 struct DevBuf {
     T *p = nullptr;
-    size_t n = 0;
+    size_t n = 0, cap_bytes = 0;
     DevBuf() = default;
     DevBuf(const DevBuf &) = delete;
     DevBuf &operator=(const DevBuf &) = delete;
@@ -60,12 +97,29 @@ struct DevBuf {
     void alloc(size_t count) {
         release();
         n = count;
-        if (count) CK(cudaMalloc(&p, count * sizeof(T)));
+        if (!count) return;
+        const size_t bytes = ((count * sizeof(T) + 511) / 512) * 512;
+        if (void *q = g_pool.take(bytes)) {
+            p = static_cast<T *>(q);
+            cap_bytes = bytes;   // the cached block may be larger; only its first `bytes` are used
+            return;
+        }
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e != cudaSuccess) {   // out of memory: drop the cache and try once more
+            cudaGetLastError();
+            g_pool.clear();
+            CK(cudaMalloc(&p, bytes));
+        }
+        cap_bytes = bytes;
     }
     void release() {
-        if (p) cudaFree(p);
+        if (p) {
+            // the block may be handed to another buffer at once: work queued on it must have finished
+            if (g_ctx.ready) cudaStreamSynchronize(g_ctx.stream);
+            if (!g_pool.give(cap_bytes, p)) cudaFree(p);
+        }
         p = nullptr;
-        n = 0;
+        n = cap_bytes = 0;
     }
 };
 
@@ -236,6 +290,7 @@ int sfb_init(int device_ordinal, const char *par_file_or_null) {
 
 void sfb_shutdown(void) {
     std::lock_guard<std::mutex> lk(g_mu);
+    g_pool.clear();
     if (g_ctx.d_mfe) cudaFree(g_ctx.d_mfe);
     if (g_ctx.d_pf) cudaFree(g_ctx.d_pf);
     if (g_ctx.own_stream) cudaStreamDestroy(g_ctx.own_stream);
