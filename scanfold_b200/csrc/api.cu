@@ -153,6 +153,13 @@ int check_model(const sfb_model *m) {
     return 0;
 }
 
+// hard constraints without enforced pairs: only per-nucleotide flags, which the fast kernels fold in
+bool hc_is_simple(const uint8_t *hc, size_t n) {
+    for (size_t k = 0; k < n; k++)
+        if (hc[k] == '(' || hc[k] == ')') return false;
+    return true;
+}
+
 void encode_host(const uint8_t *ascii, size_t n, std::vector<uint8_t> &codes) {
     codes.resize(n);
     for (size_t k = 0; k < n; k++) codes[k] = (uint8_t)encode_nt(ascii[k]);
@@ -181,11 +188,12 @@ struct FoldWork {  // device scratch for one MFE launch
     // energy-only unconstrained folds: int16 warp-per-fold kernel, then the int32 kernel on whatever it flagged
     void launch_energy_only(MfeLaunch L, cudaStream_t st, int *n_launch) const {
         const bool use3 = engine() == 3 && mfe3_supports(L.W), use2 = engine() != 1 && mfe2_supports(L.W) && !L.pair_tbl;
-        if ((use3 || use2) && !L.hc && !L.sc && L.max_span <= 0) {   // mfe3 also traces the structure back
+        const bool hc3 = L.hc && L.hc_simple && use3;   // per-nucleotide hard constraints: folded into mfe3
+        if ((use3 || use2) && (!L.hc || hc3) && !L.sc && L.max_span <= 0) {   // mfe3 also traces the structure back
             MfeLaunch L2 = L;
             L2.gscratch = scratch2.p;
             L2.gscratch_per_cta = (long long)per_warp2;
-            if (use3)
+            if (use3 && (!L.hc || hc3))
                 launch_mfe3(L2, g_ctx.d_mfe, g_ctx.n_sm, st, n_launch);
             else
                 launch_mfe2(L2, g_ctx.d_mfe, g_ctx.n_sm, st, n_launch);
@@ -221,6 +229,7 @@ struct sfb_scan_plan {
     int n_slots = 0;        // n_windows + final
     int chunk = 0;          // windows per chunk
     bool constrained = false;
+    bool hc_simple = false;   // the record's constraint line has no '(' ')': the fast kernels take it
     std::vector<uint8_t> parity_host;  // not owned copy avoided: pointer kept in a.parity_shuffles
     DevBuf<uint8_t> seq, hc, nat, shuf, hc_win, parity_ascii;
     DevBuf<int32_t> es1, sc_win;
@@ -354,6 +363,7 @@ int sfb_fold_batch(const uint8_t *seqs, int n_seq, int len, const sfb_model *mod
         MfeLaunch L{};
         L.seqs = d_seq.p;
         L.hc = d_hc.p;
+        L.hc_simple = hc && hc_is_simple(hc, (size_t)n_seq * len);
         L.sc = d_sc.p;
         L.n_fold = n_seq;
         L.W = len;
@@ -415,6 +425,7 @@ int sfb_pf_batch(const uint8_t *seqs, int n_seq, int len, const sfb_model *model
         PfLaunch L{};
         L.seqs = d_seq.p;
         L.hc = d_hc.p;
+        L.hc_simple = hc && hc_is_simple(hc, (size_t)n_seq * len);
         L.sc = d_sc.p;
         L.n_fold = n_seq;
         L.W = len;
@@ -463,6 +474,7 @@ int sfb_scan_plan_create(const sfb_scan_args *args, sfb_scan_plan **plan_out) {
         P->a = a;
         P->n_slots = a.n_windows + (a.final_window ? 1 : 0);
         P->constrained = a.hc || a.react;
+        P->hc_simple = a.hc && hc_is_simple(a.hc, (size_t)a.L);
         const int n = P->n_slots;
         long long per_win = (long long)std::max(a.r, 1) * a.W;
         long long chunk = (768ll << 20) / std::max(per_win, 1ll);
@@ -632,8 +644,13 @@ int sfb_scan_plan_run(sfb_scan_plan *P, float *ms_total, float *ms_mfe, int32_t 
                 L.max_span = a.model.max_bp_span;
                 L.e_out = P->mfe.p + c0;
                 L.pair_tbl = P->pair_tbl.p + (size_t)c0 * W;
-                P->fw.fill(L);
-                launch_mfe(L, g_ctx.d_mfe, g_ctx.n_sm, st, &n_launch);
+                L.hc_simple = P->hc_simple;
+                if (P->hc_simple && !a.react && a.model.max_bp_span <= 0) {
+                    P->fw.launch_energy_only(L, st, &n_launch);   // per-nucleotide flags only: mfe3 (+ int32 redo)
+                } else {
+                    P->fw.fill(L);
+                    launch_mfe(L, g_ctx.d_mfe, g_ctx.n_sm, st, &n_launch);
+                }
             } else if (!need_unc) {
                 CK(cudaMemcpyAsync(P->mfe.p + c0, P->nat_unc.p + c0, sizeof(int32_t) * cn, cudaMemcpyDeviceToDevice, st));
             }
@@ -643,6 +660,7 @@ int sfb_scan_plan_run(sfb_scan_plan *P, float *ms_total, float *ms_mfe, int32_t 
                 PfLaunch L{};
                 L.seqs = P->nat.p;
                 L.hc = a.hc ? P->hc_win.p : nullptr;
+                L.hc_simple = P->hc_simple;
                 L.n_fold = cn_regular;
                 L.W = W;
                 L.max_span = a.model.max_bp_span;

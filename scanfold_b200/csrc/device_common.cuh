@@ -77,6 +77,7 @@ struct MfeLaunch {
     long long gscratch_per_cta;  // ints
     int mats_in_gmem;     // 0: everything in shared memory; 1: C/FML in global; 2: rolling buffers too
     int redo_only;        // 1: only folds whose e_out holds MFE_REDO (flagged by the int16 kernel)
+    int hc_simple;        // hc holds no '(' ')' : per-nucleotide flags only ('x' '<' '>'), which mfe3 folds in
 };
 constexpr int MFE_REDO = 0x7fffff00;  // e_out marker: int16 range exceeded, fold again in int32
 
@@ -90,6 +91,7 @@ struct PfLaunch {
     double *bpp;          // NULL or [n_fold][W][W]
     double *gscratch;     // per-CTA workspace
     long long gscratch_per_cta;  // doubles
+    int hc_simple;        // hc holds no '(' ')' : per-nucleotide flags only, which pf2 folds in
 };
 
 void launch_mfe(const MfeLaunch &L, const MfeTables *d_tab, int n_sm, cudaStream_t stream, int *n_launches);

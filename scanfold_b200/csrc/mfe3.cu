@@ -99,6 +99,8 @@ struct Smem3 {
                                                  // closing pair; the traceback stack of the natives reuses it
     unsigned char ctx[R16 * PR];
     unsigned char sx[P + 8];   // sx[k+1] = code of nucleotide k, sx[0] = sx[W+1] = 5
+    unsigned char sx5[P + 8], sx3[P + 8];   // the same, 5 (never pairs) where hard constraints forbid the nucleotide
+                                            // as 5' / 3' partner ('x' both, '>' 5', '<' 3')
     alignas(16) int cnt[4];   // pairable cells of the diagonals d with d & 3 = slot (0 beyond the last diagonal)
     int ctr[2];
     int minv[32];
@@ -381,7 +383,7 @@ mfe3_kernel(MfeLaunch L, const MfeTables *__restrict__ T, const Tab3 *__restrict
         const int ncells = W - d, slot = d & 3;
         for (int i0 = 0; i0 < ncells; i0 += 32) {
             const int i = i0 + lane;
-            const int t = i < ncells ? tb.ptype[sx[i + 1] * 6 + sx[i + d + 1]] : 0;
+            const int t = i < ncells ? tb.ptype[sm.sx5[i + 1] * 6 + sm.sx3[i + d + 1]] : 0;
             const unsigned m = __ballot_sync(full, t != 0);
             if (t) {
                 const int mi = (t * 5 + sx[i + 2]) * 5 + sx[i + d];
@@ -457,7 +459,7 @@ mfe3_kernel(MfeLaunch L, const MfeTables *__restrict__ T, const Tab3 *__restrict
         const int x = sg * SEG - 7 + lane;
         const bool valid = x >= 0 && x < ncells;
         const int i = valid ? x : 0, j = i + d;
-        const int t = valid ? tb.ptype[sx[i + 1] * 6 + sx[j + 1]] : 0;
+        const int t = valid ? tb.ptype[sm.sx5[i + 1] * 6 + sm.sx3[j + 1]] : 0;
         int e = INF16;
         if (t) {
             e = min((int)sm.partc[(d & 3) * PR + i], (int)sm.parts[(d & 3) * PR + i]);
@@ -598,8 +600,14 @@ mfe3_kernel(MfeLaunch L, const MfeTables *__restrict__ T, const Tab3 *__restrict
     for (int fold = blockIdx.x; fold < L.n_fold; fold += gridDim.x) {
         __syncthreads();
         // ---- prologue: sequence with sentinels, INF in every ring row and in the FML matrix
-        for (int k = tid; k < W + 2; k += NT)
-            sm.sx[k] = (k == 0 || k == W + 1) ? 5 : L.seqs[(size_t)fold * W + k - 1];
+        for (int k = tid; k < W + 2; k += NT) {
+            const bool edge = k == 0 || k == W + 1;
+            const int code = edge ? 5 : L.seqs[(size_t)fold * W + k - 1];
+            const char ch = (L.hc && !edge) ? (char)L.hc[(size_t)fold * W + k - 1] : '.';
+            sm.sx[k] = (unsigned char)code;
+            sm.sx5[k] = (unsigned char)((ch == 'x' || ch == '>') ? 5 : code);   // '>' : pairs upstream only
+            sm.sx3[k] = (unsigned char)((ch == 'x' || ch == '<') ? 5 : code);   // '<' : pairs downstream only
+        }
         {
             const int4 inf4 = make_int4(INF16 * 65537, INF16 * 65537, INF16 * 65537, INF16 * 65537);
             int4 *p = reinterpret_cast<int4 *>(sm.ne);

@@ -2,7 +2,8 @@
 // shared memory, windows up to 120 nt without constraints.
 //
 // Replaces fc.pf(), fc.centroid(), fc.mean_bp_distance() -- ScanFold.py:498,503-504 -- for the unconstrained
-// native windows of a scan (pf.cu keeps the hard / soft constrained and the long windows).
+// native windows of a scan, also under per-nucleotide hard constraints ('x' '<' '>'); pf.cu keeps enforced pairs,
+// soft constraints and the long windows.
 //
 // Both passes walk the matrix by COLUMN (3' end) instead of by anti-diagonal: every cell of a column only depends
 // on earlier columns, all lanes of a warp share the column, and an interior-loop candidate (u1, u2) is then a
@@ -57,6 +58,7 @@ struct Smem2 {
     short cen[P2 + 8];
     unsigned char S[P2 + 8];
     unsigned char ty[P2 + 8];   // pair type of the cells of the current column
+    unsigned char can5[P2 + 8], can3[P2 + 8];   // hard constraints: may be the 5' / 3' partner of a pair
 };
 
 template <int A, int B, class F>
@@ -277,7 +279,12 @@ pf2_kernel(PfLaunch L, const MfeTables *__restrict__ MT, const PfTables *__restr
 
     for (int fold = blockIdx.x; fold < L.n_fold; fold += gridDim.x) {
         __syncthreads();
-        for (int k = tid; k < W; k += NT2) sm.S[k] = L.seqs[(long long)fold * W + k];
+        for (int k = tid; k < W; k += NT2) {
+            sm.S[k] = L.seqs[(long long)fold * W + k];
+            const char ch = L.hc ? (char)L.hc[(long long)fold * W + k] : '.';
+            sm.can5[k] = !(ch == 'x' || ch == '>');
+            sm.can3[k] = !(ch == 'x' || ch == '<');
+        }
         for (int k = tid; k < P2 + 8; k += NT2) {
             sm.cen[k] = 0;
             sm.qm1[0][k] = 0.;
@@ -298,7 +305,7 @@ pf2_kernel(PfLaunch L, const MfeTables *__restrict__ MT, const PfTables *__restr
             // ---- A: separable interior loops, warp = (32 cells) x (u2 group)
             {
                 const int iblk = warp & 3, s = warp >> 2, i = iblk * 32 + lane;
-                const int t = i <= j - TURN - 1 ? pair_type(S[i], S[j]) : 0;
+                const int t = (i <= j - TURN - 1 && sm.can5[i] && sm.can3[j]) ? pair_type(S[i], S[j]) : 0;
                 if (s == 0 && i < P2) sm.ty[i] = (unsigned char)t;
                 if (__any_sync(full, t != 0)) {
                     if (t) {
@@ -572,7 +579,7 @@ static bool &pf2_enabled() {
 void pf2_set_enabled(bool on) { pf2_enabled() = on; }
 
 bool pf2_supports(const PfLaunch &L) {
-    return pf2_enabled() && !L.hc && !L.sc && L.max_span <= 0 && L.W >= 2 * TURN + 4 && L.W <= P2;
+    return pf2_enabled() && (!L.hc || L.hc_simple) && !L.sc && L.max_span <= 0 && L.W >= 2 * TURN + 4 && L.W <= P2;
 }
 
 size_t pf2_scratch_doubles_per_cta() { return 2 * (size_t)P2 * P2; }

@@ -124,6 +124,35 @@ def test_partition_function_constraints(engine, oracle):
         assert db_from_pt(res["centroid"][k]) == o["centroid"]
 
 
+@pytest.mark.parametrize("W", [40, 90, 120, 200])
+def test_flag_only_hard_constraints_fast_kernels(engine, oracle, W):
+    """Constraint lines without brackets ('x' '<' '>' '|' only) run on the fast kernels (mfe3 with traceback, pf2 up to
+    120 nt): energies / structures bit-exact and PF within 1e-6 of the oracle, and equal to the int32 / first PF kernel."""
+    rng = random.Random(100 + W)
+    seqs = rand_seqs(900 + W, 48, W, gc_rich=True)
+    hcs = [_rand_hc(rng, W, False) for _ in seqs]
+    hcs[0] = "x" * W
+    hcs[1] = "." * W
+    e, pt = engine.fold_batch(seqs, hc=hcs, structure=True)
+    res = engine.pf_batch(seqs, hc=hcs)
+    try:
+        engine.set_engines(mfe=1, pf=1)
+        e1, pt1 = engine.fold_batch(seqs, hc=hcs, structure=True)
+        res1 = engine.pf_batch(seqs, hc=hcs)
+    finally:
+        engine.set_engines(mfe=3, pf=2)
+    assert np.array_equal(e, e1) and np.array_equal(pt, pt1)
+    assert np.allclose(res["ed"], res1["ed"], rtol=1e-9, atol=1e-9) and np.allclose(res["dG"], res1["dG"], rtol=1e-9, atol=1e-9)
+    assert np.array_equal(res["centroid"], res1["centroid"])
+    for k in range(0, len(seqs), 3):
+        eo, so = oracle.mfe(seqs[k], hc=hcs[k])
+        assert e[k] == eo and db_from_pt(pt[k]) == so, (W, k, seqs[k], hcs[k])
+        o = oracle.pf(seqs[k], hc=hcs[k])
+        assert abs(res["dG"][k] - o["dG"]) <= 1e-6 * max(1.0, abs(o["dG"]))
+        assert abs(res["ed"][k] - o["ed"]) <= 1e-6 * max(1.0, abs(o["ed"]))
+        assert db_from_pt(res["centroid"][k]) == o["centroid"]
+
+
 def test_random_parameter_file(engine, oracle, tmp_path):
     """A randomised table set catches any index-order disagreement between the two table loaders / kernels."""
     import os
