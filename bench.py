@@ -300,7 +300,11 @@ def run_ours(args):
                          "achieved_dense": dense * n_folds / mfe_s / 1e9,
                          "smem_ld32_peak_per_s": peak_lds, "kernel_ms_per_step": mfe_s * 1e3,
                          "kernel_share_of_step": ms_mfe / ms_dev if world == 1 else None,
-                         "hbm_algorithmic_bytes_per_fold": W + 4, "traffic": None},
+                         "hbm_algorithmic_bytes_per_fold": W + 4,
+                         # DRAM bytes of the fold kernels of one step: ncu --set full capture of mfe3_kernel
+                         # (profiles/r01n_mfe3_kernel_ncu.txt: 25.0 MB read + written per 200,000 folds at W=120)
+                         "traffic": (125.0 * n_folds) if W == 120 else None,
+                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per fold from profiles/r01n (ncu), x folds per step"},
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:

@@ -175,8 +175,9 @@ struct FoldWork {  // device scratch for one MFE launch
         size_t need = per_cta * (size_t)mfe_grid_size(W, g_ctx.n_sm, n_fold);
         if (need > scratch.n) scratch.alloc(need);
         if (mfe2_supports(W) || mfe3_supports(W)) {
-            per_warp2 = mfe2_scratch_shorts_per_warp(W);
-            size_t rows = std::max((size_t)4 * mfe2_grid_size(g_ctx.n_sm, n_fold), (size_t)mfe3_max_ctas(g_ctx.n_sm));
+            per_warp2 = mfe3_supports(W) ? mfe3_scratch_shorts_per_cta(W) : mfe2_scratch_shorts_per_warp(W);
+            size_t rows = (size_t)mfe3_max_ctas(g_ctx.n_sm, W);
+            if (mfe2_supports(W)) rows = std::max(rows, (size_t)4 * mfe2_grid_size(g_ctx.n_sm, n_fold));
             size_t need2 = (per_warp2 * rows + 1) / 2;
             if (need2 > scratch2.n) scratch2.alloc(need2);
         }

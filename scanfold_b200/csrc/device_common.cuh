@@ -104,7 +104,8 @@ void mfe2_upload_tables(const MfeTables &M);
 void launch_mfe2(const MfeLaunch &L, const MfeTables *d_tab, int n_sm, cudaStream_t stream, int *n_launches);
 // third-generation energy-only kernel (mfe3.cu): one CTA per fold, stencil / range-minimum interior loops
 bool mfe3_supports(int W);
-int mfe3_max_ctas(int n_sm);
+int mfe3_max_ctas(int n_sm, int W);
+size_t mfe3_scratch_shorts_per_cta(int W);
 void mfe3_upload_tables(const MfeTables &M);
 void launch_mfe3(const MfeLaunch &L, const MfeTables *d_tab, int n_sm, cudaStream_t stream, int *n_launches);
 int mfe_grid_size(int W, int n_sm, int n_fold);

@@ -74,10 +74,11 @@ Tab3 *g_dtab3 = nullptr;
 bool g_mfe3_ok = false;
 
 constexpr int BIG = 1 << 20;  // size term of a disabled tap: the sum never wins whatever the load returns
-constexpr int KSMAX = 2;      // the split loop of a tile diagonal is cut into at most 2 work items
+constexpr int KSMAX = 4;      // the split loop of a tile diagonal is cut into at most 2 (4: global FML) work items
 
-template <int P>
+template <int P, bool FMG = false>
 struct Smem3 {
+    static constexpr int KSM = FMG ? 4 : 2;   // copies of the split-minimum ring
     // ring pitch in shorts: PR/2 words = 31 (mod 32), so lane U reading row (c-U) at offset a*U (a = 0, 1/2, 1) lands in
     // bank (1+a/2)*U: the 32 taps of one warp load hit 32 different banks
     static constexpr int PR = P <= 64 ? P + 2 : ((P + 2 + 63) / 64) * 64 - 2;   // small windows: shared memory first
@@ -90,8 +91,9 @@ struct Smem3 {
     unsigned rpq[R32 * PRW];  // [row][q]: lo = C + TerminalAU of cell (q-dd, q), hi = C + mismatch1nI of cell (.., q-1)
     short g[R16 * PR];
     short rc[R16 * PR];
-    short fm[P * P];          // fm[a][b]: FML[a,b] for b > a (row = 5' end), FML[b,a] for b < a (row = 3' end)
-    short decp[KSMAX * 8 * PR];   // split minima of the last 8 diagonals, one copy per k part
+    short fm[FMG ? 8 : P * P];   // fm[a][b]: FML[a,b] for b > a (row = 5' end), FML[b,a] for b < a (row = 3' end);
+                                 // FMG: the matrix sits behind the scratch row in global memory instead
+    short decp[KSM * 8 * PR];   // split minima of the last 8 diagonals, one copy per k part
     short partc[4 * PR], parts[4 * PR];   // partial minima by diagonal & 3: loops of size >= 2 / everything else
     short f5[P + 8];
     static constexpr int LP = P;              // list pitch (entries): a diagonal has fewer than P cells
@@ -114,7 +116,12 @@ __host__ __device__ __forceinline__ int tri4(int d, int W) {  // first cell of d
 
 // work units the split loop of tile diagonal D is cut into (long diagonals have few tiles: their k range is
 // split over the lanes of one warp instead)
-__host__ __device__ __forceinline__ int ksplit(int D, int W) { return (D < 36 || (W - 1 - D) / 2 + 1 <= 16) ? 1 : 2; }
+// FMG: the multiloop matrix lives in global memory (windows above 200 nt): its loads have L2 latency, so long split loops
+// are cut in four whatever the number of tiles
+__host__ __device__ __forceinline__ int ksplit(int D, int W, bool fmg = false) {
+    if (fmg) return D >= 71 ? 4 : (D >= 36 ? 2 : 1);
+    return (D < 36 || (W - 1 - D) / 2 + 1 <= 16) ? 1 : 2;
+}
 
 __device__ int hairpin_special3(const MfeTables *T, const Tab3 &tb, const unsigned char *sx, int i, int j, int type) {
     // loops of 3, 4 and 6 nucleotides: tabulated tri- / tetra- / hexaloops; sx is offset by one
@@ -176,8 +183,8 @@ __device__ int e_intloop3(const MfeTables *T, int n1, int n2, int type, int t2, 
 // Traceback by one warp in the candidate order of SURVEY A.4 (the same order as mfe.cu's serial traceback): the
 // control flow is warp-uniform, every candidate search is spread over the lanes and the first match in order wins.
 // cx: C + exterior stem term by diagonal (the F5 staging area); pt: 1-based partner, 0 = unpaired.
-template <int P>
-__device__ bool traceback3(Smem3<P> &sm, const MfeTables *T, const short *cx, short *pt, int W, int lane) {
+template <int P, bool FMG, class SMT>
+__device__ bool traceback3(SMT &sm, const short *fm, const MfeTables *T, const short *cx, short *pt, int W, int lane) {
     const Tab3 &tb = sm.tb;
     const unsigned char *sx = sm.sx;
     const unsigned full = 0xffffffffu;
@@ -190,7 +197,9 @@ __device__ bool traceback3(Smem3<P> &sm, const MfeTables *T, const short *cx, sh
     };
     auto MM = [&](int i, int j) {
         if (j - i <= TURN) return INF;
-        const int v = sm.fm[i * P + j];
+        int v;
+        if constexpr (FMG) v = __ldcg(fm + i * P + j);
+        else v = fm[i * P + j];
         return v >= FIN16 ? INF : v;
     };
     for (int k = lane; k < W; k += 32) pt[k] = 0;
@@ -322,11 +331,11 @@ __device__ bool traceback3(Smem3<P> &sm, const MfeTables *T, const short *cx, sh
     return true;
 }
 
-template <int P, int NW, int OCC>
+template <int P, int NW, int OCC, bool FMG>
 __global__ void __launch_bounds__(NW * 32, OCC)
 mfe3_kernel(MfeLaunch L, const MfeTables *__restrict__ T, const Tab3 *__restrict__ gtab) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    using SM = Smem3<P>;
+    using SM = Smem3<P, FMG>;
     SM &sm = *reinterpret_cast<SM *>(smem_raw);
     constexpr int NT = NW * 32, PR = SM::PR, NWH = NW / 2;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -348,13 +357,23 @@ mfe3_kernel(MfeLaunch L, const MfeTables *__restrict__ T, const Tab3 *__restrict
         const int nF = d0 - 2 < W ? (W - (d0 - 2) + 30) / 31 : 0;
         const int D = d0 + 1;
         const int ntile = D <= W - 1 ? (W - 1 - D) / 2 + 1 : 0;
-        const int KS = ksplit(D, W), ksh = KS >> 1 /* log2 of 1, 2, 4 */;
+        const int KS = ksplit(D, W, FMG), ksh = KS == 4 ? 2 : KS >> 1 /* log2 of 1, 2, 4 */;
         const int kwsh = ntile > 16 ? 0 : (ntile > 8 ? 1 : 2), TPW = 32 >> kwsh;   // k parts inside a warp
         const int nT = ((ntile + TPW - 1) >> (5 - kwsh)) << ksh;
         reinterpret_cast<int2 *>(sm.stepinfo)[st] =
             make_int2(nseg0 | ((nseg0 + nseg1) << 8) | (nF << 16), ntile | (ksh << 8) | (kwsh << 12) | (nT << 16));
     }
     short *gC = reinterpret_cast<short *>(L.gscratch) + (size_t)blockIdx.x * L.gscratch_per_cta;
+    auto ldfm = [&](const short *q) -> short {   // FMG: from L2 (written by this CTA in an earlier phase)
+        if constexpr (FMG) return __ldcg(q);
+        else return *q;
+    };
+    auto ldfm32 = [&](const unsigned *q) -> unsigned {
+        if constexpr (FMG) return __ldcg(q);
+        else return *q;
+    };
+    // the multiloop matrix: shared memory, or (FMG) the P x P shorts behind the scratch row of this CTA
+    short *const fm = FMG ? gC + (((size_t)tri4(W, W) + 63) & ~(size_t)63) : sm.fm;
     const short *smb = sm.ne;   // every tap address below is an offset (in shorts) from here
     constexpr int PRW = SM::PRW;
     constexpr int O_NE = 0, O_NO = R32 * PR, O_M8 = 2 * R32 * PR;   // in shorts from smb
@@ -398,7 +417,7 @@ mfe3_kernel(MfeLaunch L, const MfeTables *__restrict__ T, const Tab3 *__restrict
     auto decof = [&](int d, int xi) {
         if (d < 2 * TURN + 3) return INF16;
         const int Dsrc = (d & 1) ? ((xi & 1) ? d + 1 : d - 1) : d;
-        const int ks = ksplit(Dsrc, W);
+        const int ks = ksplit(Dsrc, W, FMG);
         int v = sm.decp[(d & 7) * PR + xi];
         for (int kp = 1; kp < ks; kp++) v = min(v, (int)sm.decp[(kp * 8 + (d & 7)) * PR + xi]);
         return v;
@@ -528,12 +547,12 @@ mfe3_kernel(MfeLaunch L, const MfeTables *__restrict__ T, const Tab3 *__restrict
         if (nc0 > 0) {
             m0 = min(decof(dA, xx), stemof(dA, xx));
             if (dA - 1 > TURN)
-                m0 = min(m0, min((int)sm.fm[(xx + 1) * P + xx + dA], (int)sm.fm[xx * P + xx + dA - 1]) + tb.MLbase);
+                m0 = min(m0, min((int)ldfm(fm + (xx + 1) * P + xx + dA), (int)ldfm(fm + xx * P + xx + dA - 1)) + tb.MLbase);
             if (m0 >= FIN16) m0 = INF16;
             if (v0) {
                 minv = min(minv, m0);
-                sm.fm[x * P + x + dA] = (short)m0;
-                sm.fm[(x + dA) * P + x] = (short)m0;
+                fm[x * P + x + dA] = (short)m0;
+                fm[(x + dA) * P + x] = (short)m0;
             }
         }
         const int m0n = __shfl_down_sync(full, m0, 1);
@@ -543,8 +562,8 @@ mfe3_kernel(MfeLaunch L, const MfeTables *__restrict__ T, const Tab3 *__restrict
             m1 = min(m1, min(m0, m0n) + tb.MLbase);
             if (m1 >= FIN16) m1 = INF16;
             minv = min(minv, m1);
-            sm.fm[x * P + x + d] = (short)m1;
-            sm.fm[(x + d) * P + x] = (short)m1;
+            fm[x * P + x + d] = (short)m1;
+            fm[(x + d) * P + x] = (short)m1;
         }
     };
 
@@ -560,20 +579,26 @@ mfe3_kernel(MfeLaunch L, const MfeTables *__restrict__ T, const Tab3 *__restrict
         const int cntk = max(D - 7, 0);
         const int pidx = (kp << kwsh) + kq, psh = ksh + kwsh;
         const int k0 = i + 4 + ((cntk * pidx) >> psh), k1 = i + 4 + ((cntk * (pidx + 1)) >> psh);
-        const unsigned *pa = reinterpret_cast<const unsigned *>(sm.fm + k0 * P + i);
-        const unsigned *pb = reinterpret_cast<const unsigned *>(sm.fm + (k0 + 1) * P + j);
+        const unsigned *pa = reinterpret_cast<const unsigned *>(fm + k0 * P + i);
+        const unsigned *pb = reinterpret_cast<const unsigned *>(fm + (k0 + 1) * P + j);
         unsigned acc0 = INF16 * 65537u, acc1 = INF16 * 65537u;
         int k = k0;
-        for (; k + 3 < k1; k += 4, pa += 2 * P, pb += 2 * P) {
+        constexpr int UNR = FMG ? 8 : 4;   // loads in flight per lane: 2 * UNR (L2 latency when the matrix is global)
+        for (; k + UNR - 1 < k1; k += UNR, pa += UNR * (P / 2), pb += UNR * (P / 2)) {
+            unsigned a[UNR], b[UNR];
 #pragma unroll
-            for (int z = 0; z < 4; z++) {
-                const unsigned a = pa[z * (P / 2)], b = pb[z * (P / 2)];
-                acc0 = __viaddmin_s16x2(a, __byte_perm(b, 0, 0x1010), acc0);
-                acc1 = __viaddmin_s16x2(a, __byte_perm(b, 0, 0x3232), acc1);
+            for (int z = 0; z < UNR; z++) {
+                a[z] = ldfm32(pa + z * (P / 2));
+                b[z] = ldfm32(pb + z * (P / 2));
+            }
+#pragma unroll
+            for (int z = 0; z < UNR; z++) {
+                acc0 = __viaddmin_s16x2(a[z], __byte_perm(b[z], 0, 0x1010), acc0);
+                acc1 = __viaddmin_s16x2(a[z], __byte_perm(b[z], 0, 0x3232), acc1);
             }
         }
         for (; k < k1; k++, pa += P / 2, pb += P / 2) {
-            const unsigned a = pa[0], b = pb[0];
+            const unsigned a = ldfm32(pa), b = ldfm32(pb);
             acc0 = __viaddmin_s16x2(a, __byte_perm(b, 0, 0x1010), acc0);
             acc1 = __viaddmin_s16x2(a, __byte_perm(b, 0, 0x3232), acc1);
         }
@@ -614,15 +639,26 @@ mfe3_kernel(MfeLaunch L, const MfeTables *__restrict__ T, const Tab3 *__restrict
             constexpr int n16 = (int)((offsetof(SM, decp) - offsetof(SM, ne) + 15) / 16);   // a ragged tail spills
             for (int k = tid; k < n16; k += NT) p[k] = inf4;                                 // into decp (rewritten before use)
             for (int k = tid; k < 4 * PR; k += NT) sm.partc[k] = INF16;   // diagonals 4 .. 7 have no interior loops of size >= 2
+            if constexpr (FMG) {
+                int4 *q = reinterpret_cast<int4 *>(fm);
+                for (int k = tid; k < P * P / 8; k += NT) q[k] = inf4;
+            }
         }
         minv = 0;
         __syncthreads();
         // diagonals 4 .. 6: lists, hairpins (all they can close), then the rows of diagonal 4 and the lists of 7, 8
         if (warp < 3) build_list(TURN + 1 + warp);
         __syncthreads();
-        for (int it = warp; it < 12; it += NW) {   // at most 4 list chunks per diagonal
-            const int d = TURN + 1 + (it >> 2), c = it & 3;
-            if (d < W && c * 32 < sm.cnt[d & 3]) unit_P(d, c);
+        {
+            const int c4 = (sm.cnt[0] + 31) >> 5, c5 = (sm.cnt[1] + 31) >> 5, c6 = (sm.cnt[2] + 31) >> 5;
+            for (int it = warp; it < c4 + c5 + c6; it += NW) {
+                if (it < c4)
+                    unit_P(TURN + 1, it);
+                else if (it < c4 + c5)
+                    unit_P(TURN + 2, it - c4);
+                else
+                    unit_P(TURN + 3, it - c4 - c5);
+            }
         }
         __syncthreads();
         for (int u = warp; u < (W - TURN - 1 + SEG - 1) / SEG + 2; u += NW) {
@@ -738,7 +774,7 @@ mfe3_kernel(MfeLaunch L, const MfeTables *__restrict__ T, const Tab3 *__restrict
             if (L.pair_tbl && mv >= LOW16) {   // native folds: structure (CTA-uniform branch)
                 short *pt = sm.partc;
                 if (warp == 0) {
-                    const bool ok = traceback3<P>(sm, T, cx, pt, W, lane);
+                    const bool ok = traceback3<P, FMG>(sm, fm, T, cx, pt, W, lane);
                     if (!ok && lane == 0) L.e_out[fold] = MFE_REDO;   // the int32 kernel folds it again
                 }
                 __syncthreads();
@@ -748,25 +784,33 @@ mfe3_kernel(MfeLaunch L, const MfeTables *__restrict__ T, const Tab3 *__restrict
     }
 }
 
-template <int P, int NW, int OCC>
+template <int P, int NW, int OCC, bool FMG = false>
 void launch_mfe3_t(const MfeLaunch &L, const MfeTables *d_tab, int n_sm, cudaStream_t stream) {
-    const size_t smem = sizeof(Smem3<P>);
+    const size_t smem = sizeof(Smem3<P, FMG>);
     static bool cfg = false;
     if (!cfg) {
-        cudaFuncSetAttribute(mfe3_kernel<P, NW, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(mfe3_kernel<P, NW, OCC, FMG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cfg = true;
     }
     const int grid = L.n_fold < n_sm * OCC ? L.n_fold : n_sm * OCC;
-    mfe3_kernel<P, NW, OCC><<<grid, NW * 32, smem, stream>>>(L, d_tab, g_dtab3);
+    mfe3_kernel<P, NW, OCC, FMG><<<grid, NW * 32, smem, stream>>>(L, d_tab, g_dtab3);
 }
 
 }  // namespace
 
 static_assert(sizeof(Smem3<200>) <= 227 * 1024, "the 200-nt configuration must fit one SM");
-bool mfe3_supports(int W) { return g_mfe3_ok && W >= 16 && W <= 200; }
+static_assert(sizeof(Smem3<300, true>) <= 227 * 1024, "the 300-nt configuration must fit one SM");
+static_assert(300 * 300 % 8 == 0, "the global matrix is cleared with 16-byte stores");
+bool mfe3_supports(int W) { return g_mfe3_ok && W >= 16 && W <= 300; }
+
+// scratch shorts per resident CTA: C (+ exterior stem term) by diagonal, and above 200 nt the FML matrix (300 x 300)
+size_t mfe3_scratch_shorts_per_cta(int W) {
+    const size_t tri = ((size_t)tri4(W, W) + 63) & ~(size_t)63;
+    return tri + (W > 200 ? (size_t)300 * 300 : 0);
+}
 
 // scratch rows (one per resident CTA, the most any configuration launches)
-int mfe3_max_ctas(int n_sm) { return n_sm * 6; }
+int mfe3_max_ctas(int n_sm, int W) { return n_sm * (W <= 64 ? 4 : (W <= 120 ? 2 : 1)); }
 
 void mfe3_upload_tables(const MfeTables &M) {
     static Tab3 h;
@@ -841,6 +885,8 @@ void launch_mfe3(const MfeLaunch &L, const MfeTables *d_tab, int n_sm, cudaStrea
     static const int nw = getenv("SFB_MFE3_WARPS") ? atoi(getenv("SFB_MFE3_WARPS")) : 12;  // tuning knob
     if (L.W <= 64)
         launch_mfe3_t<64, 4, 4>(L, d_tab, n_sm, stream);
+    else if (L.W > 200)
+        launch_mfe3_t<300, 16, 1, true>(L, d_tab, n_sm, stream);
     else if (L.W > 120)
         launch_mfe3_t<200, 16, 1>(L, d_tab, n_sm, stream);
     else if (nw == 4)

@@ -299,7 +299,7 @@ def test_scan_shape_mode(engine, oracle):
             assert res.mfe_dcal[nwin] == eo
 
 
-@pytest.mark.parametrize("W", [16, 17, 33, 40, 64, 65, 97, 119, 120, 121, 128, 150, 199, 200, 201])
+@pytest.mark.parametrize("W", [16, 17, 33, 40, 64, 65, 97, 119, 120, 121, 128, 150, 199, 200, 201, 250, 299, 300, 301])
 def test_fold_kernels_agree(engine, oracle, W):
     """The three MFE kernel generations -- int32 CTA kernel (mfe.cu), int16 warp teams (mfe2.cu), int16 CTA kernel
     with stencil / range-minimum interior loops and on-device traceback (mfe3.cu) -- give the same energies and
