@@ -391,6 +391,10 @@ mfe3_kernel(MfeLaunch L, const MfeTables *__restrict__ T, const Tab3 *__restrict
     const int cB26 = (uok && U > 27) ? c3_cap[U] : BIG;
     const int cC = (uok && U > 11) ? c3_cap[U] : BIG;
     // a disabled tap reads the address of an enabled lane (same word: a broadcast, never a bank conflict)
+    // rows d-2, d-3 are being written in the same phase: the (disabled) lanes 0, 1 read the rows of lanes 2, 3 instead.
+    // compute-sanitizer racecheck is clean except for disabled B taps that run past a short row's end into the next
+    // ring row (value discarded: their size term is BIG).
+    const int UB = U < 2 ? U + 2 : (U > MAXLOOP ? MAXLOOP : U);
     const int UA = U < 7 ? U + 8 : (U > MAXLOOP ? MAXLOOP - 1 : U);
     const int UC = U < 12 ? U + 12 : (U > MAXLOOP ? MAXLOOP : U);
     const int kA = ((UA & 1) ? O_NO : O_NE) + 3 + (UA >> 1), kC = O_M8 + UC - 1;
@@ -673,9 +677,7 @@ mfe3_kernel(MfeLaunch L, const MfeTables *__restrict__ T, const Tab3 *__restrict
             const int2 si = reinterpret_cast<const int2 *>(sm.stepinfo)[(d0 - TURN - 2) >> 1];
             const int nseg0 = si.x & 255, nS = (si.x >> 8) & 255, nF = si.x >> 16;
             const int ntile = si.y & 255, ksh = (si.y >> 8) & 15, kwsh = (si.y >> 12) & 15, nT = si.y >> 16;
-            const int4 cn = *reinterpret_cast<const int4 *>(sm.cnt);   // d0 is odd: d0+2, d0+3 sit in slots (d0+2) & 3, +1
-            const bool up = ((d0 + 2) & 2) != 0;                       // (d0 + 2) & 3 is 3 or 1
-            const int n2 = up ? cn.w : cn.y, n3 = up ? cn.x : cn.z;
+            const int n2 = sm.cnt[(d0 + 2) & 3], n3 = sm.cnt[(d0 + 3) & 3];   // (the other two slots are being rewritten)
             const int nch2 = (n2 + 31) >> 5, nP = nch2 + ((n3 + 31) >> 5);
             const int uP = nS, uT = uP + nP, uF = uT + nT, uL = uF + nF, nH = uL + 2;
             for (int u = warp; u < nH; u += NW) {
@@ -702,7 +704,7 @@ mfe3_kernel(MfeLaunch L, const MfeTables *__restrict__ T, const Tab3 *__restrict
                 for (int ds = 0; ds < 2; ds++) {
                     const int d = d0 + 2 + ds, n = ds ? n3 : n2;
                     if (c < n) {
-                        const int slot = (d - 2 - U) & (R32 - 1);
+                        const int slot = (d - 2 - UB) & (R32 - 1);
                         const short *qA = smb + kA + ((d - 2 - UA) & (R32 - 1)) * PR;
                         const short *qB = smb + O_M8 + slot * PR;
                         const short *qC = smb + kC + ((d - 2 - UC) & (R32 - 1)) * PR;
