@@ -106,7 +106,7 @@ struct Smem3 {
     alignas(16) int cnt[4];   // pairable cells of the diagonals d with d & 3 = slot (0 beyond the last diagonal)
     int ctr[2];
     int minv[32];
-    int fbest[32];
+    int fbest[32];   // per-length partial minima of an exterior-loop round (8 lengths x up to 4 slices)
     alignas(8) int stepinfo[(P / 2 + 4) * 2];    // per diagonal pair: unit counts of the phase (fold independent)
 };
 
@@ -749,23 +749,40 @@ mfe3_kernel(MfeLaunch L, const MfeTables *__restrict__ T, const Tab3 *__restrict
             const int minw = __reduce_min_sync(full, minv);
             if (lane == 0) sm.minv[warp] = minw;
             __syncthreads();
-            // F5[len] only needs F5[i] for i <= len - 5, so four consecutive lengths are independent: one (or two)
-            // warps per length, then the running minimum along the block
-            constexpr int WPL = NW / 4;   // warps per length
-            for (int len0 = TURN + 2; len0 <= W; len0 += 4) {
-                const int len = len0 + (warp & 3), j = len - 1;
-                int best = INF16;
-                if (len <= W)
-                    for (int i = lane + 32 * (warp >> 2); i <= j - TURN - 1; i += 32 * WPL)
-                        best = min(best, sm.f5[i] + cx[tri4(j - i, W) + i]);
-                best = __reduce_min_sync(full, best);
-                if (lane == 0) sm.fbest[warp] = best;
+            // F5[len] = min(F5[len-1], min_{i <= len-5} F5[i] + Cx(i, len-1)).  Eight consecutive lengths per round: every
+            // term whose F5[i] is known when the round starts (i < len0) is a parallel minimum, one length per warp
+            // (slices of the i range when there are more than eight warps, several lengths per warp when fewer); the
+            // six terms that need F5 of the round itself (i = len0 .. len0+2 for the last three lengths) and the running
+            // minimum along the block are folded in by one thread.
+            constexpr int LPR = 8, NPART = NW > LPR ? NW / LPR : 1;
+            for (int len0 = TURN + 2; len0 <= W; len0 += LPR) {
+                for (int t = warp % LPR; t < LPR; t += NW) {
+                    const int len = len0 + t, j = len - 1, part = warp / LPR;
+                    int best = INF16;
+                    if (len <= W && part < NPART)
+                        for (int i = lane + 32 * part; i <= min(j - TURN - 1, len0 - 1); i += 32 * NPART)
+                            best = min(best, sm.f5[i] + cx[tri4(j - i, W) + i]);
+                    best = __reduce_min_sync(full, best);
+                    if (lane == 0 && part < NPART) sm.fbest[t + LPR * part] = best;
+                }
                 __syncthreads();
                 if (tid == 0) {
+                    int f[LPR];
                     int run = sm.f5[len0 - 1];
-                    for (int t = 0; t < 4 && len0 + t <= W; t++) {
-                        for (int h = 0; h < WPL; h++) run = min(run, sm.fbest[t + 4 * h]);
-                        sm.f5[len0 + t] = (short)run;
+#pragma unroll
+                    for (int t = 0; t < LPR; t++) {
+                        if (len0 + t <= W) {
+#pragma unroll
+                            for (int h = 0; h < NPART; h++) run = min(run, sm.fbest[t + LPR * h]);
+                            // terms with i = len0 .. len - 5 (at most three): F5[i] was set earlier in this round
+#pragma unroll
+                            for (int q = 0; q + 5 <= t; q++) {
+                                const int i = len0 + q, j = len0 + t - 1;
+                                run = min(run, f[q] + cx[tri4(j - i, W) + i]);
+                            }
+                            f[t] = run;
+                            sm.f5[len0 + t] = (short)run;
+                        }
                     }
                 }
                 __syncthreads();
