@@ -74,3 +74,54 @@ def test_accumulator_matches_numpy_and_merges(engine):
         assert np.array_equal(getattr(both, name), getattr(whole, name)), name
     for x in (acc, A, B):
         x.close()
+
+
+def test_repeated_plans_reuse_device_memory(engine):
+    """The library keeps freed device blocks for the next plan (DevPool in api.cu): alternating plans of different
+    geometry must give the same results as the first time each one ran."""
+    rng = np.random.default_rng(11)
+    seq_a = "".join("ACGU"[k] for k in rng.integers(0, 4, 400))
+    seq_b = "".join("ACGU"[k] for k in rng.integers(0, 4, 900))
+
+    def run(seq, W, r):
+        res = engine.scan(seq, W, 1, r, seed=5)
+        return res.mfe_dcal.copy(), res.shuffle_dcal.copy(), res.ed.copy(), res.pair_tbl.copy()
+
+    first_a, first_b = run(seq_a, 60, 8), run(seq_b, 120, 5)
+    for _ in range(2):
+        for first, args in ((first_a, (seq_a, 60, 8)), (first_b, (seq_b, 120, 5))):
+            again = run(*args)
+            for x, y in zip(first, again):
+                assert np.array_equal(x, y)
+
+
+def test_cli_two_records_device_shuffles(tmp_path, monkeypatch, engine):
+    """Stock run (device shuffles, no parity file) on a two-record FASTA: one output folder per record with the full
+    file set, and the structure-extraction outputs are consistent with each other."""
+    from scanfold_b200 import cli
+    rng = np.random.default_rng(3)
+    hp = "GGGGCGCUUCGGCGCCCC"
+    recs = {"recA": "AAUAC" + hp + "AUAAUUAAUAUAUUAAUUA" + "GCCGGAUCGAAAGAUCCGGC" + "AAUAUAAUAAAUUAUAUA",
+            "recB": "".join("ACGU"[k] for k in rng.integers(0, 4, 130))}
+    with open(tmp_path / "two.fa", "w") as f:
+        for k, v in recs.items():
+            f.write(">%s\n%s\n" % (k, v))
+    monkeypatch.chdir(tmp_path)
+    cli.main(["two.fa", "-w", "40", "-r", "20", "--seed", "9"])
+    for name, seq in recs.items():
+        out = tmp_path / name
+        files = sorted(os.listdir(out))
+        assert "ExtractedStructures.gff3" in files and "AllDBN.txt" in files and "Zavg_-2_pairs.ct" in files
+        assert any(f.endswith(".out") for f in files) and any(f.endswith(".scan-zscores.wig") for f in files)
+        gff = [ln for ln in open(out / "ExtractedStructures.gff3").read().split("\n") if ln]
+        motifs = sorted(f for f in files if "_motif_" in f)
+        assert len(motifs) == 2 * len(gff)          # one .dbn and one .ct per gff3 line
+        for k, ln in enumerate(gff, 1):
+            fields = ln.split("\t")
+            start, end = int(fields[3]), int(fields[4])
+            attrs = dict(a.split("=", 1) for a in fields[8].split(";")[1:])
+            assert attrs["sequence"] == seq[start - 1:end]
+            dbn = open(out / ("UserInput_motif_%d.dbn" % k)).read().split("\n")
+            assert dbn[1] == attrs["sequence"] and dbn[2] == attrs["refoldedMFE"]
+            assert len(attrs["structure"]) == len(attrs["sequence"])
+    assert any(ln for ln in open(tmp_path / "recA" / "ExtractedStructures.gff3"))   # the designed hairpins are found
