@@ -190,7 +190,8 @@ struct FoldWork {  // device scratch for one MFE launch
     void launch_energy_only(MfeLaunch L, cudaStream_t st, int *n_launch) const {
         const bool use3 = engine() == 3 && mfe3_supports(L.W), use2 = engine() != 1 && mfe2_supports(L.W) && !L.pair_tbl;
         const bool hc3 = L.hc && L.hc_simple && use3;   // per-nucleotide hard constraints: folded into mfe3
-        if ((use3 || use2) && (!L.hc || hc3) && !L.sc && L.max_span <= 0) {   // mfe3 also traces the structure back
+        // mfe3 also traces the structure back and takes stacking pseudo-energies (Deigan)
+        if ((use3 || (use2 && !L.sc)) && (!L.hc || hc3) && L.max_span <= 0) {
             MfeLaunch L2 = L;
             L2.gscratch = scratch2.p;
             L2.gscratch_per_cta = (long long)per_warp2;
@@ -646,8 +647,8 @@ int sfb_scan_plan_run(sfb_scan_plan *P, float *ms_total, float *ms_mfe, int32_t 
                 L.e_out = P->mfe.p + c0;
                 L.pair_tbl = P->pair_tbl.p + (size_t)c0 * W;
                 L.hc_simple = P->hc_simple;
-                if (P->hc_simple && !a.react && a.model.max_bp_span <= 0) {
-                    P->fw.launch_energy_only(L, st, &n_launch);   // per-nucleotide flags only: mfe3 (+ int32 redo)
+                if ((!a.hc || P->hc_simple) && a.model.max_bp_span <= 0) {
+                    P->fw.launch_energy_only(L, st, &n_launch);   // flags / Deigan only: mfe3 (+ int32 redo)
                 } else {
                     P->fw.fill(L);
                     launch_mfe(L, g_ctx.d_mfe, g_ctx.n_sm, st, &n_launch);

@@ -97,14 +97,14 @@ struct Smem3 {
     short partc[4 * PR], parts[4 * PR];   // partial minima by diagonal & 3: loops of size >= 2 / everything else
     short f5[P + 8];
     static constexpr int LP = P;              // list pitch (entries): a diagonal has fewer than P cells
-    alignas(16) int list[(4 * LP + 32) * 4];     // per pairable cell: i, mismatchI / mismatch1nI / TerminalAU term of the
+    alignas(16) int list[(4 * LP + 16) * 4];     // per pairable cell: i, mismatchI / mismatch1nI / TerminalAU term of the
                                                  // closing pair; the traceback stack of the natives reuses it
     unsigned char ctx[R16 * PR];
     unsigned char sx[P + 8];   // sx[k+1] = code of nucleotide k, sx[0] = sx[W+1] = 5
     unsigned char sx5[P + 8], sx3[P + 8];   // the same, 5 (never pairs) where hard constraints forbid the nucleotide
                                             // as 5' / 3' partner ('x' both, '>' 5', '<' 3')
     alignas(16) int cnt[4];   // pairable cells of the diagonals d with d & 3 = slot (0 beyond the last diagonal)
-    int ctr[2];
+    short scp[P + 8];   // soft constraints: scp[k] = sc[k] + sc[k+1] (0-based), the stack (i,j)-(i+1,j-1) adds scp[i] + scp[j-1]
     int minv[32];
     int fbest[32];   // per-length partial minima of an exterior-loop round (8 lengths x up to 4 slices)
     alignas(8) int stepinfo[(P / 2 + 4) * 2];    // per diagonal pair: unit counts of the phase (fold independent)
@@ -297,7 +297,8 @@ __device__ bool traceback3(SMT &sm, const short *fm, const MfeTables *T, const s
                     const int cpq = CC(p, q);
                     if (cpq < INF) {
                         const int t2 = tb.rtype[ptype(p, q)];
-                        const int e = e_intloop3(T, p - i - 1, j - q - 1, type, t2, sx[i + 2], sx[j], sx[p], sx[q + 2]);
+                        int e = e_intloop3(T, p - i - 1, j - q - 1, type, t2, sx[i + 2], sx[j], sx[p], sx[q + 2]);
+                        if (p == i + 1 && q == j - 1) e += sm.scp[i] + sm.scp[j - 1];   // Deigan: stacked pairs only
                         hit = cij == e + cpq;
                     }
                 }
@@ -488,7 +489,9 @@ mfe3_kernel(MfeLaunch L, const MfeTables *__restrict__ T, const Tab3 *__restrict
             e = min((int)sm.partc[(d & 3) * PR + i], (int)sm.parts[(d & 3) * PR + i]);
             if (d - 2 > TURN) {   // stack: inner pair (i+1, j-1)
                 const int o = ((d - 2) & (R16 - 1)) * PR + i + 1;
-                e = min(e, sm.rc[o] + tb.stack[t * 8 + sm.ctx[o]]);
+                int es = sm.rc[o] + tb.stack[t * 8 + sm.ctx[o]];
+                if (L.sc) es += sm.scp[i] + sm.scp[j - 1];   // Deigan pseudo-energy of the stack (kernel-uniform branch)
+                e = min(e, es);
             }
             if (d - 3 > TURN) {   // bulge of one: inner pairs (i+1, j-2) and (i+2, j-1)
                 const int o = ((d - 3) & (R16 - 1)) * PR + i + 1;
@@ -649,6 +652,15 @@ mfe3_kernel(MfeLaunch L, const MfeTables *__restrict__ T, const Tab3 *__restrict
             }
         }
         minv = 0;
+        for (int k = tid; k < W + 2; k += NT) {
+            int v = 0;
+            if (L.sc && k < W) {   // L.sc is 1-based: nucleotide k sits at index k + 1
+                const int a = L.sc[(size_t)fold * (W + 1) + k + 1], b = k + 1 < W ? L.sc[(size_t)fold * (W + 1) + k + 2] : 0;
+                v = a + b;
+                if (abs(a) > 4000 || abs(b) > 4000) minv = LOW16 - 1;   // int16 cannot hold it: redo in int32
+            }
+            sm.scp[k] = (short)max(-8000, min(8000, v));
+        }
         __syncthreads();
         // diagonals 4 .. 6: lists, hairpins (all they can close), then the rows of diagonal 4 and the lists of 7, 8
         if (warp < 3) build_list(TURN + 1 + warp);
