@@ -369,10 +369,6 @@ mfe3_kernel(MfeLaunch L, const MfeTables *__restrict__ T, const Tab3 *__restrict
         if constexpr (FMG) return __ldcg(q);
         else return *q;
     };
-    auto ldfm32 = [&](const unsigned *q) -> unsigned {
-        if constexpr (FMG) return __ldcg(q);
-        else return *q;
-    };
     // the multiloop matrix: shared memory, or (FMG) the P x P shorts behind the scratch row of this CTA
     short *const fm = FMG ? gC + (((size_t)tri4(W, W) + 63) & ~(size_t)63) : sm.fm;
     const short *smb = sm.ne;   // every tap address below is an offset (in shorts) from here
@@ -586,28 +582,59 @@ mfe3_kernel(MfeLaunch L, const MfeTables *__restrict__ T, const Tab3 *__restrict
         const int cntk = max(D - 7, 0);
         const int pidx = (kp << kwsh) + kq, psh = ksh + kwsh;
         const int k0 = i + 4 + ((cntk * pidx) >> psh), k1 = i + 4 + ((cntk * (pidx + 1)) >> psh);
-        const unsigned *pa = reinterpret_cast<const unsigned *>(fm + k0 * P + i);
-        const unsigned *pb = reinterpret_cast<const unsigned *>(fm + (k0 + 1) * P + j);
         unsigned acc0 = INF16 * 65537u, acc1 = INF16 * 65537u;
-        int k = k0;
-        constexpr int UNR = FMG ? 8 : 4;   // loads in flight per lane: 2 * UNR (L2 latency when the matrix is global)
-        for (; k + UNR - 1 < k1; k += UNR, pa += UNR * (P / 2), pb += UNR * (P / 2)) {
-            unsigned a[UNR], b[UNR];
+        if constexpr (FMG) {
+            // Global matrix: the lanes of a k part sweep the SAME rows, so a warp load is one contiguous row segment
+            // (the per-tile windows k = i+4 .. j-4 start two rows apart from tile to tile; with each lane on its own
+            // row a load touched 32 sectors).  The sweep covers the union of the windows; a lane outside its own
+            // window contributes INF.
+            const int ltl = lane & (TPW - 1);
+            const int ibase = 2 * grp * TPW;                 // i of the group's first tile
+            const int span = cntk + 2 * (TPW - 1);
+            const int s0 = (span * pidx) >> psh, s1 = min((span * (pidx + 1)) >> psh, P - 5 - ibase);   // rows stay inside
+            const unsigned *pa = reinterpret_cast<const unsigned *>(fm + (ibase + 4 + s0) * P + i);
+            const unsigned *pb = reinterpret_cast<const unsigned *>(fm + (ibase + 5 + s0) * P + j);
+            const unsigned infp = INF16 * 65537u;
+            int kk = s0;
+            constexpr int UNR = 8;
+            for (; kk + UNR - 1 < s1; kk += UNR, pa += UNR * (P / 2), pb += UNR * (P / 2)) {
+                unsigned a[UNR], b[UNR];
 #pragma unroll
-            for (int z = 0; z < UNR; z++) {
-                a[z] = ldfm32(pa + z * (P / 2));
-                b[z] = ldfm32(pb + z * (P / 2));
-            }
+                for (int z = 0; z < UNR; z++) {
+                    a[z] = __ldcg(pa + z * (P / 2));
+                    b[z] = __ldcg(pb + z * (P / 2));
+                }
 #pragma unroll
-            for (int z = 0; z < UNR; z++) {
-                acc0 = __viaddmin_s16x2(a[z], __byte_perm(b[z], 0, 0x1010), acc0);
-                acc1 = __viaddmin_s16x2(a[z], __byte_perm(b[z], 0, 0x3232), acc1);
+                for (int z = 0; z < UNR; z++) {
+                    const unsigned rel = (unsigned)(kk + z - 2 * ltl);
+                    const unsigned av = rel < (unsigned)cntk ? a[z] : infp;
+                    acc0 = __viaddmin_s16x2(av, __byte_perm(b[z], 0, 0x1010), acc0);
+                    acc1 = __viaddmin_s16x2(av, __byte_perm(b[z], 0, 0x3232), acc1);
+                }
             }
-        }
-        for (; k < k1; k++, pa += P / 2, pb += P / 2) {
-            const unsigned a = ldfm32(pa), b = ldfm32(pb);
-            acc0 = __viaddmin_s16x2(a, __byte_perm(b, 0, 0x1010), acc0);
-            acc1 = __viaddmin_s16x2(a, __byte_perm(b, 0, 0x3232), acc1);
+            for (; kk < s1; kk++, pa += P / 2, pb += P / 2) {
+                const unsigned rel = (unsigned)(kk - 2 * ltl);
+                const unsigned av = rel < (unsigned)cntk ? __ldcg(pa) : infp, b = __ldcg(pb);
+                acc0 = __viaddmin_s16x2(av, __byte_perm(b, 0, 0x1010), acc0);
+                acc1 = __viaddmin_s16x2(av, __byte_perm(b, 0, 0x3232), acc1);
+            }
+        } else {
+            const unsigned *pa = reinterpret_cast<const unsigned *>(fm + k0 * P + i);
+            const unsigned *pb = reinterpret_cast<const unsigned *>(fm + (k0 + 1) * P + j);
+            int k = k0;
+            for (; k + 3 < k1; k += 4, pa += 2 * P, pb += 2 * P) {
+#pragma unroll
+                for (int z = 0; z < 4; z++) {
+                    const unsigned a = pa[z * (P / 2)], b = pb[z * (P / 2)];
+                    acc0 = __viaddmin_s16x2(a, __byte_perm(b, 0, 0x1010), acc0);
+                    acc1 = __viaddmin_s16x2(a, __byte_perm(b, 0, 0x3232), acc1);
+                }
+            }
+            for (; k < k1; k++, pa += P / 2, pb += P / 2) {
+                const unsigned a = pa[0], b = pb[0];
+                acc0 = __viaddmin_s16x2(a, __byte_perm(b, 0, 0x1010), acc0);
+                acc1 = __viaddmin_s16x2(a, __byte_perm(b, 0, 0x3232), acc1);
+            }
         }
         if (kwsh >= 1) {
             acc0 = __vmins2(acc0, __shfl_xor_sync(full, acc0, 16));
