@@ -74,7 +74,7 @@ Tab3 *g_dtab3 = nullptr;
 bool g_mfe3_ok = false;
 
 constexpr int BIG = 1 << 20;  // size term of a disabled tap: the sum never wins whatever the load returns
-constexpr int KSMAX = 4;      // the split loop of a tile diagonal is cut into at most 2 (4: global FML) work items
+
 
 template <int P, bool FMG = false>
 struct Smem3 {
@@ -338,7 +338,7 @@ mfe3_kernel(MfeLaunch L, const MfeTables *__restrict__ T, const Tab3 *__restrict
     extern __shared__ __align__(16) unsigned char smem_raw[];
     using SM = Smem3<P, FMG>;
     SM &sm = *reinterpret_cast<SM *>(smem_raw);
-    constexpr int NT = NW * 32, PR = SM::PR, NWH = NW / 2;
+    constexpr int NT = NW * 32, PR = SM::PR;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const unsigned full = 0xffffffffu;
     {
