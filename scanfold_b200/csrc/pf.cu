@@ -133,7 +133,10 @@ __device__ __forceinline__ double group_sum(double v, int G) {
     return v;
 }
 
-__global__ void __launch_bounds__(NT) pf_kernel(PfLaunch L, const MfeTables *__restrict__ MT,
+#ifndef SFB_PF_MINB
+#define SFB_PF_MINB 6   // resident CTAs per SM: measured 3 -> 9.99 k, 4 -> 10.6 k, 6 -> 13.0 k, 8 -> 8.9 k windows/s at 200 nt
+#endif
+__global__ void __launch_bounds__(NT, SFB_PF_MINB) pf_kernel(PfLaunch L, const MfeTables *__restrict__ MT,
                                                 const PfTables *__restrict__ T) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int W = L.W;
@@ -581,7 +584,12 @@ size_t pf_scratch_doubles_per_cta(int W) {
 }
 
 int pf_grid_size(int W, int n_sm, int n_fold) {
-    long long g = (long long)n_sm * 4;
+    // resident CTAs: the kernel waits on L2, occupancy is what hides it (registers allow SFB_PF_MINB, shared memory less
+    // for long windows)
+    long long per_sm = (long long)((227 * 1024) / (pf_smem_bytes(W) + 1024));
+    if (per_sm > SFB_PF_MINB) per_sm = SFB_PF_MINB;
+    if (per_sm < 1) per_sm = 1;
+    long long g = (long long)n_sm * per_sm;
     if (g > n_fold) g = n_fold;
     return (int)g;
 }
