@@ -253,7 +253,10 @@ __device__ bool traceback(const FoldCtx &c, const int *C, const int *M, const in
 
 __device__ __forceinline__ int floor_pow2(int x) { return x <= 1 ? 1 : 1 << (31 - __clz(x)); }
 
-__global__ void __launch_bounds__(NT) mfe_fold_kernel(MfeLaunch L, const MfeTables *__restrict__ T) {
+#ifndef SFB_MFE1_MINB
+#define SFB_MFE1_MINB 6   // resident CTAs per SM (global-memory mode, W=600): 3 -> 3.1 k, 4 -> 3.9 k, 6 -> 4.5 k folds/s
+#endif
+__global__ void __launch_bounds__(NT, SFB_MFE1_MINB) mfe_fold_kernel(MfeLaunch L, const MfeTables *__restrict__ T) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int W = L.W;
     const int tid = threadIdx.x, lane = tid & 31;
@@ -578,7 +581,7 @@ int mfe_grid_size(int W, int n_sm, int n_fold) {
     size_t smem = mfe_smem_bytes(W, mode);
     int per_sm = (int)((227 * 1024) / (smem + 1024));
     if (per_sm < 1) per_sm = 1;
-    if (per_sm > 16) per_sm = 16;
+    if (per_sm > SFB_MFE1_MINB) per_sm = SFB_MFE1_MINB;   // registers: resident CTAs per SM
     long long g = (long long)n_sm * per_sm;
     if (g > n_fold) g = n_fold;
     return (int)g;
