@@ -570,6 +570,13 @@ size_t mfe_scratch_ints_per_cta(int W, int *mats_in_gmem) {
     int mode = 0;
     if (mfe_smem_bytes(W, 0) > limit) mode = 1;
     if (mode == 1 && mfe_smem_bytes(W, 1) > limit) mode = 2;
+#ifndef SFB_MFE1_GMEM_OCC
+#define SFB_MFE1_GMEM_OCC 3   // measured: W=260 22.5 k -> 48.6 k, W=400 6.4 k -> 15.9 k folds/s with the buffers in global memory
+#endif
+    {
+    // rolling buffers in shared memory leave room for few CTAs per SM; in global memory the kernel keeps SFB_MFE1_MINB
+    if (mode == 1 && (227 * 1024) / (mfe_smem_bytes(W, 1) + 1024) < SFB_MFE1_GMEM_OCC) mode = 2;
+    }
     if (mats_in_gmem) *mats_in_gmem = mode;
     if (mode == 0) return 0;
     return 2 * ntri + (mode == 2 ? 3 * ROLL * (size_t)W : 0);
