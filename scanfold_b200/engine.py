@@ -158,6 +158,18 @@ def pair_table_to_dotbracket(pt):
     return out.tobytes().decode()
 
 
+def pair_tables_to_dotbrackets(tbl):
+    """[n, W] int16 pair tables -> list of n dot-bracket strings (one vectorised pass)"""
+    tbl = np.asarray(tbl)
+    n, W = tbl.shape
+    idx = np.arange(1, W + 1, dtype=tbl.dtype)[None, :]
+    out = np.full((n, W), ord("."), dtype=np.uint8)
+    out[tbl > idx] = ord("(")
+    out[(tbl > 0) & (tbl < idx)] = ord(")")
+    text = out.tobytes().decode()
+    return [text[k * W:(k + 1) * W] for k in range(n)]
+
+
 def fold_batch(seqs, hc=None, sc=None, structure=False, temperature=37.0, max_span=0):
     """MFE of equal-length sequences.  -> (int32 energies in dcal, int16 pair tables or None)."""
     ensure_init()

@@ -25,12 +25,16 @@ def write_out(path, read_name, seq, table, temperature):
     W = table.W
     rows = ["i\tj\tTemperature\tNative_dG\tZ-score\tP-score\tEnsembleDiversity\tSequence\tStructure\tCentroid\t"
             + read_name + "\n"]
-    for k in range(len(table)):
+    from .engine import pair_tables_to_dotbrackets
+    n = len(table)
+    structures = pair_tables_to_dotbrackets(table.pair_tbl[:n])
+    centroids = pair_tables_to_dotbrackets(table.centroid_tbl[:n])
+    for k in range(n):
         s0 = int(table.start1[k]) - 1
         frag = seq[s0:s0 + W]
         rows.append("%d\t%d\t%s\t%s\t%s\t%s\t%s\t%s\t%s\t%s\t%s\n" % (
             table.start1[k], table.end1[k], str(temperature), str(float(table.mfe[k])), str(float(table.z[k])),
-            str(float(table.p[k])), str(float(table.ed[k])), frag, table.structure(k), table.centroid(k),
+            str(float(table.p[k])), str(float(table.ed[k])), frag, structures[k], centroids[k],
             str(gc_content(frag))))
     with open(path, "w") as f:
         f.write("".join(rows))
