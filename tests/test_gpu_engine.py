@@ -347,3 +347,30 @@ def test_partition_function_kernels_agree(engine, oracle, W):
         assert abs(r2["dG"][k] - o["dG"]) <= 1e-6 * max(1.0, abs(o["dG"]))
         assert abs(r2["ed"][k] - o["ed"]) <= 1e-6 * max(1.0, abs(o["ed"]))
         assert np.abs(r2["bpp"][k] - o["bpp"]).max() < 1e-9
+
+
+def test_scan_across_chunk_boundary(engine, oracle):
+    """A record with more than 65,536 windows is scanned in chunks: the windows on both sides of the boundary (and the
+    final-window slot) must equal a separate scan of just that range -- device shuffles are keyed by the absolute window
+    index -- and the oracle."""
+    rng = np.random.default_rng(21)
+    W, r = 40, 4
+    L = 65536 + 300 + W - 1
+    seq = "".join("ACGU"[k] for k in rng.integers(0, 4, L))
+    full = engine.scan(seq, W, 1, r, seed=3, keep_shuffles=True)
+    n = L - W + 1
+    assert full.n == n + 1
+    lo, cnt = 65536 - 20, 40
+    part = engine.scan(seq, W, 1, r, seed=3, first_window=lo, n_windows=cnt, final_window=False, keep_shuffles=True)
+    for key in ("mfe_dcal", "native_unconstrained_dcal", "shuffle_dcal", "pair_tbl", "centroid_tbl", "shuffles"):
+        assert np.array_equal(getattr(full, key)[lo:lo + cnt], getattr(part, key)[:cnt]), key
+    assert np.allclose(full.ed[lo:lo + cnt], part.ed[:cnt], rtol=0, atol=1e-12)
+    for w in (65535, 65536, n - 1):
+        frag = seq[w:w + W]
+        e, s = oracle.mfe(frag)
+        assert e == full.mfe_dcal[w] and s == db_from_pt(full.pair_tbl[w])
+        for k in range(r):
+            sh = bytes(full.shuffles[w, k]).decode()
+            assert sorted(sh) == sorted(frag) and oracle.mfe(sh, structure=False)[0] == full.shuffle_dcal[w, k]
+    # final-window slot: the stale fold compound of the last regular window, fresh shuffles of seq[L-W:L] (Q5)
+    assert full.mfe_dcal[n] == full.mfe_dcal[n - 1] and np.array_equal(full.pair_tbl[n], full.pair_tbl[n - 1])
