@@ -1,7 +1,9 @@
-// MFE fold kernel, third generation: one CTA per fold, energy only, no constraints, windows up to 320 nt.
+// MFE fold kernel, third generation: one CTA per fold, int16 energies, windows up to 300 nt; energy only or with an
+// on-device traceback; per-nucleotide hard constraints ('x' '<' '>') and Deigan stacking pseudo-energies folded in.
 //
 // Replaces the r background folds per window of energies()/rna_folder (ScanFoldFunctions.py:774-789,805-814)
-// -- more than 99 % of all fold arithmetic of a scan.
+// -- more than 99 % of all fold arithmetic of a scan -- and the native fold fc.mfe() of ScanFold.py:494-497,
+// :512-513 (flag-only constraint lines) and :534-541 (Deigan).
 //
 // What changed against mfe2.cu: the <= 496 interior-loop candidates of a cell are no longer walked one by one.
 // For generic loops (both sides >= 2 unpaired, not 2x2 / 2x3) of total size u the energy is
