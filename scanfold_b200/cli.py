@@ -25,6 +25,14 @@ import numpy as np
 from . import motifs, pipeline, scan
 
 
+BESTEFFORT_WARNING = (
+    "scanfold_b200: WARNING -- the built-in energy table is a BEST-EFFORT stand-in for ViennaRNA's rna_turner2004.par\n"
+    "  (the real file is not redistributable from this image; stack / loop values were re-typed from the published\n"
+    "  model and the 1x1, 2x1 and 2x2 interior-loop tables are rule-generated).  Energies, z-scores and structures\n"
+    "  therefore differ from a ViennaRNA-backed ScanFold run.  Pass --params /path/to/rna_turner2004.par (or set\n"
+    "  SCANFOLD_PARAMS) to fold with the real Turner-2004 parameters.\n")
+
+
 def build_parser():
     p = argparse.ArgumentParser(prog="ScanFold.py")
     p.add_argument("filename", type=str, help="input FASTA file")
@@ -144,6 +152,32 @@ def make_output_folder(cwd, out_name, read_name):
     return folder
 
 
+def emit_window_prints(args, seq, table, react, hc, temperature):
+    """What the reference prints per window, in window order: the reactivity slice in the SHAPE branch
+    (ScanFold.py:524), the energy list under --print_random (:551-552) and the result row under --print (:680-684)."""
+    if react is None and not args.print_random and not args.print:
+        return
+    from . import engine, stats, writers
+    W, step = table.W, table.step
+    db = engine.pair_tables_to_dotbrackets(table.pair_tbl) if args.print else None
+    cen = engine.pair_tables_to_dotbrackets(table.centroid_tbl) if args.print else None
+    for k in range(len(table)):
+        s1, e1 = int(table.start1[k]), int(table.end1[k])
+        if react is not None:
+            print(react[s1:e1 + 1])
+        if args.print_random:
+            row = np.concatenate([[table.native_unconstrained_dcal[k]], table.shuffle_dcal[k]])
+            print([float(x) for x in stats.energy_to_float(row)])
+        if args.print:
+            frag = seq[s1 - 1:e1]
+            cols = [s1, e1, temperature, float(table.mfe[k]), float(table.z[k]), float(table.p[k]), float(table.ed[k])]
+            if hc is not None:
+                print("\t".join(str(c) for c in cols) + "\n" + frag + "\n" + hc[s1 - 1:e1] + "\n" + db[k] + "\n" + cen[k] +
+                      str(writers.gc_content(frag)) + "\n")
+            else:
+                print("\t".join(str(c) for c in cols + [frag, db[k], cen[k], writers.gc_content(frag)]) + "\n")
+
+
 def run_record(args, record_name, raw_seq, original_directory, dist=None):
     """One FASTA record.  With a torch.distributed process group (torchrun, one process per GPU) the windows are
     sharded by range over the ranks; rank 0 owns the output folder and writes every file."""
@@ -175,18 +209,27 @@ def run_record(args, record_name, raw_seq, original_directory, dist=None):
             return
         hc = None
         if args.constraints is not None:
-            # opened after the chdir into the output folder in the reference (Appendix B Q8): absolute paths only
-            path = args.constraints if os.path.isabs(args.constraints) or rank != 0 else os.path.join(os.getcwd(), args.constraints)
-            hc = open(path).readlines()[2].rstrip("\n")
+            # opened after the chdir into the output folder in the reference (Appendix B Q8): a relative path is looked
+            # up in the freshly made folder and fails there; every rank takes the same decision before any collective
+            if not os.path.isabs(args.constraints):
+                raise FileNotFoundError("[Errno 2] No such file or directory: %r (the reference opens --constraints "
+                                        "from inside the output folder: give an absolute path)" % args.constraints)
+            if rank == 0:
+                print("Considering constraint input")
+            hc = open(args.constraints).readlines()[2].rstrip("\n")
         react = None
         if args.react is not None:
+            if rank == 0:
+                print("Considering SHAPE reactivity input")
             react = read_reactivities(os.path.join(original_directory, args.react))
-            if args.shapeZ and not args.shapeD:
+            if hc is not None:
+                react = None       # ScanFold.py:508-519: the constraints branch wins, the reactivities are never applied
+            elif args.shapeZ and not args.shapeD:
                 raise TypeError("sc_add_SHAPE_zarringhalam() is called with one argument by the reference "
                                 "(ScanFold.py:536) and fails there too; use --shapeD")
         total = scan.n_windows_of(len(seq), W, step)
         w0, w1 = multigpu.shard_windows(total, world, rank)
-        last = w1 == total
+        last = w1 == total and w1 > w0
         parity = None
         if args.parity_shuffles:
             allsh = np.load(args.parity_shuffles if os.path.isabs(args.parity_shuffles)
@@ -194,19 +237,25 @@ def run_record(args, record_name, raw_seq, original_directory, dist=None):
             parity = allsh[w0:w1 + (1 if last else 0)]
         if rank == 0:
             print("Scanning input sequence:", read_name)
-        shard = scan.scan_record(seq.upper(), W, step, r, shuffle_type=str(args.type), seed=args.seed,
-                                 parity_shuffles=parity, temperature=float(args.t), max_span=args.span or 0, hc=hc,
-                                 react=react, shape_m=args.m, shape_b=args.b, first_window=w0, n_windows=w1 - w0,
-                                 final_window=last)
-        z100, mfe100, ed100 = pipeline.fold_inputs(shard)
-        acc = engine.Accumulator(len(seq), W, step, w0, shard.pair_tbl, z100, mfe100, ed100)
+        acc = None
+        if w1 > w0:
+            shard = scan.scan_record(seq.upper(), W, step, r, shuffle_type=str(args.type), seed=args.seed,
+                                     parity_shuffles=parity, temperature=float(args.t), max_span=args.span or 0, hc=hc,
+                                     react=react, shape_m=args.m, shape_b=args.b, first_window=w0, n_windows=w1 - w0,
+                                     final_window=last)
+            z100, mfe100, ed100 = pipeline.fold_inputs(shard)
+            acc = engine.Accumulator(len(seq), W, step, w0, shard.pair_tbl, z100, mfe100, ed100)
+        else:                  # more ranks than windows: this rank only takes part in the collectives
+            shard = scan.empty_table(W, step, r, w0)
         try:
-            ptable = multigpu.partner_table_distributed(acc, W, step, rank, world, dist)
+            ptable = multigpu.partner_table_distributed(acc, W, step, rank, world, dist, total)
         finally:
-            acc.close()
-        table = multigpu.gather_window_tables(shard, rank, world, dist)
+            if acc is not None:
+                acc.close()
+        table = multigpu.gather_window_tables(shard, rank, world, dist, with_shuffle_energies=bool(args.print_random))
         if rank != 0:
             return
+        emit_window_prints(args, seq, table, react, hc, int(args.t))
         minz = pipeline.write_scan_outputs(seq, table, names, int(args.t), step)   # Sequence column keeps input case (Q11)
         print("Elapsed time: %ss" % round(time.time() - t0, 2))
         print("Determining best base pairs...")
@@ -244,6 +293,10 @@ def main(argv=None):
         torch.cuda.set_device(device)
         dist.init_process_group("nccl", device_id=torch.device("cuda", device))
     engine.init(device, args.params)
+    if dist is not None:       # NCCL orders its work against torch's current stream: run the library on that stream too
+        engine.set_stream(torch.cuda.current_stream().cuda_stream)
+    if engine.params_besteffort() and (dist is None or dist.get_rank() == 0):
+        sys.stderr.write(BESTEFFORT_WARNING)
     original_directory = os.getcwd()
     if dist is None or dist.get_rank() == 0:
         print(original_directory)

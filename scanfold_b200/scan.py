@@ -60,6 +60,18 @@ def round_ed(ed):
     return out
 
 
+def empty_table(W, step, r, first_window=0):
+    """a shard without windows (more ranks than windows): zero-length columns of the right dtypes and widths"""
+    t = WindowTable()
+    t.W, t.r, t.step, t.first_window = W, r, step, first_window
+    t.start1 = t.end1 = np.zeros(0, dtype=np.int64)
+    t.mfe_dcal = t.native_unconstrained_dcal = np.zeros(0, dtype=np.int32)
+    t.mfe = t.z = t.p = t.ed = np.zeros(0, dtype=np.float64)
+    t.shuffle_dcal = np.zeros((0, r), dtype=np.int32)
+    t.pair_tbl = t.centroid_tbl = np.zeros((0, W), dtype=np.int16)
+    return t
+
+
 def table_from_result(res, first_window, step, n_regular, final_window):
     """ScanResult (raw engine arrays) -> WindowTable (reference-rounded values)"""
     t = WindowTable()

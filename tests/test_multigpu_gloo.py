@@ -26,9 +26,21 @@ WORKER = textwrap.dedent("""
     z100, mfe100, ed100 = pipeline.fold_inputs(table)
     W, step, n = case["W"], case["step"], case["n_windows"]
     w0, w1 = multigpu.shard_windows(n, world, rank)
-    acc = NumpyAccumulator(case["L"], W, step, w0, table.pair_tbl[w0:w1], z100[w0:w1], mfe100[w0:w1], ed100[w0:w1])
-    merged = multigpu.partner_table_distributed(acc, W, step, rank, world, dist)
+    acc = NumpyAccumulator(case["L"], W, step, w0, table.pair_tbl[w0:w1], z100[w0:w1], mfe100[w0:w1], ed100[w0:w1]) \
+        if w1 > w0 else None
+    merged = multigpu.partner_table_distributed(acc, W, step, rank, world, dist, n)
+    # the per-window columns travel as flat byte tensors too (no pickled objects)
+    from scanfold_b200 import scan
+    shard = scan.empty_table(W, step, table.r, w0)
+    for k in ("start1", "end1", "mfe_dcal", "mfe", "z", "p", "ed", "pair_tbl", "centroid_tbl",
+              "native_unconstrained_dcal", "shuffle_dcal"):
+        setattr(shard, k, getattr(table, k)[w0:w1])
+    shard.final = table.final if w1 == n and w1 > w0 else None
+    whole_w = multigpu.gather_window_tables(shard, rank, world, dist, with_shuffle_energies=True)
     if rank == 0:
+        for k in ("start1", "mfe", "z", "p", "ed", "pair_tbl", "centroid_tbl", "shuffle_dcal"):
+            assert np.array_equal(getattr(whole_w, k), getattr(table, k)[:n]), k
+        assert whole_w.final == table.final
         whole = foldstep.table_from_compact(*accumulate_numpy(case["L"], W, step, 0, table.pair_tbl, z100, mfe100, ed100))
         for name in ("nt_ptr", "partner", "count", "first_seen", "sums"):
             assert np.array_equal(getattr(merged, name), getattr(whole, name)), name
@@ -37,7 +49,10 @@ WORKER = textwrap.dedent("""
 """)
 
 
-@pytest.mark.parametrize("case,world", [("mono_w40", 2), ("step7_w40", 2), ("mono_w60_gc", 3)])
+# world 4 / 8 on the 111-window case: shards shorter than the W - step overlap, so halo rows cross several ranks
+# (the single-hop exchange lost them); world 8 on step7_w40 has 16 windows: 2 per rank
+@pytest.mark.parametrize("case,world", [("mono_w40", 2), ("step7_w40", 2), ("mono_w60_gc", 3), ("mono_w40", 4),
+                                        ("step7_w40", 8)])
 def test_two_rank_halo_exchange_equals_single_process(case, world, tmp_path):
     script = tmp_path / "worker.py"
     script.write_text(WORKER % {"root": ROOT, "case": case})
