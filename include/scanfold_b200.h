@@ -117,6 +117,9 @@ int sfb_scan_plan_create(const sfb_scan_args *args, sfb_scan_plan **plan);
 void sfb_scan_plan_keep_shuffles(sfb_scan_plan *plan);
 int sfb_scan_plan_run(sfb_scan_plan *plan, float *ms_total, float *ms_mfe, int32_t *n_launches);
 int sfb_scan_plan_fetch(sfb_scan_plan *plan, sfb_scan_out *out);
+/* CUDA-event times of the last run by stage: ms[0] window gather + shuffles, ms[1] MFE kernels, ms[2] partition
+ * function kernels, ms[3] everything else (copies, final-window slot).  bench.py's roofline blocks use them. */
+int sfb_scan_plan_stage_ms(const sfb_scan_plan *plan, float ms[4]);
 void sfb_scan_plan_destroy(sfb_scan_plan *plan);
 
 /* ScanFold-Fold accumulation step: the per-window pair records of ScanFold.py:564-677 gathered per nucleotide
@@ -159,6 +162,7 @@ void sfb_accumulate_free(sfb_partner_table *table);
  * 32-bit shared-memory loads per second (x4 = bytes/s).  No reference counterpart. */
 #define SFB_MICROBENCH_ADDMIN 0
 #define SFB_MICROBENCH_SMEM_LD32 1
+#define SFB_MICROBENCH_DFMA 2 /* fp64 fused multiply-adds per second (partition-function roofline) */
 int sfb_microbench(int which, double *ops_per_s);
 
 #if defined(__GNUC__)

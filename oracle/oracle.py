@@ -36,6 +36,7 @@ def lib():
                              C.c_void_p, C.c_void_p, C.c_char_p, C.c_void_p]
         L.sfo_deigan.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_void_p]
         L.sfo_fold_batch.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_void_p, C.c_int]
+        L.sfo_fold_batch_fast.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_void_p, C.c_int]
         L.sfo_pf_batch.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.sfo_eval_weight.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_double]
         L.sfo_eval_weight.restype = C.c_double
@@ -104,12 +105,13 @@ def deigan(react1, m, b):
     return out
 
 
-def fold_batch(seqs, n_threads=1):
-    """seqs: uint8/bytes array [n_seq, len] of ASCII -> int32 energies (dcal)."""
+def fold_batch(seqs, n_threads=1, fast=False):
+    """seqs: uint8/bytes array [n_seq, len] of ASCII -> int32 energies (dcal).  fast: the tuned CPU path."""
     a = np.ascontiguousarray(seqs, dtype=np.uint8)
     n_seq, ln = a.shape
     out = np.zeros(n_seq, dtype=np.int32)
-    if lib().sfo_fold_batch(a.tobytes(), n_seq, ln, out.ctypes.data, int(n_threads)) != 0:
+    fn = lib().sfo_fold_batch_fast if fast else lib().sfo_fold_batch
+    if fn(a.tobytes(), n_seq, ln, out.ctypes.data, int(n_threads)) != 0:
         raise RuntimeError("oracle fold_batch: " + lib().sfo_last_error().decode())
     return out
 

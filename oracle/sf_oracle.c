@@ -51,6 +51,7 @@ typedef struct {
 static params_t P;
 static char g_err[512];
 static long long g_dense, g_useful;
+static int g_par_gen = 0; /* bumped by every sfo_load_params: invalidates derived tables */
 
 static void set_err(const char *fmt, ...) {
     va_list ap;
@@ -315,6 +316,7 @@ int sfo_load_params(const char *path) {
                 }
             }
         P.loaded = 1;
+        g_par_gen++;
         rc = 0;
     } while (0);
     free(t.tok);
@@ -852,7 +854,7 @@ void sfo_deigan(const double *react1, int n, double m, double b, int *es1) {
 }
 
 /* ------------------------------------------------------------------ partition function (A.7) */
-typedef struct {
+typedef struct pfpar_s {
     double kT, pf_scale;
     double expstack[8][8], exphairpin[31], expbulge[31], expinternal[31];
     double expmismatchI[8][5][5], expmismatchH[8][5][5], expmismatch1nI[8][5][5], expmismatch23I[8][5][5];
@@ -871,7 +873,25 @@ static double smooth(double X) { /* X in dcal (A.7) */
     return 10. * 0.38490018 * s * s;
 }
 
-static pfpar_t *pf_params(double T) {
+/* Boltzmann factors are a function of (parameter file, T): built once and kept (41 k exp() calls otherwise dominate
+ * short windows); rebuilt when either changes.  Entries are never freed while a batch may still read them. */
+static pthread_mutex_t g_pf_mu = PTHREAD_MUTEX_INITIALIZER;
+static struct pfpar_s *g_pf_cache = NULL;
+static double g_pf_cache_T = -1e9;
+static int g_pf_cache_gen = -1;
+static struct pfpar_s *pf_params_build(double T);
+static struct pfpar_s *pf_params(double T) {
+    pthread_mutex_lock(&g_pf_mu);
+    if (!g_pf_cache || g_pf_cache_T != T || g_pf_cache_gen != g_par_gen) {
+        g_pf_cache = pf_params_build(T);   /* the previous table set is leaked on purpose (rare: tests reload parameters) */
+        g_pf_cache_T = T;
+        g_pf_cache_gen = g_par_gen;
+    }
+    struct pfpar_s *q = g_pf_cache;
+    pthread_mutex_unlock(&g_pf_mu);
+    return q;
+}
+static struct pfpar_s *pf_params_build(double T) {
     pfpar_t *q = (pfpar_t *)calloc(1, sizeof(pfpar_t));
     double kT = (T + K0) * GASCONST; /* cal/mol */
     q->kT = kT;
@@ -917,12 +937,7 @@ static pfpar_t *pf_params(double T) {
         }
     return q;
 }
-static void pf_params_free(pfpar_t *q) {
-    free(q->expint11);
-    free(q->expint21);
-    free(q->expint22);
-    free(q);
-}
+static void pf_params_free(pfpar_t *q) { (void)q; /* owned by the cache above */ }
 
 static double exp_E_Hairpin(const pfpar_t *q, int u, int type, int si1, int sj1, const char *str) {
     double z = (u <= 30) ? q->exphairpin[u] : q->exphairpin[30] * exp(-(q->lxc * log(u / 30.)) * 10. / q->kT);
@@ -1315,4 +1330,288 @@ int sfo_fold_batch(const char *seqs, int n_seq, int len, int *e_dcal, int n_thre
 int sfo_pf_batch(const char *seqs, int n_seq, int len, double *ed, double *dG, char *centroids, int n_threads) {
     job_t jb = {seqs, n_seq, len, 1, NULL, ed, dG, centroids, NULL, 0};
     return run_batch(&jb, n_threads);
+}
+
+/* ------------------------------------------------------------------ fast batch path (bench CPU arm)
+ * The same recursions as mfe_core for unconstrained, energy-only folds (the background folds of
+ * ScanFoldFunctions.py:774-789 are > 99 % of a scan), written the way a tuned CPU library does it: one
+ * reusable workspace per thread (no per-fold allocation or INF fill), the multiloop matrix kept in both
+ * orientations so the split loop reads two contiguous rows, and the three separable interior-loop classes
+ * (generic, 1xn, bulge) read copies of C that already carry the inner pair's mismatch term, so their inner
+ * loops are branch-free add-min sweeps over contiguous memory that gcc vectorises.  The nine table-driven
+ * shapes call E_IntLoop as before.  tests/test_oracle.py checks fast == simple fold by fold. */
+typedef struct {
+    int n;
+    int *C, *G, *V1, *VB, *V1T, *VBT, *M, *MT, *DM, *f5, *S;
+    unsigned char *T;
+    char *s;
+} fastws_t;
+
+static void fastws_free(fastws_t *w) {
+    free(w->C);
+    free(w->f5);
+    free(w->S);
+    free(w->T);
+    free(w->s);
+    memset(w, 0, sizeof *w);
+}
+
+static int fastws_reserve(fastws_t *w, int n) {
+    if (w->n >= n) return 0;
+    fastws_free(w);
+    const size_t N1 = (size_t)n + 2, sq = N1 * N1;
+    w->C = (int *)malloc(sizeof(int) * sq * 9);
+    w->f5 = (int *)malloc(sizeof(int) * (n + 2));
+    w->S = (int *)malloc(sizeof(int) * (n + 3));
+    w->T = (unsigned char *)malloc(sq);
+    w->s = (char *)malloc(n + 3);
+    if (!w->C || !w->f5 || !w->S || !w->T || !w->s) return -1;
+    w->G = w->C + sq;
+    w->V1 = w->G + sq;
+    w->VB = w->V1 + sq;
+    w->V1T = w->VB + sq;
+    w->VBT = w->V1T + sq;
+    w->M = w->VBT + sq;
+    w->MT = w->M + sq;
+    w->DM = w->MT + sq;
+    w->n = n;
+    return 0;
+}
+
+static int SZG[32][32];  /* generic loops: internal_loop[u1+u2] + asymmetry, reversed in u2: SZG[u1][30-u2] */
+static int SZ1[32];      /* 1xn loops of total size u */
+static int SZB[32];      /* bulges of size u */
+static int g_fast_tables = 0;
+
+static void fast_tables(void) {
+    const int BIG = INF;
+    for (int u1 = 0; u1 < 32; u1++)
+        for (int k = 0; k < 32; k++) {
+            const int u2 = 30 - k;
+            int v = BIG;
+            if (u1 >= 2 && u2 >= 2 && u1 + u2 <= MAXLOOP && !(u1 == 2 && u2 <= 3) && !(u2 == 2 && u1 <= 3))
+                v = P.internal_loop[u1 + u2] + MIN2(P.max_ninio, abs(u1 - u2) * P.ninio);
+            SZG[u1][k] = v;
+        }
+    for (int u = 0; u < 32; u++) {
+        SZ1[u] = (u >= 4 && u <= MAXLOOP) ? P.internal_loop[u] + MIN2(P.max_ninio, (u - 2) * P.ninio) : BIG;
+        SZB[u] = (u >= 2 && u <= MAXLOOP) ? P.bulge[u] : BIG;
+    }
+    g_fast_tables = 1;
+}
+
+static int mfe_fast(fastws_t *w, const char *seq, int n) {
+    if (fastws_reserve(w, n)) return INF;
+    const int N1 = n + 2;
+    int *restrict C = w->C, *restrict G = w->G, *restrict V1 = w->V1, *restrict VB = w->VB;
+    int *restrict V1T = w->V1T, *restrict VBT = w->VBT, *restrict M = w->M, *restrict MT = w->MT, *restrict DM = w->DM;
+    unsigned char *restrict T = w->T;
+    int *S = w->S;
+    char *s = w->s;
+    S[0] = S[n + 1] = S[n + 2] = 0;
+    for (int i = 1; i <= n; i++) {
+        char ch = (char)toupper((unsigned char)seq[i - 1]);
+        if (ch == 'T') ch = 'U';
+        s[i] = ch;
+        S[i] = enc(ch);
+    }
+    s[0] = ' ';
+    s[n + 1] = 0;
+#define X(A, i, j) A[(i) * N1 + (j)]
+    for (int i = n - TURN - 1; i >= 1; i--) {
+        for (int j = i + TURN + 1; j <= n; j++) {
+            const int type = pair_tab[S[i]][S[j]];
+            X(T, i, j) = (unsigned char)type;
+            int cij = INF;
+            if (type) {
+                const int si1 = S[i + 1], sj1 = S[j - 1];
+                cij = E_Hairpin(j - i - 1, type, si1, sj1, s + i);
+                /* the nine table-driven shapes */
+                static const signed char SH[9][2] = {{0, 0}, {0, 1}, {1, 0}, {1, 1}, {1, 2}, {2, 1}, {2, 2}, {2, 3}, {3, 2}};
+                for (int z = 0; z < 9; z++) {
+                    const int p = i + 1 + SH[z][0], q = j - 1 - SH[z][1];
+                    if (q - p <= TURN) continue;
+                    const int t2 = X(T, p, q);
+                    if (!t2) continue;
+                    const int e = X(C, p, q) + E_IntLoop(SH[z][0], SH[z][1], type, rtype[t2], si1, sj1, S[p - 1], S[q + 1]);
+                    if (e < cij) cij = e;
+                }
+                /* generic loops: rows p = i+1+u1, candidates contiguous in q */
+                int bg = INF;
+                for (int u1 = 2; u1 <= MAXLOOP - 2; u1++) {
+                    const int p = i + 1 + u1;
+                    int qlo = j - 1 - (MAXLOOP - u1), qhi = j - 3;
+                    if (qlo < p + TURN + 1) qlo = p + TURN + 1;
+                    if (qlo > qhi) {
+                        if (p + TURN + 1 > qhi) break;
+                        continue;
+                    }
+                    const int *restrict g = G + p * N1;
+                    const int *restrict sz = SZG[u1] + (31 - j);   /* sz[q] = size term of u2 = j-1-q */
+                    int b = INF;
+                    for (int q = qlo; q <= qhi; q++) {
+                        const int e = g[q] + sz[q];
+                        b = e < b ? e : b;
+                    }
+                    bg = b < bg ? b : bg;
+                }
+                if (bg < INF) {
+                    bg += P.mismatchI[type][si1][sj1];
+                    if (bg < cij) cij = bg;
+                }
+                /* 1xn loops: u1 = 1 along row i+2, u2 = 1 along column j-2 (transposed copy) */
+                {
+                    int b = INF;
+                    const int p = i + 2;
+                    int qlo = j - 1 - (MAXLOOP - 1), qhi = j - 4;
+                    if (qlo < p + TURN + 1) qlo = p + TURN + 1;
+                    const int *restrict v = V1 + p * N1;
+                    for (int q = qlo; q <= qhi; q++) {   /* total size u = 1 + (j-1-q) */
+                        const int e = v[q] + SZ1[j - q];
+                        b = e < b ? e : b;
+                    }
+                    const int q2 = j - 2;
+                    int plo = i + 4, phi = i + 1 + (MAXLOOP - 1);
+                    if (phi > q2 - TURN - 1) phi = q2 - TURN - 1;
+                    const int *restrict vt = V1T + q2 * N1;
+                    for (int pp = plo; pp <= phi; pp++) {   /* u = (pp-i-1) + 1 */
+                        const int e = vt[pp] + SZ1[pp - i];
+                        b = e < b ? e : b;
+                    }
+                    if (b < INF) {
+                        b += P.mismatch1nI[type][si1][sj1];
+                        if (b < cij) cij = b;
+                    }
+                }
+                /* bulges of size >= 2 */
+                {
+                    int b = INF;
+                    const int p = i + 1;
+                    int qlo = j - 1 - MAXLOOP, qhi = j - 3;
+                    if (qlo < p + TURN + 1) qlo = p + TURN + 1;
+                    const int *restrict v = VB + p * N1;
+                    for (int q = qlo; q <= qhi; q++) {
+                        const int e = v[q] + SZB[j - 1 - q];
+                        b = e < b ? e : b;
+                    }
+                    const int q2 = j - 1;
+                    int plo = i + 3, phi = i + 1 + MAXLOOP;
+                    if (phi > q2 - TURN - 1) phi = q2 - TURN - 1;
+                    const int *restrict vt = VBT + q2 * N1;
+                    for (int pp = plo; pp <= phi; pp++) {
+                        const int e = vt[pp] + SZB[pp - i - 1];
+                        b = e < b ? e : b;
+                    }
+                    if (b < INF) {
+                        b += type > 2 ? P.TerminalAU : 0;
+                        if (b < cij) cij = b;
+                    }
+                }
+                /* multiloop closed by (i,j) */
+                if (j - i - 2 > TURN) {
+                    const int d = X(DM, i + 1, j - 1);
+                    if (d < INF) {
+                        const int e = d + E_MLstem(rtype[type], sj1, si1) + P.MLclosing;
+                        if (e < cij) cij = e;
+                    }
+                }
+            }
+            X(C, i, j) = cij;
+            {
+                int vg = INF, v1 = INF, vb = INF;
+                if (type && i > 1 && j < n) {
+                    const int t2 = rtype[type];
+                    vg = cij + P.mismatchI[t2][S[j + 1]][S[i - 1]];
+                    v1 = cij + P.mismatch1nI[t2][S[j + 1]][S[i - 1]];
+                    vb = cij + (t2 > 2 ? P.TerminalAU : 0);
+                }
+                X(G, i, j) = vg;
+                X(V1, i, j) = v1;
+                X(VB, i, j) = vb;
+                X(V1T, j, i) = v1;
+                X(VBT, j, i) = vb;
+            }
+            /* fML */
+            int m = INF;
+            if (j - i - 1 > TURN) {
+                const int a = X(M, i + 1, j), b = X(M, i, j - 1);
+                if (a < INF) m = a + P.MLbase;
+                if (b < INF && b + P.MLbase < m) m = b + P.MLbase;
+            }
+            if (type) {
+                const int e = cij + E_MLstem(type, i > 1 ? S[i - 1] : -1, j < n ? S[j + 1] : -1);
+                if (e < m) m = e;
+            }
+            int dec = 2 * INF;
+            {
+                const int *restrict a = M + i * N1;          /* M[i][k] */
+                const int *restrict b = MT + j * N1 + 1;     /* MT[j][k+1] = M[k+1][j] */
+                for (int k = i + 1 + TURN; k <= j - 2 - TURN; k++) {
+                    const int e = a[k] + b[k];
+                    dec = e < dec ? e : dec;
+                }
+            }
+            if (dec >= INF - 1000000) dec = INF;
+            X(DM, i, j) = dec;
+            m = MIN2(m, dec);
+            X(M, i, j) = m;
+            X(MT, j, i) = m;
+        }
+    }
+    int *f5 = w->f5;
+    for (int j = 0; j <= MIN2(TURN + 1, n); j++) f5[j] = 0;
+    for (int j = TURN + 2; j <= n; j++) {
+        int best = f5[j - 1];
+        for (int i = j - TURN - 1; i >= 1; i--) {
+            const int type = X(T, i, j);
+            if (!type) continue;
+            const int e = f5[i - 1] + X(C, i, j) + E_ExtLoop(type, i > 1 ? S[i - 1] : -1, j < n ? S[j + 1] : -1);
+            if (e < best) best = e;
+        }
+        f5[j] = best;
+    }
+#undef X
+    return f5[n];
+}
+
+static void *worker_fast(void *arg) {
+    job_t *jb = (job_t *)arg;
+    fastws_t ws;
+    memset(&ws, 0, sizeof ws);
+    for (;;) {
+        int k0 = __sync_fetch_and_add(jb->next, 8);
+        if (k0 >= jb->n_seq) break;
+        for (int k = k0; k < MIN2(k0 + 8, jb->n_seq); k++) {
+            jb->e[k] = mfe_fast(&ws, jb->seqs + (size_t)k * jb->len, jb->len);
+            if (jb->e[k] >= INF) jb->bad = 1;
+        }
+    }
+    fastws_free(&ws);
+    return NULL;
+}
+
+int sfo_fold_batch_fast(const char *seqs, int n_seq, int len, int *e_dcal, int n_threads) {
+    if (!P.loaded) {
+        set_err("parameters not loaded");
+        return -1;
+    }
+    init_pair_tab();
+    fast_tables();
+    if (n_threads < 1) n_threads = 1;
+    if (n_threads > 256) n_threads = 256;
+    volatile int next = 0;
+    job_t jobs[256];
+    pthread_t th[256];
+    for (int t = 0; t < n_threads; t++) {
+        job_t jb = {seqs, n_seq, len, 0, e_dcal, NULL, NULL, NULL, &next, 0};
+        jobs[t] = jb;
+        pthread_create(&th[t], NULL, worker_fast, &jobs[t]);
+    }
+    int bad = 0;
+    for (int t = 0; t < n_threads; t++) {
+        pthread_join(th[t], NULL);
+        bad |= jobs[t].bad;
+    }
+    if (bad) set_err("fast fold failed");
+    return bad ? -1 : 0;
 }

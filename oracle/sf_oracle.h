@@ -46,6 +46,9 @@ void sfo_deigan(const double *react1, int n, double m, double b, int *es1);
 
 /* batch of equal-length folds, energy only, OpenMP over folds (bench cpu_baseline) */
 int sfo_fold_batch(const char *seqs, int n_seq, int len, int *e_dcal, int n_threads);
+/* the same energies through the tuned path (per-thread reusable buffers, vectorisable inner loops): what a CPU
+ * library would run; bench.py's CPU arm times this one, tests check it against sfo_fold_batch fold by fold */
+int sfo_fold_batch_fast(const char *seqs, int n_seq, int len, int *e_dcal, int n_threads);
 /* batch of PF/ED (no constraints) */
 int sfo_pf_batch(const char *seqs, int n_seq, int len, double *ed, double *dG, char *centroids,
                  int n_threads);

@@ -242,6 +242,7 @@ struct sfb_scan_plan {
     FoldWork fw;
     PfWork pw;
     bool keep_shuffles = false;
+    float stage_ms[4] = {0.f, 0.f, 0.f, 0.f};   // last run: gather + shuffles, MFE, PF, rest
 };
 
 struct sfb_partner_table {
@@ -563,14 +564,16 @@ int sfb_scan_plan_run(sfb_scan_plan *P, float *ms_total, float *ms_mfe, int32_t 
     const sfb_scan_args &a = P->a;
     cudaStream_t st = g_ctx.stream;
     int n_launch = 0;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, em0 = nullptr, em1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, em0 = nullptr, em1 = nullptr, es0 = nullptr, ep1 = nullptr;
     try {
         CK(cudaSetDevice(g_ctx.device));
         CK(cudaEventCreate(&ev0));
         CK(cudaEventCreate(&ev1));
         CK(cudaEventCreate(&em0));
         CK(cudaEventCreate(&em1));
-        float mfe_ms = 0.f;
+        CK(cudaEventCreate(&es0));
+        CK(cudaEventCreate(&ep1));
+        float mfe_ms = 0.f, shuf_ms = 0.f, pf_ms = 0.f;
         CK(cudaEventRecord(ev0, st));
         const int n = P->n_slots, r = a.r, W = a.W;
         for (int c0 = 0, cn = 0; c0 < n; c0 += cn) {
@@ -578,6 +581,7 @@ int sfb_scan_plan_run(sfb_scan_plan *P, float *ms_total, float *ms_mfe, int32_t 
             if (a.final_window && n - (c0 + cn) == 1) cn++;  // never leave the final-window slot alone
             const bool has_final = a.final_window && (c0 + cn == n);
             const int cn_regular = cn - (has_final ? 1 : 0);
+            CK(cudaEventRecord(es0, st));
             // natives (final slot = seq[L-W:L])
             launch_gather_windows(P->seq.p, a.L, W, a.step, a.first_window + c0, cn, has_final, P->nat.p, st, &n_launch);
             // background sequences
@@ -673,6 +677,7 @@ int sfb_scan_plan_run(sfb_scan_plan *P, float *ms_total, float *ms_mfe, int32_t 
                 L.gscratch_per_cta = (long long)P->pw.per_cta;
                 launch_pf(L, g_ctx.d_mfe, g_ctx.d_pf, g_ctx.n_sm, st, &n_launch);
             }
+            CK(cudaEventRecord(ep1, st));
             if (has_final) {
                 // Q5: the final-window block re-evaluates the STALE fold compound of the last regular window
                 const int last = n - 2, fin = n - 1;
@@ -696,10 +701,14 @@ int sfb_scan_plan_run(sfb_scan_plan *P, float *ms_total, float *ms_mfe, int32_t 
                                                                        P->dG.p, last, fin, W, copy_pf);
                 n_launch++;
             }
-            CK(cudaEventSynchronize(em1));
+            CK(cudaEventSynchronize(ep1));
             float ms = 0.f;
             CK(cudaEventElapsedTime(&ms, em0, em1));
             mfe_ms += ms;
+            CK(cudaEventElapsedTime(&ms, es0, em0));
+            shuf_ms += ms;
+            CK(cudaEventElapsedTime(&ms, em1, ep1));
+            pf_ms += ms;
         }
         CK(cudaEventRecord(ev1, st));
         CK(cudaEventSynchronize(ev1));
@@ -708,13 +717,21 @@ int sfb_scan_plan_run(sfb_scan_plan *P, float *ms_total, float *ms_mfe, int32_t 
         CK(cudaEventElapsedTime(&tot, ev0, ev1));
         if (ms_total) *ms_total = tot;
         if (ms_mfe) *ms_mfe = mfe_ms;
+        P->stage_ms[0] = shuf_ms;
+        P->stage_ms[1] = mfe_ms;
+        P->stage_ms[2] = pf_ms;
+        P->stage_ms[3] = tot - shuf_ms - mfe_ms - pf_ms;
         if (n_launches_out) *n_launches_out = n_launch;
         cudaEventDestroy(ev0);
         cudaEventDestroy(ev1);
         cudaEventDestroy(em0);
         cudaEventDestroy(em1);
+        cudaEventDestroy(es0);
+        cudaEventDestroy(ep1);
         return 0;
     } catch (const CudaError &e) {
+        if (es0) cudaEventDestroy(es0);
+        if (ep1) cudaEventDestroy(ep1);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
         if (em0) cudaEventDestroy(em0);
@@ -757,6 +774,12 @@ int sfb_scan_plan_fetch(sfb_scan_plan *P, sfb_scan_out *out) {
     } catch (const CudaError &e) {
         return fail(SFB_E_CUDA, e.what());
     }
+}
+
+int sfb_scan_plan_stage_ms(const sfb_scan_plan *plan, float ms[4]) {
+    if (!plan || !ms) return fail(SFB_E_ARG, "null argument");
+    for (int k = 0; k < 4; k++) ms[k] = plan->stage_ms[k];
+    return 0;
 }
 
 void sfb_scan_plan_destroy(sfb_scan_plan *plan) {

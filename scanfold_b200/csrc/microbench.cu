@@ -51,10 +51,29 @@ __global__ void __launch_bounds__(MB_THREADS) smem_kernel(int *out, int iters) {
     if (s == 0x7fffffff) out[0] = s;
 }
 
+// 8 independent DFMA chains per thread: the fp64 FMA issue rate the partition-function kernels are measured against
+__global__ void __launch_bounds__(MB_THREADS) dfma_kernel(int *out, int iters, double x) {
+    double acc[MB_CHAINS];
+#pragma unroll
+    for (int k = 0; k < MB_CHAINS; k++) acc[k] = 1e-3 * (threadIdx.x + k) + blockIdx.x;
+    const double y = 1.0 - 1e-9 * x;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int rep = 0; rep < 4; rep++) {
+#pragma unroll
+            for (int k = 0; k < MB_CHAINS; k++) acc[k] = fma(acc[k], y, x);
+        }
+    }
+    double s = 0.;
+#pragma unroll
+    for (int k = 0; k < MB_CHAINS; k++) s += acc[k];
+    if (s == 12345.678) out[0] = 1;
+}
+
 }  // namespace
 
 extern "C" int sfb_microbench(int which, double *ops_per_s) {
-    if (!ops_per_s || (which != SFB_MICROBENCH_ADDMIN && which != SFB_MICROBENCH_SMEM_LD32)) return SFB_E_ARG;
+    if (!ops_per_s || (which != SFB_MICROBENCH_ADDMIN && which != SFB_MICROBENCH_SMEM_LD32 && which != SFB_MICROBENCH_DFMA)) return SFB_E_ARG;
     int dev = 0, n_sm = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return SFB_E_CUDA;
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
@@ -64,19 +83,21 @@ extern "C" int sfb_microbench(int which, double *ops_per_s) {
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
     const int grid = n_sm * 2;
-    const int iters = which == SFB_MICROBENCH_ADDMIN ? 8192 : 2048;
+    const int iters = which == SFB_MICROBENCH_ADDMIN ? 8192 : (which == SFB_MICROBENCH_DFMA ? 1024 : 2048);
     double best = 0.;
     for (int rep = 0; rep < 4; rep++) {
         cudaEventRecord(e0);
         if (which == SFB_MICROBENCH_ADDMIN)
             addmin_kernel<<<grid, MB_THREADS>>>(d_out, iters, rep + 1);
+        else if (which == SFB_MICROBENCH_DFMA)
+            dfma_kernel<<<grid, MB_THREADS>>>(d_out, iters, 1e-3 * (rep + 1));
         else
             smem_kernel<<<grid, MB_THREADS>>>(d_out, iters);
         cudaEventRecord(e1);
         if (cudaEventSynchronize(e1) != cudaSuccess) break;
         float ms = 0.f;
         cudaEventElapsedTime(&ms, e0, e1);
-        const double per_thread = which == SFB_MICROBENCH_ADDMIN ? (double)iters * 4 * MB_CHAINS : (double)iters * 8 * 4;
+        const double per_thread = which == SFB_MICROBENCH_SMEM_LD32 ? (double)iters * 8 * 4 : (double)iters * 4 * MB_CHAINS;
         const double ops = per_thread * MB_THREADS * grid;
         if (rep > 0 && ms > 0.f) best = ops / (ms * 1e-3) > best ? ops / (ms * 1e-3) : best;
     }

@@ -20,7 +20,7 @@ SHUFFLE_MONO, SHUFFLE_DI = 0, 1
 
 EXPORTS = ["sfb_version", "sfb_init", "sfb_shutdown", "sfb_last_error", "sfb_params_besteffort", "sfb_fold_batch",
            "sfb_pf_batch", "sfb_deigan", "sfb_scan", "sfb_scan_plan_create", "sfb_scan_plan_keep_shuffles",
-           "sfb_scan_plan_run", "sfb_scan_plan_fetch", "sfb_scan_plan_destroy", "sfb_accumulate_begin",
+           "sfb_scan_plan_run", "sfb_scan_plan_fetch", "sfb_scan_plan_stage_ms", "sfb_scan_plan_destroy", "sfb_accumulate_begin",
            "sfb_accumulate_geometry", "sfb_accumulate_export", "sfb_accumulate_merge", "sfb_accumulate_compact",
            "sfb_accumulate_fetch", "sfb_accumulate_launches", "sfb_accumulate_free", "sfb_microbench", "sfb_set_stream", "sfb_set_engines"]
 
@@ -80,6 +80,7 @@ def load_library():
         L.sfb_scan_plan_keep_shuffles.restype = None
         L.sfb_scan_plan_run.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_int32)]
         L.sfb_scan_plan_fetch.argtypes = [C.c_void_p, C.POINTER(ScanOut)]
+        L.sfb_scan_plan_stage_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
         L.sfb_scan_plan_destroy.argtypes = [C.c_void_p]
         L.sfb_scan_plan_destroy.restype = None
         L.sfb_accumulate_begin.argtypes = [C.POINTER(AccumArgs), C.POINTER(C.c_void_p)]
@@ -279,6 +280,9 @@ class ScanPlan:
         ms_t, ms_m, nl = C.c_float(), C.c_float(), C.c_int32()
         _check(self._lib.sfb_scan_plan_run(self._plan, C.byref(ms_t), C.byref(ms_m), C.byref(nl)))
         self.ms_total, self.ms_mfe, self.n_launches = ms_t.value, ms_m.value, nl.value
+        st = (C.c_float * 4)()
+        _check(self._lib.sfb_scan_plan_stage_ms(self._plan, st))
+        self.stage_ms = {"shuffle": st[0], "mfe": st[1], "pf": st[2], "other": st[3]}
         return self
 
     def fetch(self):
@@ -400,7 +404,7 @@ class Accumulator:
 
 
 def microbench(which):
-    """Measured device peak: which=0 int32 add-min ops/s, which=1 32-bit shared-memory loads/s."""
+    """Measured device peak: which=0 int32 add-min ops/s, which=1 32-bit shared-memory loads/s, which=2 fp64 FMA/s."""
     ensure_init()
     v = C.c_double()
     _check(load_library().sfb_microbench(int(which), C.byref(v)))

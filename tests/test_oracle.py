@@ -124,3 +124,19 @@ def test_work_counters_match_closed_forms(oracle):
         dense, useful = oracle.counters()
         assert dense == wc.dense_relaxations(len(s))
         assert useful == wc.useful_relaxations(s)
+
+
+@pytest.mark.parametrize("W", [4, 5, 9, 17, 40, 77, 120, 200])
+def test_fast_batch_path_equals_simple(oracle, W):
+    """The tuned batch path bench.py's CPU arm times (sfo_fold_batch_fast: reusable buffers, vectorised sweeps over
+    mismatch-carrying copies of C) returns exactly the energies of the simple checker path, sequence by sequence."""
+    from util import rand_seqs
+    n = 200 if W <= 120 else 24
+    seqs = rand_seqs(31 * W, n, W, gc_rich=True) + ["A" * W, ("GC" * W)[:W], ("GGGGAAAACCCC" * W)[:W], "N" * W,
+                                                    ("ACGUN" * W)[:W], ("CUUCGG" * W)[:W], ("gggaaaccc" * W)[:W]]
+    a = np.frombuffer("".join(seqs).encode(), dtype=np.uint8).reshape(len(seqs), W)
+    simple = oracle.fold_batch(a, n_threads=2)
+    fast = oracle.fold_batch(a, n_threads=3, fast=True)
+    assert np.array_equal(simple, fast)
+    for k in (0, 1, len(seqs) - 1):
+        assert simple[k] == oracle.mfe(seqs[k], structure=False)[0]
