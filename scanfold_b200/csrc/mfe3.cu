@@ -391,11 +391,14 @@ mfe3_kernel(MfeLaunch L, const MfeTables *__restrict__ T, const Tab3 *__restrict
     const int cC = (uok && U > 11) ? c3_cap[U] : BIG;
     // a disabled tap reads the address of an enabled lane (same word: a broadcast, never a bank conflict)
     // rows d-2, d-3 are being written in the same phase: the (disabled) lanes 0, 1 read the rows of lanes 2, 3 instead.
-    // compute-sanitizer racecheck is clean except for disabled B taps that run past a short row's end into the next
-    // ring row (value discarded: their size term is BIG).
+    // The three range-minimum taps (offsets 10, 18, 26 of the M8 row) do the same with the rows of lanes 11, 20, 28: an
+    // enabled tap never leaves its row (row d-2-U has W-d+2+U entries), while a disabled one at its own row could run
+    // past a short row's end into the ring row unit S is writing in the same phase (racecheck r01: mfe3.cu:530 / :718).
     const int UB = U < 2 ? U + 2 : (U > MAXLOOP ? MAXLOOP : U);
     const int UA = U < 7 ? U + 8 : (U > MAXLOOP ? MAXLOOP - 1 : U);
     const int UC = U < 12 ? U + 12 : (U > MAXLOOP ? MAXLOOP : U);
+    const int UB10 = U < 11 ? 11 : (U > MAXLOOP ? MAXLOOP : U), UB18 = U < 20 ? 20 : (U > MAXLOOP ? MAXLOOP : U);
+    const int UB26 = U < 28 ? 28 : (U > MAXLOOP ? MAXLOOP : U);
     const int kA = ((UA & 1) ? O_NO : O_NE) + 3 + (UA >> 1), kC = O_M8 + UC - 1;
     const int g6a = c3_sG6[0], g6b = c3_sG6[1], g6c = c3_sG6[2], g9 = c3_cap[9], g10 = c3_cap[10];
 
@@ -747,7 +750,9 @@ mfe3_kernel(MfeLaunch L, const MfeTables *__restrict__ T, const Tab3 *__restrict
                     if (c < n) {
                         const int slot = (d - 2 - UB) & (R32 - 1);
                         const short *qA = smb + kA + ((d - 2 - UA) & (R32 - 1)) * PR;
-                        const short *qB = smb + O_M8 + slot * PR;
+                        const short *qB10 = smb + O_M8 + 10 + ((d - 2 - UB10) & (R32 - 1)) * PR;
+                        const short *qB18 = smb + O_M8 + 18 + ((d - 2 - UB18) & (R32 - 1)) * PR;
+                        const short *qB26 = smb + O_M8 + 26 + ((d - 2 - UB26) & (R32 - 1)) * PR;
                         const short *qC = smb + kC + ((d - 2 - UC) & (R32 - 1)) * PR;
                         const unsigned *qR = sm.rpa + slot * PRW + 1;        // inner pair (i+1, j-1-U) and 1xn neighbour
                         const unsigned *qL = sm.rpq + slot * PRW + d - 1;    // inner pair (i+1+U, j-1) and 1xn neighbour
@@ -758,8 +763,8 @@ mfe3_kernel(MfeLaunch L, const MfeTables *__restrict__ T, const Tab3 *__restrict
                             const int i = en.x, eI = en.y, e1 = en.z, eB = en.w;
                             en = lst[c + NW];   // next entry (at most NW past the list end: still inside sm.list)
                             const unsigned wr = qR[i], wl = qL[i];
-                            const short *pa = qA + i, *pb = qB + i, *pc = qC + i;
-                            const int xa = pa[0], xb10 = pb[10], xb18 = pb[18], xb26 = pb[26], xc = pc[0];
+                            const short *pa = qA + i, *pc = qC + i;
+                            const int xa = pa[0], xb10 = qB10[i], xb18 = qB18[i], xb26 = qB26[i], xc = pc[0];
                             const unsigned wm = __vmins2(wr, wl);
                             const int xb = (int)(short)(wm & 0xffffu), x1 = (int)wm >> 16;
                             int g = xa + cA;

@@ -58,6 +58,9 @@ CASES = {
     "motifs_w50": dict(L=0, seed=18, args=["-w", "50", "-r", "10"],
                        seq="AAUAC" + "GGGGCGCUUCGGCGCCCC" + "AUAAUUAAUA" + "GCCGGAUCGAAAGAUCCGGC" + "AAUAUAAUAAAUUA" +
                            "GGCACGGCUUUUGCCGUGCC" + "UUAUAAUAUA" + "CCGCGGAGAAAUCCGCGG" + "AUUAAUAUAAUAUUAAAUUAAUAAUAUUAAUA"),
+    # C1 geometry (BASELINE.json configs[0]: 120-nt window, step 1, 100 mono shuffles) on a 400-nt record: pins the host
+    # pipeline where the r = 100 z-score rounding and the exact-mean paths matter
+    "c1_w120_r100": dict(L=400, seed=19, args=["-w", "120", "-r", "100"]),
     "dna_name_w30": dict(L=100, seed=17, alpha="ACGT", args=["-w", "30", "-r", "8", "--name", "chrTest"],
                          header="rec17|extra|fields"),
 }

@@ -103,3 +103,46 @@ class NumpyAccumulator:
         partner = self.nt0 + row0 + rows + 1 + cols - (self.W - 1)
         return (nparts, partner, cnt[rows, cols], self.first[row0:row0 + n_rows][rows, cols],
                 self.sums[:, row0:row0 + n_rows][:, rows, cols])
+
+
+def dinucl_shuffle(s, rng):
+    """Altschul-Erikson dinucleotide shuffle (uniform over the Eulerian paths of the dinucleotide multigraph), the
+    algorithm the reference uses for --type di (ScanFoldFunctions.py:155-277).  Test-side host implementation that
+    feeds parity shuffles and host z-score samples; `rng` is a random.Random."""
+    n = len(s)
+    if n < 3:
+        return s
+    succ = {}
+    for a, b in zip(s[:-1], s[1:]):
+        succ.setdefault(a, []).append(b)
+    last = s[-1]
+    verts = sorted(set(s))
+    while True:                                   # last edge per vertex: must form a tree towards `last`
+        last_edge = {v: rng.choice(succ[v]) for v in verts if v != last}
+        ok = True
+        for v in last_edge:
+            u, hops = v, 0
+            while u != last and hops <= len(verts):
+                u = last_edge[u]
+                hops += 1
+            ok &= u == last
+        if ok:
+            break
+    lists = {}
+    for v in verts:
+        lst = list(succ.get(v, []))
+        if v in last_edge:
+            lst.remove(last_edge[v])
+        rng.shuffle(lst)
+        if v in last_edge:
+            lst.append(last_edge[v])
+        lists[v] = lst
+    out, cur = [s[0]], s[0]
+    ptr = {v: 0 for v in verts}
+    for _ in range(n - 2):
+        nxt = lists[cur][ptr[cur]]
+        ptr[cur] += 1
+        out.append(nxt)
+        cur = nxt
+    out.append(last)
+    return "".join(out)
