@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <cstddef>
 #include <cstring>
 #include <dlfcn.h>
 #include <memory>
@@ -166,11 +167,22 @@ void encode_host(const uint8_t *ascii, size_t n, std::vector<uint8_t> &codes) {
 }
 
 // ---------------------------------------------------------------------------------------------
+constexpr int MFE4_MIN_W = 301;                       // windows the shared-memory kernels do not take (mfe3: <= 300 nt)
+constexpr size_t MFE4_SCRATCH_CAP = (size_t)24 << 30;  // HBM the blocked kernel may use for the matrices of one batch
+
 struct FoldWork {  // device scratch for one MFE launch
     DevBuf<int32_t> scratch, scratch2;
+    DevBuf<char> scratch4;   // mfe4: C / FML / split matrices of the folds in flight
     int mode = 0;
     size_t per_cta = 0, per_warp2 = 0;
+    static bool use4(int W) { return engine() >= 3 && W >= MFE4_MIN_W; }
     void prepare(int W, int n_fold) {
+        if (use4(W)) {
+            const size_t per = mfe4_bytes_per_fold(W);
+            size_t folds = std::max<size_t>(1, std::min<size_t>((size_t)std::max(n_fold, 1), MFE4_SCRATCH_CAP / per));
+            if (folds * per > scratch4.n) scratch4.alloc(folds * per);
+            return;
+        }
         per_cta = mfe_scratch_ints_per_cta(W, &mode);
         size_t need = per_cta * (size_t)mfe_grid_size(W, g_ctx.n_sm, n_fold);
         if (need > scratch.n) scratch.alloc(need);
@@ -187,7 +199,26 @@ struct FoldWork {  // device scratch for one MFE launch
         return e;
     }
     // energy-only unconstrained folds: int16 warp-per-fold kernel, then the int32 kernel on whatever it flagged
+    // any fold above 300 nt (energy only or native with structure, constraints, span): blocked kernel
+    void launch4(const MfeLaunch &L, cudaStream_t st, int *n_launch) const {
+        const int32_t *hp = reinterpret_cast<const int32_t *>(reinterpret_cast<const char *>(g_ctx.d_mfe) +
+                                                              offsetof(MfeTables, hairpin_len));
+        launch_mfe4(L, g_ctx.d_mfe, hp, scratch4.p, scratch4.n, nullptr, g_ctx.n_sm, st, n_launch);
+    }
+    // native fold with enforced pairs / span (everything the fast kernels do not take)
+    void launch_general(MfeLaunch L, cudaStream_t st, int *n_launch) const {
+        if (use4(L.W)) {
+            launch4(L, st, n_launch);
+            return;
+        }
+        fill(L);
+        launch_mfe(L, g_ctx.d_mfe, g_ctx.n_sm, st, n_launch);
+    }
     void launch_energy_only(MfeLaunch L, cudaStream_t st, int *n_launch) const {
+        if (use4(L.W)) {
+            launch4(L, st, n_launch);
+            return;
+        }
         const bool use3 = engine() == 3 && mfe3_supports(L.W), use2 = engine() != 1 && mfe2_supports(L.W) && !L.pair_tbl;
         const bool hc3 = L.hc && L.hc_simple && use3;   // per-nucleotide hard constraints: folded into mfe3
         // mfe3 also traces the structure back and takes stacking pseudo-energies (Deigan)
@@ -290,6 +321,7 @@ int sfb_init(int device_ordinal, const char *par_file_or_null) {
         CK(cudaMemcpy(g_ctx.d_mfe, &g_ctx.hp.mfe, sizeof(MfeTables), cudaMemcpyHostToDevice));
         mfe2_upload_tables(g_ctx.hp.mfe);
         mfe3_upload_tables(g_ctx.hp.mfe);
+        mfe4_upload_tables(g_ctx.hp.mfe);
         CK(cudaGetLastError());
         g_ctx.pf_temperature = -1e9;
         g_ctx.ready = true;
@@ -654,8 +686,7 @@ int sfb_scan_plan_run(sfb_scan_plan *P, float *ms_total, float *ms_mfe, int32_t 
                 if ((!a.hc || P->hc_simple) && a.model.max_bp_span <= 0) {
                     P->fw.launch_energy_only(L, st, &n_launch);   // flags / Deigan only: mfe3 (+ int32 redo)
                 } else {
-                    P->fw.fill(L);
-                    launch_mfe(L, g_ctx.d_mfe, g_ctx.n_sm, st, &n_launch);
+                    P->fw.launch_general(L, st, &n_launch);
                 }
             } else if (!need_unc) {
                 CK(cudaMemcpyAsync(P->mfe.p + c0, P->nat_unc.p + c0, sizeof(int32_t) * cn, cudaMemcpyDeviceToDevice, st));

@@ -109,6 +109,13 @@ size_t mfe3_scratch_shorts_per_cta(int W);
 void mfe3_upload_tables(const MfeTables &M);
 void launch_mfe3(const MfeLaunch &L, const MfeTables *d_tab, int n_sm, cudaStream_t stream, int *n_launches);
 int mfe_grid_size(int W, int n_sm, int n_fold);
+// fourth-generation kernel (mfe4.cu): blocked int32 fill in HBM for windows above 300 nt and whole-sequence folds.
+// `scratch` holds the matrices of as many folds as fit (mfe4_bytes_per_fold each; at least one); d_hp_len = hairpin
+// initiation by loop size [W + 1] on the device; pair32 = optional 32-bit pair table (whole-sequence folds)
+void mfe4_upload_tables(const MfeTables &M);
+size_t mfe4_bytes_per_fold(int n);
+void launch_mfe4(const MfeLaunch &L, const MfeTables *d_tab, const int32_t *d_hp_len, void *scratch, size_t scratch_bytes,
+                 int32_t *pair32, int n_sm, cudaStream_t stream, int *n_launches);
 
 void launch_pf(const PfLaunch &L, const MfeTables *d_mfe, const PfTables *d_pf, int n_sm, cudaStream_t stream,
                int *n_launches);

@@ -374,3 +374,42 @@ def test_scan_across_chunk_boundary(engine, oracle):
             assert sorted(sh) == sorted(frag) and oracle.mfe(sh, structure=False)[0] == full.shuffle_dcal[w, k]
     # final-window slot: the stale fold compound of the last regular window, fresh shuffles of seq[L-W:L] (Q5)
     assert full.mfe_dcal[n] == full.mfe_dcal[n - 1] and np.array_equal(full.pair_tbl[n], full.pair_tbl[n - 1])
+
+
+@pytest.mark.parametrize("W", [301, 333, 450, 600, 1024])
+def test_blocked_kernel_long_windows(engine, oracle, W):
+    """Windows above 300 nt run on the blocked int32 kernel (mfe4.cu): energies and structures equal the int32 CTA kernel
+    (mfe.cu, selected with set_engines(mfe=1)) and the oracle -- unconstrained, with per-nucleotide flags, with enforced
+    pairs, with stacking pseudo-energies and with a span limit."""
+    rng = random.Random(W)
+    n_seq = 10 if W <= 600 else 4
+    seqs = rand_seqs(8100 + W, n_seq, W, gc_rich=True) + [("GGGGAAAACCCC" * W)[:W], ("GC" * W)[:W], "A" * W, ("ACGUN" * W)[:W]]
+    hc_flags = [_rand_hc(rng, W, False) for _ in seqs]
+    hc_br = [_rand_hc(rng, W, True) for _ in seqs]
+    hc_br[0] = "((((" + "." * (W - 8) + "))))"
+    hc_br[1] = ")" + "." * (W - 2) + "("
+    sc = np.random.default_rng(W).integers(-150, 150, size=(len(seqs), W + 1)).astype(np.int32)
+    sc[:, 0] = 0
+    cases = {"plain": {}, "flags": {"hc": hc_flags}, "brackets": {"hc": hc_br}, "sc": {"sc": sc}, "span": {"max_span": 150}}
+    got, ref = {}, {}
+    for name, kw in cases.items():
+        got[name] = engine.fold_batch(seqs, structure=True, **kw)
+    e_only, _ = engine.fold_batch(seqs, structure=False)
+    assert np.array_equal(e_only, got["plain"][0])
+    try:
+        engine.set_engines(mfe=1)
+        for name, kw in cases.items():
+            ref[name] = engine.fold_batch(seqs, structure=True, **kw)
+    finally:
+        engine.set_engines(mfe=3)
+    for name in cases:
+        bad = np.nonzero(got[name][0] != ref[name][0])[0]
+        assert len(bad) == 0, (name, W, [(int(k), int(got[name][0][k]), int(ref[name][0][k])) for k in bad[:5]])
+        assert np.array_equal(got[name][1], ref[name][1]), (name, W)
+    for k in (0, len(seqs) - 4):
+        for name, okw in (("plain", {}), ("flags", {"hc": hc_flags[k]}), ("brackets", {"hc": hc_br[k]}),
+                          ("sc", {"sc_stack": sc[k]}), ("span", {"max_span": 150})):
+            if W > 600 and name not in ("plain", "brackets"):
+                continue
+            eo, so = oracle.mfe(seqs[k], **okw)
+            assert got[name][0][k] == eo and db_from_pt(got[name][1][k]) == so, (name, W, k)
