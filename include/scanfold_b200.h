@@ -130,7 +130,8 @@ void sfb_scan_plan_destroy(sfb_scan_plan *plan);
  * (first seen: the reference's dict insertion order) and EXACT sums of the window values z, MFE, ED: each
  * value d = k/100 enters as A = rint(d*2^20), B = (d - A*2^-20)*2^59, so sum(d) == sumA*2^-20 + sumB*2^-59
  * exactly -- order independent, which makes the multi-GPU halo merge bit exact.
- * Inputs are host arrays of the shard: pair_tbl [n_windows*W], z100 = round(z*100), mfe_dcal, ed100 = round(ED*100). */
+ * Inputs are host arrays of the shard: pair_tbl [n_windows*W], z100 = round(z*100), mfe_dcal, ed100 = round(ED*100).
+ * A window whose pair-table row is negative leaves no records (the all-N short-circuit of ScanFold.py:486-492). */
 typedef struct sfb_accum_args {
     int32_t L, W, step, first_window, n_windows;
     const int16_t *pair_tbl;

@@ -38,6 +38,7 @@ __global__ void accumulate_kernel(AccumLaunch A) {
         const int slot = w - A.first_window;
         const int pos = k - w * step;
         const int partner = A.pair_tbl[(long long)slot * W + pos];
+        if (partner < 0) continue;   // window without pair records: the all-N short-circuit (Appendix B Q10)
         const int off = partner ? (partner - 1) - pos : 0;
         const long long idx = base + off + (W - 1);
         long long a, b;

@@ -175,7 +175,7 @@ struct FoldWork {  // device scratch for one MFE launch
     DevBuf<char> scratch4;   // mfe4: C / FML / split matrices of the folds in flight
     int mode = 0;
     size_t per_cta = 0, per_warp2 = 0;
-    static bool use4(int W) { return engine() >= 3 && W >= MFE4_MIN_W; }
+    static bool use4(int W) { return engine() >= 3 && W >= MFE4_MIN_W && mfe4_supports(W); }
     void prepare(int W, int n_fold) {
         if (use4(W)) {
             const size_t per = mfe4_bytes_per_fold(W);

@@ -113,6 +113,7 @@ int mfe_grid_size(int W, int n_sm, int n_fold);
 // `scratch` holds the matrices of as many folds as fit (mfe4_bytes_per_fold each; at least one); d_hp_len = hairpin
 // initiation by loop size [W + 1] on the device; pair32 = optional 32-bit pair table (whole-sequence folds)
 void mfe4_upload_tables(const MfeTables &M);
+bool mfe4_supports(int n);
 size_t mfe4_bytes_per_fold(int n);
 void launch_mfe4(const MfeLaunch &L, const MfeTables *d_tab, const int32_t *d_hp_len, void *scratch, size_t scratch_bytes,
                  int32_t *pair32, int n_sm, cudaStream_t stream, int *n_launches);

@@ -185,6 +185,18 @@ __device__ __forceinline__ int mlstem4(const Tab4 &s, int type, int si1, int sj1
     return e + (type > 2 ? s.TerminalAU : 0) + s.MLintern;
 }
 
+template <class TB>
+__device__ __forceinline__ int mlstem4b(const TB &s, int type, int si1, int sj1) {
+    int e = 0;
+    if (si1 >= 0 && sj1 >= 0)
+        e = s.mmM[mmi(type, si1, sj1)];
+    else if (si1 >= 0)
+        e = s.d5[type * 5 + si1];
+    else if (sj1 >= 0)
+        e = s.d3[type * 5 + sj1];
+    return e + (type > 2 ? s.TerminalAU : 0) + s.MLintern;
+}
+
 __device__ __forceinline__ int extloop4(const Tab4 &s, int type, int si1, int sj1) {
     int e = 0;
     if (si1 >= 0 && sj1 >= 0)
@@ -197,30 +209,61 @@ __device__ __forceinline__ int extloop4(const Tab4 &s, int type, int si1, int sj
 }
 
 constexpr int TAB4_INTS = (int)((sizeof(Tab4) + 15) / 16 * 4);
-constexpr int O_WIN = TAB4_INTS;                  // [3][WR][WP]; doubles as the tile staging area of step 1
-constexpr int O_CB = O_WIN + 3 * WR * WP;         // [32][33]   C of the block
-constexpr int O_MB = O_CB + 32 * 33;              // [33][34]   FML: row 32 = first row of block (I+1,J), column 0 = column 32J-1
-constexpr int O_DB = O_MB + 33 * 34;              // [33][34]   split minima, same halo
-constexpr int O_MII = O_DB + 33 * 34;             // [32][33]   FML of the diagonal block (I,I)
-constexpr int O_MJJ = O_MII + 32 * 33;            // [32][33]   FML of the diagonal block (J,J)
-constexpr int O_LIST = O_MJJ + 32 * 33;           // [32] pairable cells of the step + [32] their types
-constexpr int O_END = O_LIST + 64 + 4;
-constexpr size_t SMEM4_BYTES = (size_t)O_END * 4 + 2 * 160;   // + row / column slices of the sequence
-static_assert(4 * (32 * 36 + 32 * 32) <= 3 * WR * WP, "the staging tiles of step 1 fit the window area");
 
-__global__ void __launch_bounds__(NT4, 2)
-mfe4_block_kernel(Mfe4Launch L, const MfeTables *__restrict__ T, const Tab4 *__restrict__ gtab, int delta) {
+// What the block kernel keeps in shared memory (the rarely used tables stay in the global Tab4): interior-loop candidates
+// as ONE word each -- window offset u1 * WP - u2 + 30 (12 bits), shift of the class field 10 * class (5 bits), size term
+// minus the two field biases (15 bits, signed) -- and only the separable classes; the nine table-driven shapes run apart.
+struct TabB {
+    int stack[64];
+    int mmI[200], mm1n[200], mmM[200];
+    int d5[40], d3[40];
+    int MLbase, MLclosing, MLintern, TerminalAU, bulge1, pad0, pad1, pad2;
+    int ncand_upto[32];
+    int cand[NCAND];
+};
+TabB *g_dtabB = nullptr;
+bool g_mfe4_ok = false;
+
+constexpr int TABB_INTS = (int)(sizeof(TabB) / 4);
+constexpr int TRI = 32 * 33 / 2;                  // upper triangle of a 32 x 32 block, diagonal included
+constexpr int O_MB = TABB_INTS;                   // [33][34] FML: row 32 = first row of block (I+1,J), column 0 = column 32J-1
+constexpr int O_DB = O_MB + 33 * 34;              // [33][34] split minima, same halo
+constexpr int O_WIN = O_DB + 33 * 34;             // int2 [WR][WP]: C and the packed mismatch fields of the inner-pair window;
+                                                  // from here on the area doubles as the tile staging of step 1
+constexpr int O_MII = O_WIN + 2 * WR * WP;        // [TRI] FML of the diagonal block (I,I), upper triangle
+constexpr int O_MJJ = O_MII + TRI;                // [TRI] FML of the diagonal block (J,J)
+constexpr int O_PART = O_MJJ + TRI;               // [2][2][32] partial minima of the cells of a step: separable classes / shapes
+constexpr int O_TYB = O_PART + 128;               // bytes [32][32]: pair type of every cell of the block (0 = may not pair)
+constexpr int O_SLIST = O_TYB + 256;              // bytes [63][32]: pairable cells (column b) of every step, compacted
+constexpr int O_SCNT = O_SLIST + 63 * 8;          // bytes [64]: their number
+constexpr int O_SEQ = O_SCNT + 16;                // bytes [2][160]: row / column slices of the sequence
+constexpr int O_END = O_SEQ + 80;
+constexpr size_t SMEM4_BYTES = (size_t)O_END * 4;
+static_assert(4 * (32 * 36 + 32 * 32) <= O_END - O_WIN, "the staging tiles of step 1 fit behind the accumulators");
+static_assert(4 * (SMEM4_BYTES + 1024) <= 227 * 1024, "four block tasks per SM");
+
+__device__ __forceinline__ int tri32(int r, int c) { return r * 32 - (r * (r - 1)) / 2 + (c - r); }   // c >= r
+
+constexpr int FB = 512;                           // bias of a packed 10-bit mismatch field
+__device__ __forceinline__ int pack3(int a, int b, int c) { return (a + FB) | ((b + FB) << 10) | ((c + FB) << 20); }
+
+__global__ void __launch_bounds__(NT4, 4)
+mfe4_block_kernel(Mfe4Launch L, const MfeTables *__restrict__ T, const Tab4 *__restrict__ gtab, const TabB *__restrict__ gtabB,
+                  int delta) {
     extern __shared__ __align__(16) int sm4[];
-    Tab4 &tb = *reinterpret_cast<Tab4 *>(sm4);
-    int *win = sm4 + O_WIN, *Cb = sm4 + O_CB, *Mb = sm4 + O_MB, *Db = sm4 + O_DB, *Mii = sm4 + O_MII, *Mjj = sm4 + O_MJJ;
-    int *list = sm4 + O_LIST;
-    unsigned char *sR = reinterpret_cast<unsigned char *>(sm4 + O_END);   // codes of positions 32I-1 .. 32I+78
-    unsigned char *sC = sR + 160;                                        // codes of positions 32J-33 .. 32J+46
+    TabB &tb = *reinterpret_cast<TabB *>(sm4);
+    int *Mb = sm4 + O_MB, *Db = sm4 + O_DB, *Mii = sm4 + O_MII, *Mjj = sm4 + O_MJJ, *part = sm4 + O_PART;
+    int2 *win = reinterpret_cast<int2 *>(sm4 + O_WIN);
+    unsigned char *tyb = reinterpret_cast<unsigned char *>(sm4 + O_TYB);
+    unsigned char *slist = reinterpret_cast<unsigned char *>(sm4 + O_SLIST);
+    unsigned char *scnt = reinterpret_cast<unsigned char *>(sm4 + O_SCNT);
+    unsigned char *sR = reinterpret_cast<unsigned char *>(sm4 + O_SEQ);   // codes of positions 32I-1 .. 32I+158
+    unsigned char *sC = sR + 160;                                        // codes of positions 32J-33 .. 32J+126
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const unsigned full = 0xffffffffu;
     {
-        const int *src = reinterpret_cast<const int *>(gtab);
-        for (int k = tid; k < (int)(sizeof(Tab4) / 4); k += NT4) sm4[k] = src[k];
+        const int *src = reinterpret_cast<const int *>(gtabB);
+        for (int k = tid; k < TABB_INTS; k += NT4) sm4[k] = src[k];
     }
     const int n = L.n, NP = L.NP;
     const int per_fold = L.NB - delta;   // block tasks of this diagonal per fold
@@ -246,7 +289,6 @@ mfe4_block_kernel(Mfe4Launch L, const MfeTables *__restrict__ T, const Tab4 *__r
         for (int k = tid; k < 33 * 34; k += NT4) {
             Db[k] = INF;
             Mb[k] = INF;
-            if (k < 32 * 33) Cb[k] = INF;
         }
         for (int k = tid; k < 160; k += NT4) {
             const int pr = i0 - 1 + k, pc = j0 - 33 + k;
@@ -261,7 +303,7 @@ mfe4_block_kernel(Mfe4Launch L, const MfeTables *__restrict__ T, const Tab4 *__r
         if (delta >= 2) {
             const int wp = warp >> 1, half = warp & 1;
             const int rb = 16 * half + 4 * (lane >> 3), cb = 4 * (lane & 7);
-            int *At = win + wp * (32 * 36 + 32 * 32), *Bs = At + 32 * 36;
+            int *At = sm4 + O_WIN + wp * (32 * 36 + 32 * 32), *Bs = At + 32 * 36;
             int acc[4][4];
 #pragma unroll
             for (int a = 0; a < 4; a++)
@@ -303,7 +345,7 @@ mfe4_block_kernel(Mfe4Launch L, const MfeTables *__restrict__ T, const Tab4 *__r
             __syncthreads();
         }
 
-        // ---- 2. halos, diagonal blocks, inner-pair window with the derived copies
+        // ---- 2. halos, diagonal blocks, pair types and step lists, inner-pair window
         for (int k = tid; k < 34; k += NT4) {   // row 32 (first row of block (I+1, J)), columns 32J-1 .. 32J+32
             Mb[32 * 34 + k] = ldM(gM, i0 + 32, j0 - 1 + k);
             Db[32 * 34 + k] = ldM(gD, i0 + 32, j0 - 1 + k);
@@ -315,114 +357,94 @@ mfe4_block_kernel(Mfe4Launch L, const MfeTables *__restrict__ T, const Tab4 *__r
         if (delta >= 1)
             for (int k = tid; k < 32 * 32; k += NT4) {
                 const int a = k >> 5, c = k & 31;
-                Mii[a * 33 + c] = ldM(gM, i0 + a, i0 + c);
-                Mjj[a * 33 + c] = ldM(gM, j0 + a, j0 + c);
+                if (c >= a) {
+                    Mii[tri32(a, c)] = ldM(gM, i0 + a, i0 + c);
+                    Mjj[tri32(a, c)] = ldM(gM, j0 + a, j0 + c);
+                }
             }
+        for (int k = tid; k < 32 * 32; k += NT4) {
+            const int a = k >> 5, b = k & 31;
+            tyb[k] = (unsigned char)pm.type(i0 + a, j0 + b);
+        }
+        for (int k = tid; k < 128; k += NT4) part[k] = INF;
         {
             const int r0 = i0 + 1, c0 = j0 - 31;
+            const int none = pack3(0, 0, 0);
             for (int k = tid; k < WR * WR; k += NT4) {
                 const int wr = k / WR, wc = k - wr * WR;
                 const int p = r0 + wr, q = c0 + wc;
-                int vg = INF, v1 = INF, vb = INF;
+                int2 e = make_int2(INF, none);
                 const bool own = wr <= 30 && wc >= 31;   // cells of this block: filled in step 3
                 if (!own && q >= 1 && q < n - 1 && p < n && q - p > TURN) {
                     const int c = __ldcg(gC + (size_t)p * NP + q);
                     if (c < INF) {
                         const int t2 = rtype_of(pair_type(SR(p), SCc(q)));
                         const int m2 = mmi(t2, SCc(q + 1), SR(p - 1));
-                        vg = c + tb.mmI[m2];
-                        v1 = c + tb.mm1n[m2];
-                        vb = c + (t2 > 2 ? tb.TerminalAU : 0);
+                        e = make_int2(c, pack3(tb.mmI[m2], tb.mm1n[m2], t2 > 2 ? tb.TerminalAU : 0));
                     }
                 }
-                win[wr * WP + wc] = vg;
-                win[WR * WP + wr * WP + wc] = v1;
-                win[2 * WR * WP + wr * WP + wc] = vb;
+                win[wr * WP + wc] = e;
             }
         }
         __syncthreads();
-
-        // ---- 3. the 63 anti-diagonals of the block: cell (a, b) = (i0 + a, j0 + b), step s = 31 - a + b
-        for (int s = delta == 0 ? 31 + TURN + 1 : 0; s < 63; s++) {   // diagonal blocks: j - i <= TURN before that
+        const int s_begin = delta == 0 ? 31 + TURN + 1 : 0;   // diagonal blocks: j - i <= TURN before that
+        for (int s = s_begin + warp; s < 63; s += NT4 / 32) {   // compacted list of the pairable cells of every step
             const int blo = max(0, s - 31), nc = min(s, 62 - s) + 1;
-            if (warp == 0) {   // pair permission of the cells of this step, compacted
-                const int b = blo + lane, a = 31 - s + b;
-                const int i = i0 + a, j = j0 + b;
-                int t = 0;
-                if (lane < nc && j < n) t = pm.type(i, j);
-                const unsigned m = __ballot_sync(full, t != 0);
-                if (t) {
-                    const int pos = __popc(m & ((1u << lane) - 1));
-                    list[pos] = b;
-                    list[32 + pos] = t;
-                }
-                if (lane == 0) list[64] = __popc(m);
-                if (lane < nc && !t) Cb[a * 33 + b] = INF;
-            }
-            __syncthreads();
-            const int npair = list[64];
-            for (int c = warp; c < npair; c += NT4 / 32) {
-                const int b = list[c], type = list[32 + c], a = 31 - s + b;
-                const int i = i0 + a, j = j0 + b, d = j - i;
-                const int si1 = SR(i + 1), sj1 = SCc(j - 1);
-                const int mi = mmi(type, si1, sj1);
-                const int outer0 = tb.mmI[mi], outer1 = tb.mm1n[mi], outer2 = type > 2 ? tb.TerminalAU : 0;
-                const int umax = min(MAXLOOP, d - 2 - (TURN + 1));
-                const int ncand = umax >= 0 ? tb.ncand_upto[umax] : 0;
-                int acc = INF;
-                for (int ci = lane; ci < ncand; ci += 32) {
-                    const int cd = tb.cand_code[ci];
-                    const int u1 = cd & 31, u2 = (cd >> 5) & 31, cls = cd >> 10;
-                    const int wr = a + u1, wc = b + 30 - u2;   // window coordinates of the inner pair (i+1+u1, j-1-u2)
-                    int v;
-                    if (cls != K_TABLE) {
-                        const int outer = cls == K_GENERIC ? outer0 : (cls == K_1N ? outer1 : outer2);
-                        v = win[cls * WR * WP + wr * WP + wc] + tb.cand_size[ci] + outer;
-                    } else {
-                        v = INF;
-                        const int vb = win[2 * WR * WP + wr * WP + wc];
-                        if (vb < INF) {
-                            const int p = i + 1 + u1, q = j - 1 - u2;
-                            const int t2 = rtype_of(pair_type(SR(p), SCc(q)));
-                            const int cpq = vb - (t2 > 2 ? tb.TerminalAU : 0);
-                            v = cpq + intloop4(tb, T, u1, u2, type, t2, si1, sj1, SR(p - 1), SCc(q + 1));
-                            if (u1 == 0 && u2 == 0 && scf) v += scf[i + 1] + scf[p + 1] + scf[q + 1] + scf[j + 1];
-                        }
-                    }
-                    acc = min(acc, v);
-                }
-                acc = __reduce_min_sync(full, acc);
-                if (lane == 0) {
-                    int e = min(acc, hairpin4(tb, T, L.hp_len, S, i, j, type));
-                    if (d >= 2 + TURN + 1 + 2) {   // multiloop closed by (i,j): split minimum of cell (i+1, j-1)
-                        const int dm = Db[(a + 1) * 34 + b];
-                        if (dm < INF) e = min(e, dm + mlstem4(tb, rtype_of(type), sj1, si1) + tb.MLclosing);
-                    }
-                    Cb[a * 33 + b] = e;
-                    if (a >= 1 && b <= 30 && i > 0 && j < n - 1) {   // (i,j) as the inner pair of later cells of this block
-                        const int t2 = rtype_of(type);
-                        const int m2 = mmi(t2, SCc(j + 1), SR(i - 1));
-                        const int o = (a - 1) * WP + b + 31;
-                        win[o] = e + tb.mmI[m2];
-                        win[WR * WP + o] = e + tb.mm1n[m2];
-                        win[2 * WR * WP + o] = e + (t2 > 2 ? tb.TerminalAU : 0);
-                    }
-                }
-            }
-            __syncthreads();
-            // FML of every cell of the step: 8 lanes share the splits inside the two diagonal blocks
-            {
+            const int b = blo + lane, a = 31 - s + b;
+            const int t = lane < nc ? (int)tyb[a * 32 + b] : 0;
+            const unsigned m = __ballot_sync(full, t != 0);
+            if (t) slist[s * 32 + __popc(m & ((1u << lane) - 1))] = (unsigned char)b;
+            if (lane == 0) scnt[s] = (unsigned char)__popc(m);
+        }
+        __syncthreads();
+
+        // ---- 3. the 63 anti-diagonals of the block, cell (a, b) = (i0 + a, j0 + b) on step s = 31 - a + b, software
+        // pipelined with ONE barrier per step.  Iteration t runs, side by side,
+        //   G  the separable interior loops of the pairable cells of step t, one warp per cell (warps 2..7)
+        //   H  their nine table-driven shapes and the hairpin, lane = cell (warps 0 and 1 share the shapes)
+        //   F  for the cells of step t-1: C from the partial minima of iteration t-1 plus the multiloop closing term, the
+        //      window entry, then the splits inside the two diagonal blocks and FML (8 lanes per cell, every warp)
+        // C(t) only reads cells of steps <= t-2 and the split minima of step t-2; FML(t-1) reads FML of steps <= t-2.
+        for (int t = s_begin; t <= 63; t++) {
+            // ---- F: step t - 1
+            if (t > s_begin) {
+                const int s = t - 1;
+                const int blo = max(0, s - 31), nc = min(s, 62 - s) + 1;
                 const int cell = tid >> 3, g = tid & 7;
-                int dec = INF, a = 0, b = 0;
                 const bool active = cell < nc && j0 + blo + cell < n;
+                int dec = INF, a = 0, b = 0, cij = INF;
                 if (active) {
                     b = blo + cell;
                     a = 31 - s + b;
+                    if (g == 0) {
+                        const int type = tyb[a * 32 + b];
+                        const int i = i0 + a, j = j0 + b;
+                        if (type) {
+                            int e = min(part[(s & 1) * 64 + b], part[(s & 1) * 64 + 32 + b]);
+                            part[(s & 1) * 64 + b] = INF;        // both are written again two iterations on
+                            part[(s & 1) * 64 + 32 + b] = INF;
+                            if (j - i >= 2 + TURN + 1 + 2) {   // multiloop closed by (i,j): split minimum of cell (i+1, j-1)
+                                const int dm = Db[(a + 1) * 34 + b];
+                                if (dm < INF)
+                                    e = min(e, dm + mlstem4b(tb, rtype_of(type), SCc(j - 1), SR(i + 1)) + tb.MLclosing);
+                            }
+                            cij = e;
+                            if (a >= 1 && b <= 30 && i > 0 && j < n - 1) {   // inner pair of later cells of this block
+                                const int t2 = rtype_of(type);
+                                const int m2 = mmi(t2, SCc(j + 1), SR(i - 1));
+                                win[(a - 1) * WP + b + 31] = make_int2(e, pack3(tb.mmI[m2], tb.mm1n[m2], t2 > 2 ? tb.TerminalAU : 0));
+                            }
+                        }
+                        if (j - i > TURN) {
+                            gC[(size_t)i * NP + j] = cij;
+                            gC[(size_t)j * NP + i] = cij;   // transposed copy for the exterior loop
+                        }
+                    }
                     if (delta == 0) {   // m = i0 + c, a < c <= b: FML[i][m-1] + FML[m][j], both inside this block
                         for (int c = a + 1 + g; c <= b; c += 8) dec = min(dec, Mb[a * 34 + c] + Mb[c * 34 + b + 1]);
                     } else {
-                        for (int c = a + 1 + g; c < 32; c += 8) dec = min(dec, Mii[a * 33 + c - 1] + Mb[c * 34 + b + 1]);
-                        for (int c = g; c <= b; c += 8) dec = min(dec, Mb[a * 34 + c] + Mjj[c * 33 + b]);
+                        for (int c = a + 1 + g; c < 32; c += 8) dec = min(dec, Mii[tri32(a, c - 1)] + Mb[c * 34 + b + 1]);
+                        for (int c = g; c <= b; c += 8) dec = min(dec, Mb[a * 34 + c] + Mjj[tri32(c, b)]);
                     }
                 }
                 dec = min(dec, __shfl_xor_sync(full, dec, 1));
@@ -438,29 +460,76 @@ mfe4_block_kernel(Mfe4Launch L, const MfeTables *__restrict__ T, const Tab4 *__r
                         if (x < INF) m = min(m, x + tb.MLbase);
                         if (y < INF) m = min(m, y + tb.MLbase);
                     }
-                    const int cij = j - i > TURN ? Cb[a * 33 + b] : INF;
                     if (cij < INF)
-                        m = min(m, cij + mlstem4(tb, pair_type(SR(i), SCc(j)), i > 0 ? SR(i - 1) : -1, j < n - 1 ? SCc(j + 1) : -1));
+                        m = min(m, cij + mlstem4b(tb, pair_type(SR(i), SCc(j)), i > 0 ? SR(i - 1) : -1, j < n - 1 ? SCc(j + 1) : -1));
+                    if (j - i <= TURN) m = INF;
                     Db[a * 34 + b + 1] = dec;
-                    Mb[a * 34 + b + 1] = j - i > TURN ? m : INF;
+                    Mb[a * 34 + b + 1] = m;
+                    if (j - i > TURN) {
+                        gM[(size_t)i * NP + j] = m;
+                        gD[(size_t)i * NP + j] = dec;
+                    }
+                }
+            }
+            if (t < 63) {
+                const int npair = scnt[t];
+                const unsigned char *lst = slist + t * 32;
+                int *pG = part + (t & 1) * 64, *pS = pG + 32;
+                if (warp >= 2) {
+                    // ---- G: separable classes, one warp per cell, lane = candidate
+                    for (int c = warp - 2; c < npair; c += NT4 / 32 - 2) {
+                        const int b = lst[c], a = 31 - t + b;
+                        const int type = tyb[a * 32 + b];
+                        const int i = i0 + a, j = j0 + b, d = j - i;
+                        const int mi = mmi(type, SR(i + 1), SCc(j - 1));
+                        const int opk = pack3(tb.mmI[mi], tb.mm1n[mi], type > 2 ? tb.TerminalAU : 0);
+                        const int umax = min(MAXLOOP, d - 2 - (TURN + 1));
+                        const int ncand = umax >= 0 ? tb.ncand_upto[umax] : 0;
+                        const int2 *base = win + a * WP + b;
+                        int acc = INF;
+#pragma unroll 4
+                        for (int ci = lane; ci < ncand; ci += 32) {
+                            const int cd = tb.cand[ci];
+                            const int sh = (cd >> 12) & 31;
+                            const int2 w = base[cd & 4095];
+                            acc = min(acc, w.x + ((w.y >> sh) & 1023) + ((opk >> sh) & 1023) + (cd >> 17));
+                        }
+                        acc = __reduce_min_sync(full, acc);
+                        if (lane == 0) pG[b] = min(acc, INF);
+                    }
+                } else if (lane < npair) {
+                    // ---- H: the nine table-driven shapes (warp 0: stack, bulges of one, 1x1; warp 1: 1x2, 2x1, 2x2, 2x3,
+                    // 3x2) and the hairpin, lane = cell; the loads are unconditional so that they issue together
+                    const int b = lst[lane], a = 31 - t + b;
+                    const int type = tyb[a * 32 + b];
+                    const int i = i0 + a, j = j0 + b;
+                    const int si1 = SR(i + 1), sj1 = SCc(j - 1);
+                    int best = INF;
+                    auto shape = [&](int u1, int u2) {
+                        const int2 w = win[(a + u1) * WP + b + 30 - u2];
+                        const int p = i + 1 + u1, q = j - 1 - u2;
+                        const int t2 = rtype_of(pair_type(SR(p), SCc(q)));
+                        int e = intloop4(*gtab, T, u1, u2, type, t2, si1, sj1, SR(p - 1), SCc(q + 1));
+                        if (u1 == 0 && u2 == 0 && scf) e += scf[i + 1] + scf[p + 1] + scf[q + 1] + scf[j + 1];
+                        if (w.x < INF) best = min(best, w.x + e);
+                    };
+                    if (warp == 0) {
+                        shape(0, 0);
+                        shape(0, 1);
+                        shape(1, 0);
+                        shape(1, 1);
+                        best = min(best, hairpin4(*gtab, T, L.hp_len, S, i, j, type));
+                    } else {
+                        shape(1, 2);
+                        shape(2, 1);
+                        shape(2, 2);
+                        shape(2, 3);
+                        shape(3, 2);
+                    }
+                    atomicMin(&pS[b], best);
                 }
             }
             __syncthreads();
-        }
-        // ---- write the block back (C also transposed into the lower triangle for the exterior loop)
-        for (int k = tid; k < 32 * 32; k += NT4) {
-            const int a = k >> 5, b = k & 31;
-            const int i = i0 + a, j = j0 + b;
-            if (j < n && j - i > TURN) {
-                gC[(size_t)i * NP + j] = Cb[a * 33 + b];
-                gM[(size_t)i * NP + j] = Mb[a * 34 + b + 1];
-                gD[(size_t)i * NP + j] = Db[a * 34 + b + 1];
-            }
-        }
-        for (int k = tid; k < 32 * 32; k += NT4) {
-            const int b = k >> 5, a = k & 31;
-            const int i = i0 + a, j = j0 + b;
-            if (j < n && j - i > TURN) gC[(size_t)j * NP + i] = Cb[a * 33 + b];
         }
     }
 }
@@ -717,7 +786,48 @@ void mfe4_upload_tables(const MfeTables &M) {
     h.ncand_upto[31] = nc;
     if (!g_dtab4) cudaMalloc(&g_dtab4, sizeof(Tab4));
     cudaMemcpy(g_dtab4, &h, sizeof(Tab4), cudaMemcpyHostToDevice);
+
+    // the block kernel's shared-memory copy: packed candidates of the separable classes only
+    static TabB hb;
+    bool ok = true;
+    auto fits10 = [&](int v) { return v >= -FB && v < FB; };
+    for (int k = 0; k < 64; k++) hb.stack[k] = h.stack[k];
+    for (int k = 0; k < 200; k++) {
+        hb.mmI[k] = h.mmI[k];
+        hb.mm1n[k] = h.mm1n[k];
+        hb.mmM[k] = h.mmM[k];
+        ok = ok && fits10(h.mmI[k]) && fits10(h.mm1n[k]);
+    }
+    for (int k = 0; k < 40; k++) {
+        hb.d5[k] = h.d5[k];
+        hb.d3[k] = h.d3[k];
+    }
+    hb.MLbase = M.MLbase;
+    hb.MLclosing = M.MLclosing;
+    hb.MLintern = M.MLintern;
+    hb.TerminalAU = M.TerminalAU;
+    hb.bulge1 = M.bulge[1];
+    ok = ok && fits10(M.TerminalAU);
+    int ng = 0;
+    for (int u = 0; u <= MAXLOOP; u++) {
+        for (int u1 = 0; u1 <= u; u1++) {
+            const int k = (u ? h.ncand_upto[u - 1] : 0) + u1;
+            const int cls = h.cand_code[k] >> 10, u2 = u - u1;
+            if (cls == K_TABLE) continue;
+            const int size = h.cand_size[k] - 2 * FB;        // the two 10-bit fields carry a bias of FB each
+            ok = ok && size >= -16384 && size < 16384;
+            hb.cand[ng++] = (int)(((unsigned)size << 17) | ((unsigned)(10 * cls) << 12) | (unsigned)(u1 * WP - u2 + 30));
+        }
+        hb.ncand_upto[u] = ng;
+    }
+    hb.ncand_upto[31] = ng;
+    for (int k = ng; k < NCAND; k++) hb.cand[k] = 0;
+    g_mfe4_ok = ok;
+    if (!g_dtabB) cudaMalloc(&g_dtabB, sizeof(TabB));
+    cudaMemcpy(g_dtabB, &hb, sizeof(TabB), cudaMemcpyHostToDevice);
 }
+
+bool mfe4_supports(int n) { return g_mfe4_ok && n >= 2 * BS; }
 
 size_t mfe4_pitch(int n) { return (size_t)((n + BS - 1) / BS) * BS; }
 
@@ -773,8 +883,8 @@ void launch_mfe4(const MfeLaunch &L, const MfeTables *d_tab, const int32_t *d_hp
         }
         for (int delta = 0; delta < A.NB; delta++) {
             const long long tasks = (long long)nf * (A.NB - delta);
-            const int grid = (int)std::min<long long>(tasks, (long long)n_sm * 2 * 4);
-            mfe4_block_kernel<<<grid, NT4, SMEM4_BYTES, stream>>>(A, d_tab, g_dtab4, delta);
+            const int grid = (int)std::min<long long>(tasks, (long long)n_sm * 4 * 4);
+            mfe4_block_kernel<<<grid, NT4, SMEM4_BYTES, stream>>>(A, d_tab, g_dtab4, g_dtabB, delta);
             if (n_launches) (*n_launches)++;
         }
         const size_t smx = (size_t)TAB4_INTS * 4 + 32 + (size_t)(n + 2) * 4;

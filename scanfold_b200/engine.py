@@ -332,10 +332,13 @@ class Accumulator:
     export()/merge() move halo rows through caller-provided DEVICE buffers (multi-GPU exchange);
     compact() returns the per-nucleotide partner lists as numpy arrays."""
 
-    def __init__(self, L, W, step, first_window, pair_tbl, z100, mfe_dcal, ed100):
+    def __init__(self, L, W, step, first_window, pair_tbl, z100, mfe_dcal, ed100, skip=None):
         ensure_init()
         self._lib = load_library()
         pt = np.ascontiguousarray(pair_tbl, dtype=np.int16)
+        if skip is not None and np.any(skip):          # windows that leave no pair records (all-N, Appendix B Q10)
+            pt = pt.copy()
+            pt[np.asarray(skip, dtype=bool)] = -1
         z = np.ascontiguousarray(z100, dtype=np.int32)
         m = np.ascontiguousarray(mfe_dcal, dtype=np.int32)
         e = np.ascontiguousarray(ed100, dtype=np.int32)

@@ -24,23 +24,29 @@ class PartnerTable:
     """Compact per-nucleotide partner statistics (CSR over covered nucleotides 1..n_nt, 1-based coordinates).
     Within a nucleotide the entries are in first-seen order (ascending first window index)."""
 
-    def __init__(self, nt_ptr, partner, count, first_seen, sums):
+    def __init__(self, nt_ptr, partner, count, first_seen, sums, coord=None):
         self.nt_ptr = np.asarray(nt_ptr, dtype=np.int64)     # [n_nt + 1]
         self.partner = np.asarray(partner, dtype=np.int64)   # [M] partner coordinate (== own coordinate: unpaired)
         self.count = np.asarray(count, dtype=np.int64)       # [M] windows holding this pair
         self.first_seen = np.asarray(first_seen, dtype=np.int64)
         self.sums = np.asarray(sums, dtype=np.int64)         # [6, M]: zA zB mfeA mfeB edA edB
         self.n_nt = len(self.nt_ptr) - 1
+        # 1-based coordinate of every row; rows are the keys of the reference's bp_dict in ascending order.  A nucleotide
+        # no window left a record for (only all-N windows cover it, Appendix B Q10) has no row.
+        self.coord = np.arange(1, self.n_nt + 1, dtype=np.int64) if coord is None else np.asarray(coord, dtype=np.int64)
 
 
-def table_from_compact(nparts, partner, count, first_seen, sums):
-    """sfb_accumulate_fetch arrays (entries in column order) -> PartnerTable in first-seen order"""
+def table_from_compact(nparts, partner, count, first_seen, sums, nt0=0):
+    """sfb_accumulate_fetch arrays (entries in column order) of the nucleotides nt0, nt0+1, .. (0-based) -> PartnerTable
+    in first-seen order; nucleotides without any record get no row"""
     nparts = np.asarray(nparts, dtype=np.int64)
-    ptr = np.concatenate([[0], np.cumsum(nparts)])
     own = np.repeat(np.arange(len(nparts)), nparts)
     order = np.lexsort((np.asarray(first_seen), own))
+    covered = nparts > 0
+    ptr = np.concatenate([[0], np.cumsum(nparts[covered])])
+    coord = nt0 + 1 + np.nonzero(covered)[0]
     return PartnerTable(ptr, np.asarray(partner)[order], np.asarray(count)[order], np.asarray(first_seen)[order],
-                        np.asarray(sums)[:, order])
+                        np.asarray(sums)[:, order], coord)
 
 
 def concat_tables(tables):
@@ -52,7 +58,7 @@ def concat_tables(tables):
         base += t.nt_ptr[-1]
     return PartnerTable(np.concatenate(ptr), np.concatenate([t.partner for t in tables]),
                         np.concatenate([t.count for t in tables]), np.concatenate([t.first_seen for t in tables]),
-                        np.concatenate([t.sums for t in tables], axis=1))
+                        np.concatenate([t.sums for t in tables], axis=1), np.concatenate([t.coord for t in tables]))
 
 
 def split_exact(values100):
@@ -91,19 +97,21 @@ class NtResult:
     pass
 
 
-def aggregate(table, seq, log_total=None, sirna_log=None):
-    """ScanFold.py:1051-1260.  Returns an object with, per covered nucleotide k (arrays of length n_nt):
+def aggregate(table, seq, log_total=None, sirna_log=None, by_ed=False):
+    """ScanFold.py:1051-1260.  Returns an object with, per covered nucleotide k (arrays of length n_nt, coordinates in
+    .coord):
        part        best partner coordinate (== k: unpaired)           best_coordinate
        cov_z       sum z / #total windows of the best partner         best_total_window_mean_bps[k].zscore
+                   (--by_ed: sum ED / #total windows, ScanFold.py:1190-1215,1251-1255)
        mean_z      mean z over the windows holding the best pair      best_bps[k].zscore
        mean_mfe, mean_ed                                              .mfe / .ed of both dictionaries
     and writes the .ScanFold.log / .ntPairCounts.log text when file objects are given."""
     n_nt = table.n_nt
     ptr = table.nt_ptr
     M = len(table.partner)
-    own = np.repeat(np.arange(1, n_nt + 1, dtype=np.int64), np.diff(ptr))
+    own = np.repeat(table.coord, np.diff(ptr))
     cnt = table.count
-    sum_z = _exact_sum(table.sums[0], table.sums[1])
+    sum_z = _exact_sum(table.sums[4], table.sums[5]) if by_ed else _exact_sum(table.sums[0], table.sums[1])
     mean_z = _exact_mean(table.sums[0], table.sums[1], cnt)
     mean_mfe = _exact_mean(table.sums[2], table.sums[3], cnt)
     mean_ed = _exact_mean(table.sums[4], table.sums[5], cnt)
@@ -118,10 +126,11 @@ def aggregate(table, seq, log_total=None, sirna_log=None):
 
     if log_total is not None or sirna_log is not None:
         _write_logs(table, seq, own, cnt, sum_z, mean_z, mean_mfe, mean_ed, cov_z, total_windows, num_bp,
-                    log_total, sirna_log)
+                    log_total, sirna_log, by_ed)
 
     res = NtResult()
     res.n_nt = n_nt
+    res.coord = table.coord
     res.part = table.partner[best]
     res.cov_z = cov_z[best]
     res.mean_z = mean_z[best]
@@ -137,16 +146,19 @@ def _r2(x):
 
 
 def _write_logs(table, seq, own, cnt, sum_z, mean_z, mean_mfe, mean_ed, cov_z, total_windows, num_bp, log_total,
-                sirna_log):
-    """log lines of ScanFold.py:1150-1184 (not --by_ed)"""
+                sirna_log, by_ed=False):
+    """log lines of ScanFold.py:1150-1184; --by_ed: :1155-1159,1190-1212 (sum_z / cov_z then hold the ED sums; the column
+    order avgMFE, avgZ, avgED is the same in both modes)"""
     ptr = table.nt_ptr
     partner = table.partner
     out = []
     sirna = []
+    head = "SumED\tSumED/#TotalWindows" if by_ed else "SumZ\tSumZ/#TotalWindows"
+    coord = table.coord.tolist()
     for k0 in range(table.n_nt):
-        k = k0 + 1
-        nuc = seq[k0]
-        out.append("\ni-nuc\tBP(j)\tNuc\t#BP_Win\tavgMFE\tavgZ\tavgED\tSumZ\tSumZ/#TotalWindows\tBPs= %d\n" % num_bp[k0])
+        k = coord[k0]
+        nuc = seq[k - 1]
+        out.append("\ni-nuc\tBP(j)\tNuc\t#BP_Win\tavgMFE\tavgZ\tavgED\t%s\tBPs= %d\n" % (head, num_bp[k0]))
         out.append("nt-%d\t-\t%s\t%d\t-\t-\t-\t-\t-\n" % (k, nuc, total_windows[k0]))
         sirna.append("%d\t%s\t%d\t%d\n" % (k, nuc, total_windows[k0], num_bp[k0]))
         for m in range(ptr[k0], ptr[k0 + 1]):
@@ -160,6 +172,10 @@ def _write_logs(table, seq, own, cnt, sum_z, mean_z, mean_mfe, mean_ed, cov_z, t
         sirna_log.write("".join(sirna))
 
 
+FINAL_PARTNERS_HEADER = ("i\tbp(i)\tbp(j)\tavgMFE\tavgZ\tavgED\t*Indicates most favorable bp has competition; bp(j) has "
+                         "more favorable partner or is more likely to be unpaired\n")
+
+
 class FinalPartners:
     """final_partners of ScanFold.py:1404-1442, one entry per covered nucleotide k (index k-1):
        i, j     icoordinate / jcoordinate of the stored NucPair (i == j: unpaired)
@@ -171,19 +187,24 @@ class FinalPartners:
 def compete(res, seq, log_win=None):
     """ScanFold.py:1273-1442 with competition == 1.  `res` comes from aggregate()."""
     n = res.n_nt
+    coord = res.coord
     part = res.part
     z = res.cov_z
+    top = int(max(coord.max(), part.max())) + 2 if n else 2
+    pos = np.full(top, -1, dtype=np.int64)          # coordinate -> row
+    pos[coord] = np.arange(n)
     # inverse index: inv[c] = ascending nucleotides whose best partner is c   (competing_pairs scans)
     order = np.argsort(part, kind="stable")
     sorted_part = part[order]
-    starts = np.searchsorted(sorted_part, np.arange(1, n + 2))
-    order1 = order + 1
+    keys_of = coord[order]
 
     def comp(c):
         """entries of best_total_window_mean_bps touching coordinate c, in dictionary (ascending) order
         (competing_pairs, ScanFoldFunctions.py:343-357)"""
-        lst = order1[starts[c - 1]:starts[c]].tolist()
-        if part[c - 1] != c:              # entry c itself (icoordinate == c) unless already listed
+        lo, hi = np.searchsorted(sorted_part, (c, c + 1))
+        lst = keys_of[lo:hi].tolist()
+        r = pos[c] if c < top else -1
+        if r >= 0 and part[r] != c:         # entry c itself (icoordinate == c) unless already listed
             bisect.insort(lst, c)
         return lst
 
@@ -196,6 +217,7 @@ def compete(res, seq, log_win=None):
         return r
 
     fin = FinalPartners()
+    fin.coord = coord
     fin.i = np.zeros(n, dtype=np.int64)
     fin.j = np.zeros(n, dtype=np.int64)
     fin.z = np.zeros(n)
@@ -203,34 +225,37 @@ def compete(res, seq, log_win=None):
     fin.ed = np.zeros(n)
     zl = z.tolist()
     partl = part.tolist()
+    posl = pos.tolist()
+    coordl = coord.tolist()
     lines = []
     if log_win is not None:
-        lines.append("i\tbp(i)\tbp(j)\tavgMFE\tavgZ\tavgED\t*Indicates most favorable bp has competition; bp(j) has "
-                     "more favorable partner or is more likely to be unpaired\n")
-    for k in range(1, n + 1):
-        i, j = k, partl[k - 1]
+        lines.append(FINAL_PARTNERS_HEADER)
+    for r0 in range(n):
+        k = coordl[r0]
+        i, j = k, partl[r0]
         best_m, best_z = -1, None
         for c in (i, j):
             for m in comp_c(c):
-                for cc in (partl[m - 1], m):
+                for cc in (partl[posl[m]], m):
                     for mm in comp_c(cc):
-                        zz = zl[mm - 1]
+                        zz = zl[posl[mm]]
                         if best_z is None or zz < best_z:
                             best_m, best_z = mm, zz
-        wi, wj = best_m, partl[best_m - 1]
+        wi, wj = best_m, partl[posl[best_m]]
         if k != wi and k != wj:
             if log_win is not None:
-                lines.append("nt-%d*:\t%d\t%d\t%s\t%s\t%s\n" % (k, i, j, _r2(res.mean_mfe[k - 1]), _r2(res.mean_z[k - 1]),
-                                                             _r2(res.mean_ed[k - 1])))
-            fin.i[k - 1] = fin.j[k - 1] = k
+                lines.append("nt-%d*:\t%d\t%d\t%s\t%s\t%s\n" % (k, i, j, _r2(res.mean_mfe[r0]), _r2(res.mean_z[r0]),
+                                                             _r2(res.mean_ed[r0])))
+            fin.i[r0] = fin.j[r0] = k
         else:
             if log_win is not None:
-                lines.append("nt-%d:\t%d\t%d\t%s\t%s\t%s\n" % (k, wi, wj, _r2(res.mean_mfe[k - 1]), _r2(res.mean_z[k - 1]),
-                                                            _r2(res.mean_ed[k - 1])))
-            fin.i[k - 1], fin.j[k - 1] = wi, wj
-        fin.z[k - 1] = res.mean_z[wi - 1]
-        fin.mfe[k - 1] = res.mean_mfe[wi - 1]
-        fin.ed[k - 1] = res.mean_ed[wi - 1]
+                lines.append("nt-%d:\t%d\t%d\t%s\t%s\t%s\n" % (k, wi, wj, _r2(res.mean_mfe[r0]), _r2(res.mean_z[r0]),
+                                                            _r2(res.mean_ed[r0])))
+            fin.i[r0], fin.j[r0] = wi, wj
+        w = posl[wi]
+        fin.z[r0] = res.mean_z[w]
+        fin.mfe[r0] = res.mean_mfe[w]
+        fin.ed[r0] = res.mean_ed[w]
     if log_win is not None:
         log_win.write("".join(lines))
     return fin

@@ -24,9 +24,10 @@ def partner_table_gpu(L, table):
     """ScanFold.py:564-677 + :1051-1139 on the device -> foldstep.PartnerTable"""
     from . import engine
     z100, mfe100, ed100 = fold_inputs(table)
-    acc = engine.Accumulator(L, table.W, table.step, table.first_window, table.pair_tbl, z100, mfe100, ed100)
+    acc = engine.Accumulator(L, table.W, table.step, table.first_window, table.pair_tbl, z100, mfe100, ed100,
+                             skip=getattr(table, "alln", None))
     try:
-        return foldstep.table_from_compact(*acc.compact())
+        return foldstep.table_from_compact(*acc.compact(), nt0=acc.nt0)
     finally:
         acc.close()
 
@@ -36,11 +37,20 @@ class RunNames:
 
     def __init__(self, read_name, record_name, W, step, r, shuffle_type, name="UserInput", out6="./IGV_BP_Track",
                  final_partners_wig="./IGV_BP_Zavg_metrics", dbn1="Zavg_NoFilter", dbn2="Zavg_-1_pairs",
-                 dbn3="Zavg_-2_pairs", dbn4="AllDBN.txt"):
+                 dbn3="Zavg_-2_pairs", dbn4="AllDBN.txt", out1="./ScanFold.NoFilter", out2="./ScanFold.-1Filter",
+                 out3="./ScanFold.-2Filter", dbn_refold="AllDBN-global_refold.txt"):
+        self.out1, self.out2, self.out3, self.dbn_refold = out1, out2, out3, dbn_refold
         self.read_name, self.record_name, self.name = read_name, record_name, name
         self.outname = "%s.win_%d.stp_%d.rnd_%d.shfl_%s" % (read_name, W, step, r, shuffle_type)
         self.out6, self.final_partners_wig = out6, final_partners_wig
         self.dbn1, self.dbn2, self.dbn3, self.dbn4 = dbn1, dbn2, dbn3, dbn4
+
+
+def zscore_total(table):
+    """the reference's zscore_total (ScanFold.py:556,751): every numeric z of the scan loop plus the final-window one"""
+    alln = table.alln if getattr(table, "alln", None) is not None else np.zeros(len(table), dtype=bool)
+    z = table.z[~alln].tolist()
+    return z + ([table.final["z"]] if table.final is not None else [])
 
 
 def write_scan_outputs(seq, table, names, temperature, step):
@@ -48,35 +58,71 @@ def write_scan_outputs(seq, table, names, temperature, step):
     o = names.outname
     writers.write_out(o + ".out", names.read_name, seq, table, temperature)
     fin = table.final
+    alln = table.alln if getattr(table, "alln", None) is not None else np.zeros(len(table), dtype=bool)
     extra = (lambda key: [fin[key]]) if fin is not None else (lambda key: [])
-    writers.write_wig(o + ".scan-MFE.wig", table.mfe.tolist() + extra("mfe"), step, names.name)
-    z_all = table.z.tolist() + extra("z")
-    writers.write_wig(o + ".scan-zscores.wig", z_all, step, names.name)
-    writers.write_wig(o + ".scan-pvalue.wig", table.p.tolist() + extra("p"), step, names.name)
-    writers.write_wig(o + ".scan-ED.wig", table.ed.tolist() + extra("ed"), step, names.name)
-    return min(z_all)
+
+    def track(values, all_n_value):
+        lst = values.tolist()
+        for k in np.nonzero(alln)[0]:                 # Q10: int 0 / "#DIV/0" entries of the all-N short-circuit
+            lst[k] = all_n_value
+        return lst
+
+    writers.write_wig(o + ".scan-MFE.wig", track(table.mfe, 0) + extra("mfe"), step, names.name)
+    writers.write_wig(o + ".scan-zscores.wig", track(table.z, "#DIV/0") + extra("z"), step, names.name)
+    writers.write_wig(o + ".scan-pvalue.wig", track(table.p, 0) + extra("p"), step, names.name)
+    writers.write_wig(o + ".scan-ED.wig", track(table.ed, 0) + extra("ed"), step, names.name)
+    zt = zscore_total(table)
+    if not zt:
+        raise ValueError("no window produced a z-score (every window is all-N): statistics.mean of an empty list "
+                         "fails in the reference too (ScanFold.py:761)")
+    return min(zt)
 
 
-def write_fold_outputs(seq, ptable, names, minz, step):
-    """ScanFold-Fold: logs, CT / dbn / bp / wig / fasta files (ScanFold.py:1036-1500,1554).  Returns (agg, final)."""
+def write_fold_outputs(seq, ptable, names, minz, step, by_ed=False, competition=1, zscores=None, filter_value=-2,
+                       input_filename=""):
+    """ScanFold-Fold: logs, CT / dbn / bp / wig / fasta files (ScanFold.py:1036-1500,1554).  Returns (agg, final).
+    by_ed: --by_ed (ED-weighted partner choice and log names, :380-385,1190-1215).  competition = 0: the -c 0 branch
+    (:1454-1466): .dp files instead of CT / dbn / bp, then the reference dies opening the missing dbn file -- so do we."""
+    import statistics
     o = names.outname
-    with open(o + ".ScanFold.log", "w") as log_total, open(o + ".ntPairCounts.log", "w") as sirna:
+    tag = ".ScanFold.ED-weighted" if by_ed else ".ScanFold"
+    with open(o + tag + ".log", "w") as log_total, open(o + ".ntPairCounts.log", "w") as sirna:
         sirna.write("i\tnuc\twindows\tbps\n")
-        agg = foldstep.aggregate(ptable, seq, log_total, sirna)
-    with open(o + ".ScanFold.FinalPartners.txt", "w") as log_win:
+        agg = foldstep.aggregate(ptable, seq, log_total, sirna, by_ed=by_ed)
+    key = agg.coord
+    if competition == 0:
+        with open(o + tag + ".FinalPartners.txt", "w") as log_win:
+            log_win.write(foldstep.FINAL_PARTNERS_HEADER)
+        meanz = float(statistics.mean(zscores))
+        one_sig_below = float(meanz - float(statistics.stdev(zscores)))
+        print("Writing DP files, can not write CT files...")
+        writers.write_bp(names.out6 + "." + o + names.record_name + ".ALL.bp", key, agg.part, agg.mean_z, names.name, minz,
+                         coord=key)
+        output = names.read_name + "." + str(input_filename) + ".ScanFold."
+        dp = lambda path, filt: writers.write_dp(path, key, key, agg.part, agg.mean_z, filt, minz)
+        if filter_value is not None:
+            dp(output + str(filter_value) + names.record_name + ".dp", filter_value)
+        dp(names.out1 + "." + o + ".dp", float(10))
+        dp(names.out2 + "." + o + ".dp", float(-1))
+        dp(names.out3 + "." + o + ".dp", float(-2))
+        dp(output + "." + o + "mean_" + str(round(meanz, 2)) + ".dp", meanz)
+        dp(output + "." + o + "below_mean_" + str(round(one_sig_below, 2)) + ".dp", one_sig_below)
+        print("ScanFold-Fold complete, find results in...")
+        writers.write_fasta(names.name + "." + o + ".fa", seq, names.name)
+        open(names.dbn4, "w").close()     # `cat` of three dbn files that were never written (ScanFold.py:1554)
+        return agg, None
+    with open(o + tag + ".FinalPartners.txt", "w") as log_win:
         fin = foldstep.compete(agg, seq, log_win)
-    n = agg.n_nt
-    covered = seq[:n]
+    covered = "".join(seq[k - 1] for k in key.tolist())
     dbn_text = []
     for path, filt, title in ((names.dbn1, 10.0, "NoFilter"), (names.dbn2, -1.0, "Zavg_-1"), (names.dbn3, -2.0, "Zavg_-2")):
         partner = writers.write_ct(path + ".ct", fin, seq, filt, names.name)
-        writers.write_dbn(path + ".dbn", title, covered, partner)
+        writers.write_dbn(path + ".dbn", title, covered, partner, key)
         dbn_text.append(open(path + ".dbn").read())
-    writers.write_bp(names.out6 + "." + o + ".bp", fin.i, fin.j, fin.z, names.name, minz)
+    writers.write_bp(names.out6 + "." + o + ".bp", fin.i, fin.j, fin.z, names.name, minz, coord=key)
     writers.write_wig_dict(names.final_partners_wig + "." + o + ".wig", fin.z, names.name, step)
-    key = np.arange(1, n + 1)
     writers.write_bp(names.out6 + "." + o + "." + names.record_name + ".ALL.bp", key, agg.part, agg.mean_z, names.name,
-                     minz)
+                     minz, coord=key)
     writers.write_fasta(names.name + "." + o + ".fa", seq, names.name)
     with open(names.dbn4, "w") as f:      # `cat` of the three dbn files (ScanFold.py:1554)
         f.write("".join(dbn_text))

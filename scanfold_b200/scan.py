@@ -31,6 +31,7 @@ class WindowTable:
         self.native_unconstrained_dcal = self.shuffle_dcal = None
         self.pair_tbl = self.centroid_tbl = None
         self.final = None
+        self.alln = None           # [n] bool: windows the reference short-circuits as all-N (Appendix B Q10), or None
         self.ms_total = self.ms_mfe = 0.0
         self.n_launches = 0
 
@@ -47,6 +48,22 @@ class WindowTable:
 def n_windows_of(L, W, step):
     """windows at i = 0, step, 2*step, ... <= L - W   (ScanFold.py:429,687)"""
     return (L - W) // step + 1 if L >= W else 0
+
+
+def all_n_windows(seq, W, step, first_window, n_windows):
+    """Windows the reference never folds (ScanFold.py:486-492): the fragment equals a LITERAL string of 120 'N', so the
+    test only ever fires for 120-nt windows made of upper-case N (Appendix B Q10).  -> bool [n_windows] or None."""
+    if W != 120 or "N" * 120 not in seq:
+        return None
+    is_n = np.frombuffer(seq.encode(), dtype=np.uint8) == ord("N")
+    c = np.concatenate([[0], np.cumsum(is_n)])
+    start = (first_window + np.arange(n_windows, dtype=np.int64)) * step
+    return (c[start + W] - c[start]) == W
+
+
+def final_window_all_n(seq, W):
+    """the final-window block's own test, `frag == "N" * window_size` (ScanFold.py:719): any window length"""
+    return seq[len(seq) - W:] == "N" * W
 
 
 def round_ed(ed):

@@ -42,6 +42,8 @@ def accumulate_numpy(L, W, step, first_window, pair_tbl, z100, mfe_dcal, ed100):
         for pos in range(W):
             row = w * step + pos - nt0
             p = int(pair_tbl[s][pos])
+            if p < 0:
+                continue
             col = ((p - 1) - pos if p else 0) + W - 1
             count[row, col] += 1
             first[row, col] = min(first[row, col], w)
@@ -70,6 +72,8 @@ class NumpyAccumulator:
             for pos in range(W):
                 row = s * step + pos
                 p = int(pair_tbl[s][pos])
+                if p < 0:
+                    continue
                 col = ((p - 1) - pos if p else 0) + W - 1
                 self.count[row, col] += 1
                 self.first[row, col] = min(self.first[row, col], w)
