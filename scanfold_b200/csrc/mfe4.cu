@@ -32,6 +32,7 @@ constexpr int NT4 = 256;      // threads per block task
 constexpr int WR = 62;        // rows / columns of the inner-pair window
 constexpr int WP = 64;        // its pitch
 constexpr int NCAND = 496;
+constexpr int PADG = 416, PAD1 = 64, PADB = 64;   // 406 generic, 54 1xn, 58 bulge candidates, padded to warp multiples
 
 enum { K_GENERIC = 0, K_1N = 1, K_BULGE = 2, K_TABLE = 3 };
 
@@ -210,21 +211,27 @@ __device__ __forceinline__ int extloop4(const Tab4 &s, int type, int si1, int sj
 
 constexpr int TAB4_INTS = (int)((sizeof(Tab4) + 15) / 16 * 4);
 
-// What the block kernel keeps in shared memory (the rarely used tables stay in the global Tab4): interior-loop candidates
-// as ONE word each -- window offset u1 * WP - u2 + 30 (12 bits), shift of the class field 10 * class (5 bits), size term
-// minus the two field biases (15 bits, signed) -- and only the separable classes; the nine table-driven shapes run apart.
+// What the block kernel keeps in shared memory (the rarely used tables stay in the global Tab4): the interior-loop
+// candidates of the three separable classes as ONE word each -- window offset u1 * WP - u2 + 30 in the low half, size term
+// minus the field bias in the high half -- sorted by class, then by loop size u1 + u2, so that a class is one loop with a
+// compile-time field shift; the nine table-driven shapes run apart.
 struct TabB {
     int stack[64];
     int mmI[200], mm1n[200], mmM[200];
     int d5[40], d3[40];
-    int MLbase, MLclosing, MLintern, TerminalAU, bulge1, pad0, pad1, pad2;
-    int ncand_upto[32];
+    int mm23[200], mmH[200];
+    int MLbase, MLclosing, MLintern, TerminalAU, bulge1, il5_ninio, pad1, pad2;
+    int cls_begin[4];          // first candidate of class 0, 1, 2 (and the end)
+    int ncls_upto[3][32];      // candidates of the class with u1 + u2 <= u
+    // ---- from here on the block kernel reads the global copy (start-up and the short walks of small block diagonals)
     int cand[NCAND];
+    int candp[PADG + PAD1 + PADB];   // the same lists, each padded to a multiple of 32 with never-winning entries: the full
+                                     // walk (every cell with j - i > 35) is fixed-trip and each lane keeps its 17 words in registers
 };
 TabB *g_dtabB = nullptr;
 bool g_mfe4_ok = false;
 
-constexpr int TABB_INTS = (int)(sizeof(TabB) / 4);
+constexpr int TABB_INTS = (int)(offsetof(TabB, cand) / 4);   // the part copied to shared memory
 constexpr int TRI = 32 * 33 / 2;                  // upper triangle of a 32 x 32 block, diagonal included
 constexpr int O_MB = TABB_INTS;                   // [33][34] FML: row 32 = first row of block (I+1,J), column 0 = column 32J-1
 constexpr int O_DB = O_MB + 33 * 34;              // [33][34] split minima, same halo
@@ -265,6 +272,10 @@ mfe4_block_kernel(Mfe4Launch L, const MfeTables *__restrict__ T, const Tab4 *__r
         const int *src = reinterpret_cast<const int *>(gtabB);
         for (int k = tid; k < TABB_INTS; k += NT4) sm4[k] = src[k];
     }
+    __syncthreads();
+    int cdr[(PADG + PAD1 + PADB) / 32];   // this lane's candidate words of the full walk (warps 2..6 use them)
+#pragma unroll
+    for (int k = 0; k < (PADG + PAD1 + PADB) / 32; k++) cdr[k] = gtabB->candp[k * 32 + lane];
     const int n = L.n, NP = L.NP;
     const int per_fold = L.NB - delta;   // block tasks of this diagonal per fold
     const long long n_task = (long long)L.n_fold * per_fold;
@@ -357,9 +368,9 @@ mfe4_block_kernel(Mfe4Launch L, const MfeTables *__restrict__ T, const Tab4 *__r
         if (delta >= 1)
             for (int k = tid; k < 32 * 32; k += NT4) {
                 const int a = k >> 5, c = k & 31;
-                if (c >= a) {
+                if (c >= a) {   // Mii by row (entry [a][c] at tri32(a, c)), Mjj by column (entry [a][c] at c (c + 1) / 2 + a)
                     Mii[tri32(a, c)] = ldM(gM, i0 + a, i0 + c);
-                    Mjj[tri32(a, c)] = ldM(gM, j0 + a, j0 + c);
+                    Mjj[(c * (c + 1)) / 2 + a] = ldM(gM, j0 + a, j0 + c);
                 }
             }
         for (int k = tid; k < 32 * 32; k += NT4) {
@@ -400,25 +411,23 @@ mfe4_block_kernel(Mfe4Launch L, const MfeTables *__restrict__ T, const Tab4 *__r
 
         // ---- 3. the 63 anti-diagonals of the block, cell (a, b) = (i0 + a, j0 + b) on step s = 31 - a + b, software
         // pipelined with ONE barrier per step.  Iteration t runs, side by side,
-        //   G  the separable interior loops of the pairable cells of step t, one warp per cell (warps 2..7)
+        //   G  the separable interior loops of the pairable cells of step t, one warp per cell (warps 2..6)
         //   H  their nine table-driven shapes and the hairpin, lane = cell (warps 0 and 1 share the shapes)
         //   F  for the cells of step t-1: C from the partial minima of iteration t-1 plus the multiloop closing term, the
-        //      window entry, then the splits inside the two diagonal blocks and FML (8 lanes per cell, every warp)
+        //      window entry, then the splits inside the two diagonal blocks and FML (warp 7, lane = cell)
         // C(t) only reads cells of steps <= t-2 and the split minima of step t-2; FML(t-1) reads FML of steps <= t-2.
         for (int t = s_begin; t <= 63; t++) {
-            // ---- F: step t - 1
-            if (t > s_begin) {
-                const int s = t - 1;
-                const int blo = max(0, s - 31), nc = min(s, 62 - s) + 1;
-                const int cell = tid >> 3, g = tid & 7;
-                const bool active = cell < nc && j0 + blo + cell < n;
-                int dec = INF, a = 0, b = 0, cij = INF;
-                if (active) {
-                    b = blo + cell;
-                    a = 31 - s + b;
-                    if (g == 0) {
+            if (warp == NT4 / 32 - 1) {
+                // ---- F: step t - 1, lane = cell
+                if (t > s_begin) {
+                    const int s = t - 1;
+                    const int blo = max(0, s - 31), nc = min(s, 62 - s) + 1;
+                    const int b = blo + min(lane, nc - 1), a = 31 - s + b;
+                    const int i = i0 + a, j = j0 + b;
+                    const bool active = lane < nc && j < n;
+                    int cij = INF;
+                    if (active) {
                         const int type = tyb[a * 32 + b];
-                        const int i = i0 + a, j = j0 + b;
                         if (type) {
                             int e = min(part[(s & 1) * 64 + b], part[(s & 1) * 64 + 32 + b]);
                             part[(s & 1) * 64 + b] = INF;        // both are written again two iterations on
@@ -440,91 +449,149 @@ mfe4_block_kernel(Mfe4Launch L, const MfeTables *__restrict__ T, const Tab4 *__r
                             gC[(size_t)j * NP + i] = cij;   // transposed copy for the exterior loop
                         }
                     }
-                    if (delta == 0) {   // m = i0 + c, a < c <= b: FML[i][m-1] + FML[m][j], both inside this block
-                        for (int c = a + 1 + g; c <= b; c += 8) dec = min(dec, Mb[a * 34 + c] + Mb[c * 34 + b + 1]);
+                    // splits inside the two diagonal blocks: m = i0 + c (rows below, 31 - a terms) and m = j0 + c (columns to
+                    // the left, b + 1 terms).  Both loops run over warp-uniform ranges WITHOUT a per-lane test: outside a lane's
+                    // own range one operand is a cell of this block that a later step computes -- still INF in Mb -- so the sum
+                    // stays above INF / 2 whatever the other operand reads (neighbouring entries of the triangles).
+                    int dec = 2 * INF;
+                    const int a_lo = 31 - s + blo, b_hi = blo + nc - 1;   // smallest a / largest b of the step
+                    if (delta == 0) {   // a < c <= b: FML[i][m-1] + FML[m][j], both inside this block
+                        const int *pa = Mb + a * 34, *pb = Mb + b + 1;
+#pragma unroll 4
+                        for (int c = a_lo + 1; c <= b_hi; c++) dec = __viaddmin_s32(pa[c], pb[c * 34], dec);
                     } else {
-                        for (int c = a + 1 + g; c < 32; c += 8) dec = min(dec, Mii[tri32(a, c - 1)] + Mb[c * 34 + b + 1]);
-                        for (int c = g; c <= b; c += 8) dec = min(dec, Mb[a * 34 + c] + Mjj[tri32(c, b)]);
+                        const int *pa = Mii + tri32(a, a) - a - 1, *pb = Mb + b + 1;   // pa[c] = Mii[a][c-1]
+#pragma unroll 4
+                        for (int c = a_lo + 1; c < 32; c++) dec = __viaddmin_s32(pa[c], pb[c * 34], dec);
+                        const int *qa = Mb + a * 34, *qb = Mjj + (b * (b + 1)) / 2;   // Mjj by column: [b][c], c <= b
+#pragma unroll 4
+                        for (int c = 0; c <= b_hi; c++) dec = __viaddmin_s32(qa[c], qb[c], dec);
+                    }
+                    __syncwarp();   // every lane has read the Mb entries of this step's cells (still INF) before anyone writes
+                    if (active) {
+                        dec = min(dec, Db[a * 34 + b + 1]);
+                        if (dec > INF / 2) dec = INF;
+                        int m = dec;
+                        if (j - i - 1 > TURN) {
+                            const int x = Mb[(a + 1) * 34 + b + 1], y = Mb[a * 34 + b];
+                            if (x < INF) m = min(m, x + tb.MLbase);
+                            if (y < INF) m = min(m, y + tb.MLbase);
+                        }
+                        if (cij < INF)
+                            m = min(m, cij + mlstem4b(tb, pair_type(SR(i), SCc(j)), i > 0 ? SR(i - 1) : -1, j < n - 1 ? SCc(j + 1) : -1));
+                        if (j - i <= TURN) m = INF;
+                        Db[a * 34 + b + 1] = dec;
+                        Mb[a * 34 + b + 1] = m;
+                        if (j - i > TURN) {
+                            gM[(size_t)i * NP + j] = m;
+                            gD[(size_t)i * NP + j] = dec;
+                        }
                     }
                 }
-                dec = min(dec, __shfl_xor_sync(full, dec, 1));
-                dec = min(dec, __shfl_xor_sync(full, dec, 2));
-                dec = min(dec, __shfl_xor_sync(full, dec, 4));
-                if (active && g == 0) {
-                    const int i = i0 + a, j = j0 + b;
-                    dec = min(dec, Db[a * 34 + b + 1]);
-                    if (dec > INF / 2) dec = INF;
-                    int m = dec;
-                    if (j - i - 1 > TURN) {
-                        const int x = Mb[(a + 1) * 34 + b + 1], y = Mb[a * 34 + b];
-                        if (x < INF) m = min(m, x + tb.MLbase);
-                        if (y < INF) m = min(m, y + tb.MLbase);
-                    }
-                    if (cij < INF)
-                        m = min(m, cij + mlstem4b(tb, pair_type(SR(i), SCc(j)), i > 0 ? SR(i - 1) : -1, j < n - 1 ? SCc(j + 1) : -1));
-                    if (j - i <= TURN) m = INF;
-                    Db[a * 34 + b + 1] = dec;
-                    Mb[a * 34 + b + 1] = m;
-                    if (j - i > TURN) {
-                        gM[(size_t)i * NP + j] = m;
-                        gD[(size_t)i * NP + j] = dec;
-                    }
-                }
-            }
-            if (t < 63) {
+            } else if (t < 63) {
                 const int npair = scnt[t];
                 const unsigned char *lst = slist + t * 32;
                 int *pG = part + (t & 1) * 64, *pS = pG + 32;
                 if (warp >= 2) {
-                    // ---- G: separable classes, one warp per cell, lane = candidate
-                    for (int c = warp - 2; c < npair; c += NT4 / 32 - 2) {
+                    // ---- G: separable classes, one warp per cell, lane = candidate, one loop per class
+                    for (int c = warp - 2; c < npair; c += NT4 / 32 - 3) {
                         const int b = lst[c], a = 31 - t + b;
                         const int type = tyb[a * 32 + b];
                         const int i = i0 + a, j = j0 + b, d = j - i;
                         const int mi = mmi(type, SR(i + 1), SCc(j - 1));
-                        const int opk = pack3(tb.mmI[mi], tb.mm1n[mi], type > 2 ? tb.TerminalAU : 0);
                         const int umax = min(MAXLOOP, d - 2 - (TURN + 1));
-                        const int ncand = umax >= 0 ? tb.ncand_upto[umax] : 0;
                         const int2 *base = win + a * WP + b;
-                        int acc = INF;
-#pragma unroll 4
-                        for (int ci = lane; ci < ncand; ci += 32) {
-                            const int cd = tb.cand[ci];
-                            const int sh = (cd >> 12) & 31;
-                            const int2 w = base[cd & 4095];
-                            acc = min(acc, w.x + ((w.y >> sh) & 1023) + ((opk >> sh) & 1023) + (cd >> 17));
+                        int accG = INF, acc1 = INF, accB = INF;
+                        if (umax == MAXLOOP) {   // the full candidate set: fixed trip counts, candidate words from registers
+#pragma unroll
+                            for (int k = 0; k < PADG / 32; k++) {
+                                const int2 w = base[cdr[k] & 0xffff];
+                                accG = __viaddmin_s32(w.x + (w.y & 1023), cdr[k] >> 16, accG);
+                            }
+#pragma unroll
+                            for (int k = 0; k < PAD1 / 32; k++) {
+                                const int cd = cdr[PADG / 32 + k];
+                                const int2 w = base[cd & 0xffff];
+                                acc1 = __viaddmin_s32(w.x + ((w.y >> 10) & 1023), cd >> 16, acc1);
+                            }
+#pragma unroll
+                            for (int k = 0; k < PADB / 32; k++) {
+                                const int cd = cdr[(PADG + PAD1) / 32 + k];
+                                const int2 w = base[cd & 0xffff];
+                                accB = __viaddmin_s32(w.x + ((w.y >> 20) & 1023), cd >> 16, accB);
+                            }
+                        } else if (umax >= 0) {
+                            const int *c0 = gtabB->cand + tb.cls_begin[0], *c1 = gtabB->cand + tb.cls_begin[1], *c2 = gtabB->cand + tb.cls_begin[2];
+                            const int n0 = tb.ncls_upto[0][umax], n1 = tb.ncls_upto[1][umax], n2 = tb.ncls_upto[2][umax];
+                            for (int ci = lane; ci < n0; ci += 32) {
+                                const int cd = c0[ci];
+                                const int2 w = base[cd & 0xffff];
+                                accG = __viaddmin_s32(w.x + (w.y & 1023), cd >> 16, accG);
+                            }
+                            for (int ci = lane; ci < n1; ci += 32) {
+                                const int cd = c1[ci];
+                                const int2 w = base[cd & 0xffff];
+                                acc1 = __viaddmin_s32(w.x + ((w.y >> 10) & 1023), cd >> 16, acc1);
+                            }
+                            for (int ci = lane; ci < n2; ci += 32) {
+                                const int cd = c2[ci];
+                                const int2 w = base[cd & 0xffff];
+                                accB = __viaddmin_s32(w.x + ((w.y >> 20) & 1023), cd >> 16, accB);
+                            }
                         }
+                        int acc = min(accG + tb.mmI[mi], min(acc1 + tb.mm1n[mi], accB + (type > 2 ? tb.TerminalAU : 0)));
                         acc = __reduce_min_sync(full, acc);
                         if (lane == 0) pG[b] = min(acc, INF);
                     }
                 } else if (lane < npair) {
-                    // ---- H: the nine table-driven shapes (warp 0: stack, bulges of one, 1x1; warp 1: 1x2, 2x1, 2x2, 2x3,
-                    // 3x2) and the hairpin, lane = cell; the loads are unconditional so that they issue together
+                    // ---- H: the nine table-driven shapes (warp 0: stack, bulges of one, 1x1, hairpin; warp 1: 1x2, 2x1, 2x2,
+                    // 2x3, 3x2), lane = cell.  Straight-line code: every table load is issued whether or not the inner cell
+                    // pairs (type 0 rows are valid addresses), so the L2 round trips of a warp overlap.
                     const int b = lst[lane], a = 31 - t + b;
                     const int type = tyb[a * 32 + b];
                     const int i = i0 + a, j = j0 + b;
                     const int si1 = SR(i + 1), sj1 = SCc(j - 1);
-                    int best = INF;
-                    auto shape = [&](int u1, int u2) {
-                        const int2 w = win[(a + u1) * WP + b + 30 - u2];
+                    const int2 *wb = win + a * WP + b + 30;
+                    auto inner = [&](int u1, int u2, int &cpq, int &t2, int &sp1, int &sq1) {
+                        cpq = wb[u1 * WP - u2].x;
                         const int p = i + 1 + u1, q = j - 1 - u2;
-                        const int t2 = rtype_of(pair_type(SR(p), SCc(q)));
-                        int e = intloop4(*gtab, T, u1, u2, type, t2, si1, sj1, SR(p - 1), SCc(q + 1));
-                        if (u1 == 0 && u2 == 0 && scf) e += scf[i + 1] + scf[p + 1] + scf[q + 1] + scf[j + 1];
-                        if (w.x < INF) best = min(best, w.x + e);
+                        t2 = rtype_of(pair_type(SR(p), SCc(q)));
+                        sp1 = SR(p - 1);
+                        sq1 = SCc(q + 1);
                     };
+                    auto fin = [](int c, int e) { return c < INF ? c + e : INF; };
+                    int best;
                     if (warp == 0) {
-                        shape(0, 0);
-                        shape(0, 1);
-                        shape(1, 0);
-                        shape(1, 1);
-                        best = min(best, hairpin4(*gtab, T, L.hp_len, S, i, j, type));
+                        int c00, c01, c10, c11, t00, t01, t10, t11, x, y;
+                        inner(0, 0, c00, t00, x, y);
+                        inner(0, 1, c01, t01, x, y);
+                        inner(1, 0, c10, t10, x, y);
+                        inner(1, 1, c11, t11, x, y);
+                        const int e11 = __ldg(&T->int11[type][t11][si1][sj1]);
+                        const int u = j - i - 1;
+                        int eh = __ldg(L.hp_len + u) + tb.mmH[mmi(type, si1, sj1)];
+                        if (u <= 6) eh = hairpin4(*gtab, T, L.hp_len, S, i, j, type);
+                        int e00 = tb.stack[type * 8 + t00];
+                        if (scf) e00 += scf[i + 1] + scf[i + 2] + scf[j] + scf[j + 1];
+                        best = min(eh, fin(c00, e00));
+                        best = min(best, fin(c01, tb.bulge1 + tb.stack[type * 8 + t01]));
+                        best = min(best, fin(c10, tb.bulge1 + tb.stack[type * 8 + t10]));
+                        best = min(best, fin(c11, e11));
                     } else {
-                        shape(1, 2);
-                        shape(2, 1);
-                        shape(2, 2);
-                        shape(2, 3);
-                        shape(3, 2);
+                        int c12, c21, c22, c23, c32, t12, t21, t22, t23, t32, p12, q12, p21, q21, p22, q22, p23, q23, p32, q32;
+                        inner(1, 2, c12, t12, p12, q12);
+                        inner(2, 1, c21, t21, p21, q21);
+                        inner(2, 2, c22, t22, p22, q22);
+                        inner(2, 3, c23, t23, p23, q23);
+                        inner(3, 2, c32, t32, p32, q32);
+                        const int e12 = __ldg(&T->int21[type][t12][si1][q12][sj1]);     // n1 == 1
+                        const int e21 = __ldg(&T->int21[t21][type][q21][si1][p21]);
+                        const int e22 = __ldg(&T->int22[type][t22][si1][p22][q22][sj1]);
+                        const int m23 = tb.il5_ninio + tb.mm23[mmi(type, si1, sj1)];
+                        best = min(fin(c12, e12), fin(c21, e21));
+                        best = min(best, fin(c22, e22));
+                        best = min(best, fin(c23, m23 + tb.mm23[mmi(t23, q23, p23)]));
+                        best = min(best, fin(c32, m23 + tb.mm23[mmi(t32, q32, p32)]));
                     }
                     atomicMin(&pS[b], best);
                 }
@@ -807,20 +874,40 @@ void mfe4_upload_tables(const MfeTables &M) {
     hb.MLintern = M.MLintern;
     hb.TerminalAU = M.TerminalAU;
     hb.bulge1 = M.bulge[1];
+    hb.il5_ninio = M.internal_loop[5] + M.ninio;
+    for (int k = 0; k < 200; k++) {
+        hb.mm23[k] = h.mm23[k];
+        hb.mmH[k] = h.mmH[k];
+    }
     ok = ok && fits10(M.TerminalAU);
     int ng = 0;
-    for (int u = 0; u <= MAXLOOP; u++) {
-        for (int u1 = 0; u1 <= u; u1++) {
-            const int k = (u ? h.ncand_upto[u - 1] : 0) + u1;
-            const int cls = h.cand_code[k] >> 10, u2 = u - u1;
-            if (cls == K_TABLE) continue;
-            const int size = h.cand_size[k] - 2 * FB;        // the two 10-bit fields carry a bias of FB each
-            ok = ok && size >= -16384 && size < 16384;
-            hb.cand[ng++] = (int)(((unsigned)size << 17) | ((unsigned)(10 * cls) << 12) | (unsigned)(u1 * WP - u2 + 30));
+    for (int cls = 0; cls < 3; cls++) {
+        hb.cls_begin[cls] = ng;
+        for (int u = 0; u <= MAXLOOP; u++) {
+            for (int u1 = 0; u1 <= u; u1++) {
+                const int k = (u ? h.ncand_upto[u - 1] : 0) + u1;
+                const int u2 = u - u1;
+                if ((h.cand_code[k] >> 10) != cls) continue;
+                const int size = h.cand_size[k] - FB;        // the 10-bit field carries a bias of FB
+                ok = ok && size >= -32768 && size < 32768;
+                hb.cand[ng++] = (int)(((unsigned)size << 16) | (unsigned)(u1 * WP - u2 + 30));
+            }
+            hb.ncls_upto[cls][u] = ng - hb.cls_begin[cls];
         }
-        hb.ncand_upto[u] = ng;
+        hb.ncls_upto[cls][31] = hb.ncls_upto[cls][30];
     }
-    hb.ncand_upto[31] = ng;
+    hb.cls_begin[3] = ng;
+    {
+        const int pads[3] = {PADG, PAD1, PADB};
+        int o = 0;
+        for (int cls = 0; cls < 3; cls++) {
+            const int cnt = hb.cls_begin[cls + 1] - hb.cls_begin[cls];
+            ok = ok && cnt <= pads[cls];
+            for (int k = 0; k < pads[cls]; k++)
+                hb.candp[o + k] = k < cnt ? hb.cand[hb.cls_begin[cls] + k] : (int)((unsigned)32767 << 16);   // offset 0, size 32767
+            o += pads[cls];
+        }
+    }
     for (int k = ng; k < NCAND; k++) hb.cand[k] = 0;
     g_mfe4_ok = ok;
     if (!g_dtabB) cudaMalloc(&g_dtabB, sizeof(TabB));
