@@ -67,6 +67,13 @@ int sfb_params_besteffort(void);
 int sfb_fold_batch(const uint8_t *seqs, int n_seq, int len, const sfb_model *model, const uint8_t *hc,
                    const int32_t *sc, int32_t *e_dcal, int16_t *pair_tbl);
 
+/* One fold of a whole sequence, up to SFB_MAX_LONG nt, on the blocked int32 kernel (mfe4.cu).  Replaces the three full-length
+ * folds of --global_refold: RNA.fold_compound(full sequence, md) [+ fc.hc_add_from_db(line 3 of a Zavg dbn file)] .mfe()
+ * (ScanFold.py:1518-1539).  hc as in sfb_fold_batch (NULL = unconstrained).  pair_tbl [n] int32 out: 1-based partner,
+ * 0 = unpaired (32-bit because a record can be longer than an int16 holds). */
+#define SFB_MAX_LONG 40000
+int sfb_fold_long(const uint8_t *seq, int n, const sfb_model *model, const uint8_t *hc, int32_t *e_dcal, int32_t *pair_tbl);
+
 /* Batch of partition functions.  Replaces fc.pf(); fc.centroid(); fc.mean_bp_distance():
  *   ScanFold.py:498,503-504 / :514,518-519 / :525-527.
  * ensemble_dG [n_seq] kcal/mol, ed [n_seq] (mean_bp_distance), centroid_tbl [n_seq*len] int16 pair table,

@@ -9,7 +9,8 @@ The structure-extraction step that follows the ScanFold-Fold outputs (motif .dbn
 ExtractedStructures.gff3, ScanFold.py:1557-1781) runs too, every motif as one single-window scan; only its
 PostScript plots are not written.
 
-Not carried over (out of scope): --lri, --algo rnastructure, --by_ed, -c 0, --global_refold; selecting
+--global_refold (three full-length folds on the blocked kernel), --by_ed, -c 0, --print and --print_random behave as in
+the reference.  Not carried over (out of scope): --lri, --algo rnastructure, --fold_only, --dont_scan; selecting
 one of them is an error, not a silent no-op.
 """
 import argparse
@@ -178,6 +179,25 @@ def emit_window_prints(args, seq, table, react, hc, temperature):
                 print("\t".join(str(c) for c in cols + [frag, db[k], cen[k], writers.gc_content(frag)]) + "\n")
 
 
+def global_refold(seq, names, name, temperature, max_span):
+    """--global_refold (ScanFold.py:1509-1551): the whole record folded three times -- with the Zavg < -1 pairs as hard
+    constraints, with the Zavg < -2 pairs, and unconstrained -- and written to the refold dbn file.  Line 3 of a Zavg dbn
+    file covers the nucleotides the scan covered; ViennaRNA applies a shorter constraint string to the leading positions."""
+    from . import engine
+    print("Refolding full sequence using ScanFold results as constraints...")
+    out = []
+    for path in (names.dbn2, names.dbn3):
+        hc = open(path + ".dbn").readlines()[2].rstrip("\n")
+        out.append(engine.fold_long(seq.upper(), hc=hc, temperature=temperature, max_span=max_span))
+    full = engine.fold_long(seq.upper(), temperature=temperature, max_span=max_span)
+    f32 = lambda e: str(float(np.float32(e / 100.0)))          # vrna_mfe returns a C float
+    db = lambda pt: engine.pair_table_to_dotbracket(pt)
+    with open(names.dbn_refold, "w") as f:
+        f.write(">%s\tGlobal Full MFE=%s\n%s\n%s\n" % (name, f32(full[0]), seq, db(full[1])))
+        f.write(">%s\tRefolded with -1 constraints MFE=%s\n%s\n%s\n" % (name, f32(out[0][0]), seq, db(out[0][1])))
+        f.write(">%s\tRefolded with -2 constraints MFE=%s\n%s\n%s\n" % (name, f32(out[1][0]), seq, db(out[1][1])))
+
+
 def run_record(args, record_name, raw_seq, original_directory, dist=None):
     """One FASTA record.  With a torch.distributed process group (torchrun, one process per GPU) the windows are
     sharded by range over the ranks; rank 0 owns the output folder and writes every file."""
@@ -200,7 +220,8 @@ def run_record(args, record_name, raw_seq, original_directory, dist=None):
         W, step, r = int(args.w), int(args.s), int(args.r)
         names = pipeline.RunNames(read_name, record_name, W, step, r, str(args.type), name=args.name, out6=args.out6,
                                   final_partners_wig=args.final_partners_wig, dbn1=args.dbn_file_path1,
-                                  dbn2=args.dbn_file_path2, dbn3=args.dbn_file_path3, dbn4=args.dbn_file_path4)
+                                  dbn2=args.dbn_file_path2, dbn3=args.dbn_file_path3, dbn4=args.dbn_file_path4,
+                                  out1=args.out1, out2=args.out2, out3=args.out3, dbn_refold=args.dbn_file_path)
         if rank == 0:
             print("Output name=" + names.outname)
         if len(seq) < W:
@@ -243,8 +264,11 @@ def run_record(args, record_name, raw_seq, original_directory, dist=None):
                                      parity_shuffles=parity, temperature=float(args.t), max_span=args.span or 0, hc=hc,
                                      react=react, shape_m=args.m, shape_b=args.b, first_window=w0, n_windows=w1 - w0,
                                      final_window=last)
+            shard.alln = scan.all_n_windows(seq, W, step, w0, w1 - w0)      # Q10: tested on the record as given
+            if last and scan.final_window_all_n(seq, W):
+                shard.final = None                                          # the final-window block appends nothing (:719-726)
             z100, mfe100, ed100 = pipeline.fold_inputs(shard)
-            acc = engine.Accumulator(len(seq), W, step, w0, shard.pair_tbl, z100, mfe100, ed100)
+            acc = engine.Accumulator(len(seq), W, step, w0, shard.pair_tbl, z100, mfe100, ed100, skip=shard.alln)
         else:                  # more ranks than windows: this rank only takes part in the collectives
             shard = scan.empty_table(W, step, r, w0)
         try:
@@ -259,7 +283,11 @@ def run_record(args, record_name, raw_seq, original_directory, dist=None):
         minz = pipeline.write_scan_outputs(seq, table, names, int(args.t), step)   # Sequence column keeps input case (Q11)
         print("Elapsed time: %ss" % round(time.time() - t0, 2))
         print("Determining best base pairs...")
-        pipeline.write_fold_outputs(seq, ptable, names, minz, step)
+        pipeline.write_fold_outputs(seq, ptable, names, minz, step, by_ed=bool(args.by_ed), competition=int(args.c),
+                                    zscores=pipeline.zscore_total(table), filter_value=int(args.f),
+                                    input_filename=args.filename)
+        if args.global_refold:
+            global_refold(seq, names, args.name, float(args.t), args.span or 0)
         # structure extraction: refold every top-level helix of the Zavg < -2 structure (ScanFold.py:1557-1781)
         parity_npz = None
         if args.parity_shuffles:
@@ -275,8 +303,7 @@ def run_record(args, record_name, raw_seq, original_directory, dist=None):
 
 def main(argv=None):
     args = build_parser().parse_args(argv)
-    for flag, why in ((args.lri, "--lri (experimental duplex scan)"), (args.by_ed, "--by_ed"),
-                      (args.global_refold, "--global_refold (full-length fold)"), (args.c != 1, "-c 0"),
+    for flag, why in ((args.lri, "--lri (experimental duplex scan)"),
                       (str(args.algo) != "rnafold", "--algo " + str(args.algo)),
                       (args.fold_only, "--fold_only"), (args.dont_scan, "--dont_scan")):
         if flag:

@@ -420,6 +420,61 @@ int sfb_fold_batch(const uint8_t *seqs, int n_seq, int len, const sfb_model *mod
     }
 }
 
+int sfb_fold_long(const uint8_t *seq, int n, const sfb_model *model, const uint8_t *hc, int32_t *e_dcal, int32_t *pair_tbl) {
+    if (n >= 1 && n < MFE4_MIN_W) {   // short sequences: the batch path (its pair table is 16 bit)
+        if (!seq || !e_dcal || !pair_tbl) return fail(SFB_E_ARG, "sfb_fold_long: bad argument");
+        std::vector<int16_t> pt16((size_t)n);
+        const int rc = sfb_fold_batch(seq, 1, n, model, hc, nullptr, e_dcal, pt16.data());
+        for (int k = 0; k < n && !rc; k++) pair_tbl[k] = pt16[k];
+        return rc;
+    }
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (int rc = check_model(model)) return rc;
+    if (!seq || !e_dcal || !pair_tbl || n < 1) return fail(SFB_E_ARG, "sfb_fold_long: bad argument");
+    if (n > SFB_MAX_LONG) return fail(SFB_E_RANGE, "sequence exceeds SFB_MAX_LONG");
+    if (!mfe4_supports(n)) return fail(SFB_E_PARAMS, "the loaded energy table does not fit the blocked kernel's packed fields");
+    try {
+        CK(cudaSetDevice(g_ctx.device));
+        cudaStream_t st = g_ctx.stream;
+        std::vector<uint8_t> codes;
+        encode_host(seq, (size_t)n, codes);
+        std::vector<int32_t> hp((size_t)n + 1);   // hairpin initiation by loop size, as load_params extrapolates it
+        for (int u = 0; u <= n; u++)
+            hp[u] = u <= 30 ? g_ctx.hp.mfe.hairpin[u] : g_ctx.hp.mfe.hairpin[30] + (int)(g_ctx.hp.lxc * std::log(u / 30.));
+        DevBuf<uint8_t> d_seq, d_hc;
+        DevBuf<int32_t> d_hp, d_e, d_pt;
+        DevBuf<char> scratch;
+        d_seq.alloc(n);
+        d_hp.alloc((size_t)n + 1);
+        d_e.alloc(1);
+        d_pt.alloc(n);
+        scratch.alloc(mfe4_bytes_per_fold(n));
+        CK(cudaMemcpyAsync(d_seq.p, codes.data(), n, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(d_hp.p, hp.data(), sizeof(int32_t) * ((size_t)n + 1), cudaMemcpyHostToDevice, st));
+        if (hc) {
+            d_hc.alloc(n);
+            CK(cudaMemcpyAsync(d_hc.p, hc, n, cudaMemcpyHostToDevice, st));
+        }
+        MfeLaunch L{};
+        L.seqs = d_seq.p;
+        L.hc = d_hc.p;
+        L.hc_simple = hc && hc_is_simple(hc, (size_t)n);
+        L.n_fold = 1;
+        L.W = n;
+        L.max_span = model ? model->max_bp_span : 0;
+        L.e_out = d_e.p;
+        launch_mfe4(L, g_ctx.d_mfe, d_hp.p, scratch.p, scratch.n, d_pt.p, g_ctx.n_sm, st, nullptr);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(e_dcal, d_e.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(pair_tbl, d_pt.p, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (*e_dcal >= SFB_INF) return fail(SFB_E_CUDA, "traceback failed");
+        return 0;
+    } catch (const CudaError &e) {
+        return fail(SFB_E_CUDA, e.what());
+    }
+}
+
 int sfb_pf_batch(const uint8_t *seqs, int n_seq, int len, const sfb_model *model, const uint8_t *hc,
                  const int32_t *sc, double *ensemble_dG, double *ed, int16_t *centroid_tbl, double *bpp) {
     std::lock_guard<std::mutex> lk(g_mu);

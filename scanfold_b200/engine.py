@@ -19,7 +19,7 @@ INF = 10000000
 SHUFFLE_MONO, SHUFFLE_DI = 0, 1
 
 EXPORTS = ["sfb_version", "sfb_init", "sfb_shutdown", "sfb_last_error", "sfb_params_besteffort", "sfb_fold_batch",
-           "sfb_pf_batch", "sfb_deigan", "sfb_scan", "sfb_scan_plan_create", "sfb_scan_plan_keep_shuffles",
+           "sfb_fold_long", "sfb_pf_batch", "sfb_deigan", "sfb_scan", "sfb_scan_plan_create", "sfb_scan_plan_keep_shuffles",
            "sfb_scan_plan_run", "sfb_scan_plan_fetch", "sfb_scan_plan_stage_ms", "sfb_scan_plan_destroy", "sfb_accumulate_begin",
            "sfb_accumulate_geometry", "sfb_accumulate_export", "sfb_accumulate_merge", "sfb_accumulate_compact",
            "sfb_accumulate_fetch", "sfb_accumulate_launches", "sfb_accumulate_free", "sfb_microbench", "sfb_set_stream", "sfb_set_engines"]
@@ -71,6 +71,7 @@ def load_library():
         L.sfb_init.argtypes = [C.c_int, C.c_char_p]
         L.sfb_fold_batch.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(Model), C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_void_p]
+        L.sfb_fold_long.argtypes = [C.c_void_p, C.c_int, C.POINTER(Model), C.c_void_p, C.c_void_p, C.c_void_p]
         L.sfb_pf_batch.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(Model), C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.sfb_deigan.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_void_p]
@@ -189,6 +190,24 @@ def fold_batch(seqs, hc=None, sc=None, structure=False, temperature=37.0, max_sp
                                          scm.ctypes.data if scm is not None else None, e.ctypes.data,
                                          pt.ctypes.data if structure else None))
     return e, pt
+
+
+def fold_long(seq, hc=None, temperature=37.0, max_span=0):
+    """MFE and structure of one whole sequence (the full-length folds of --global_refold, ScanFold.py:1518-1539) on the
+    blocked kernel.  hc: constraint line (shorter lines are padded with '.') or None.  -> (energy dcal, int32 pair table)."""
+    ensure_init()
+    a = np.frombuffer(seq.encode() if isinstance(seq, str) else bytes(seq), dtype=np.uint8).copy()
+    n = len(a)
+    h = None
+    if hc is not None:
+        hb = (hc.encode() if isinstance(hc, str) else bytes(hc))[:n]
+        h = np.frombuffer(hb + b"." * (n - len(hb)), dtype=np.uint8).copy()
+    e = np.zeros(1, dtype=np.int32)
+    pt = np.zeros(n, dtype=np.int32)
+    m = _model(temperature, max_span)
+    _check(load_library().sfb_fold_long(a.ctypes.data, n, C.byref(m), h.ctypes.data if h is not None else None,
+                                        e.ctypes.data, pt.ctypes.data))
+    return int(e[0]), pt
 
 
 def pf_batch(seqs, hc=None, sc=None, want_bpp=False, temperature=37.0, max_span=0):

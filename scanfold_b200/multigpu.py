@@ -166,7 +166,9 @@ def gather_window_tables(table, rank, world, dist, with_shuffle_energies=False):
     cols = _WINDOW_COLUMNS + (("shuffle_dcal",) if with_shuffle_energies else ())
     fin = table.final
     extra = np.array([[1.0, fin["mfe"], fin["z"], fin["p"], fin["ed"]]] if fin is not None else np.zeros((0, 5)))
-    parts = gather_arrays([np.asarray(getattr(table, k)) for k in cols] + [extra], rank, world, dist)
+    alln = np.asarray(table.alln, dtype=np.uint8) if getattr(table, "alln", None) is not None \
+        else np.zeros(len(table.start1), dtype=np.uint8)
+    parts = gather_arrays([np.asarray(getattr(table, k)) for k in cols] + [alln, extra], rank, world, dist)
     if rank != 0:
         return None
     res = WindowTable()
@@ -175,6 +177,8 @@ def gather_window_tables(table, rank, world, dist, with_shuffle_energies=False):
         setattr(res, k, np.concatenate([p[n] for p in parts]))
     if not with_shuffle_energies:
         res.shuffle_dcal = None
+    alln_all = np.concatenate([p[-2] for p in parts]).astype(bool)
+    res.alln = alln_all if alln_all.any() else None
     fins = [p[-1] for p in parts if len(p[-1])]
     res.final = dict(zip(("mfe", "z", "p", "ed"), (float(x) for x in fins[-1][0][1:]))) if fins else None
     return res

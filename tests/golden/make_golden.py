@@ -61,6 +61,14 @@ CASES = {
     # C1 geometry (BASELINE.json configs[0]: 120-nt window, step 1, 100 mono shuffles) on a 400-nt record: pins the host
     # pipeline where the r = 100 z-score rounding and the exact-mean paths matter
     "c1_w120_r100": dict(L=400, seed=19, args=["-w", "120", "-r", "100"]),
+    # f3 flag surface and quirks
+    "by_ed_w40": dict(L=150, seed=21, args=["-w", "40", "-r", "10", "--by_ed"]),
+    "c0_w40": dict(L=150, seed=22, args=["-w", "40", "-r", "10", "-c", "0"], expect_fail="FileNotFoundError"),
+    "refold_w40": dict(L=170, seed=23, args=["-w", "40", "-r", "10", "--global_refold"]),
+    "print_random_w40": dict(L=90, seed=24, args=["-w", "40", "-r", "6", "--print_random"], stdout=True),
+    # Q10: runs of N -- 130 (every nucleotide still covered by partly-N windows) and 260 (22 nucleotides left without a record)
+    "q10_n130_w120": dict(L=0, seed=25, args=["-w", "120", "-r", "6"], nrun=(150, 130, 140)),
+    "q10_n260_w120": dict(L=0, seed=26, args=["-w", "120", "-r", "6"], nrun=(140, 260, 135)),
     "dna_name_w30": dict(L=100, seed=17, alpha="ACGT", args=["-w", "30", "-r", "8", "--name", "chrTest"],
                          header="rec17|extra|fields"),
 }
@@ -68,6 +76,9 @@ CASES = {
 
 def make_case(name, spec):
     rng = random.Random(spec["seed"])
+    if spec.get("nrun"):
+        a, b, c = spec["nrun"]
+        spec = dict(spec, seq=rand_seq(rng, a) + "N" * b + rand_seq(rng, c))
     seq = spec.get("seq") or rand_seq(rng, spec["L"], spec.get("alpha", "ACGU"))
     header = spec.get("header", name)
     work = tempfile.mkdtemp(prefix="golden_")
@@ -101,7 +112,11 @@ def make_case(name, spec):
     env["SCANFOLD_GOLDEN_TRACE"] = trace_path
     cmd = [sys.executable, "-W", "ignore", os.path.join(REF, "ScanFold.py"), "input.fa"] + args
     p = subprocess.run(cmd, cwd=work, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
-    if p.returncode != 0:
+    if spec.get("expect_fail"):
+        if p.returncode == 0 or spec["expect_fail"] not in p.stdout:
+            print(p.stdout[-3000:])
+            raise SystemExit("reference run was expected to die with %s for %s" % (spec["expect_fail"], name))
+    elif p.returncode != 0:
         print(p.stdout[-3000:])
         raise SystemExit("reference run failed for " + name)
     rec = header.split("|")[0]
@@ -125,7 +140,13 @@ def make_case(name, spec):
     ed = np.zeros(n)
     dG = np.zeros(n)
     pos = 0
+    alln = np.zeros(n, dtype=bool)
     for w in range(n):
+        start = w * step if w < nwin else L - W
+        frag = seq[start:start + W]
+        if (w < nwin and W == 120 and frag == "N" * 120) or (w == nwin and frag == "N" * W):
+            alln[w] = True                       # Q10: the reference never folds this window
+            continue
         grp = trace[pos:pos + r + 3]
         pos += r + 3
         ops = [g["op"] for g in grp]
@@ -139,6 +160,11 @@ def make_case(name, spec):
         for k in range(r):
             she[w, k] = grp[3 + k]["e"]
             shuf[w, k] = np.frombuffer(grp[3 + k]["seq"].encode(), dtype=np.uint8)
+    if "--global_refold" in args:            # three full-length folds (ScanFold.py:1518-1539)
+        assert [g["op"] for g in trace[pos:pos + 3]] == ["mfe"] * 3, (name, "refold trace")
+        pos += 3
+    if spec.get("expect_fail"):
+        assert pos == len(trace), (name, "ops after the failure point")
     # ---- motif step (ScanFold.py:1724-1750): per motif pf (hc), pf (RNA.pf_fold), mfe (hc), then native + 100 shuffles
     motif_shuffles = {}
     k_motif = 0
@@ -157,7 +183,7 @@ def make_case(name, spec):
     for fn, path in aux.items():
         shutil.copy(path, os.path.join(dst, fn))
     np.savez_compressed(os.path.join(dst, "trace.npz"), shuffles=shuf, mfe_dcal=mfe, native_unconstrained_dcal=nat,
-                        shuffle_dcal=she, pair_tbl=pair_tbl, centroid_tbl=cen_tbl, ed=ed, ensemble_dG=dG, **motif_shuffles)
+                        shuffle_dcal=she, pair_tbl=pair_tbl, centroid_tbl=cen_tbl, ed=ed, ensemble_dG=dG, alln=alln, **motif_shuffles)
     kept = []
     for fn in sorted(os.listdir(outdir)):
         if fn.endswith(".ps"):
@@ -165,8 +191,13 @@ def make_case(name, spec):
         shutil.copy(os.path.join(outdir, fn), os.path.join(dst, "expected", fn))
         kept.append(fn)
     rel_args = [("constraints.dbn" if a == aux.get("constraints.dbn") else a) for a in args]
+    extra = {}
+    if spec.get("stdout"):                   # what the reference printed per window (--print_random energy lists)
+        extra["stdout_lists"] = [ln for ln in p.stdout.split("\n") if ln.startswith("[")]
+    if spec.get("expect_fail"):
+        extra["expect_fail"] = spec["expect_fail"]
     json.dump({"name": name, "args": rel_args, "record": rec, "L": L, "W": W, "step": step, "r": r,
-               "n_windows": nwin, "files": kept, "python": sys.version.split()[0]},
+               "n_windows": nwin, "files": kept, "python": sys.version.split()[0], **extra},
               open(os.path.join(dst, "case.json"), "w"), indent=1)
     shutil.rmtree(work)
     print("%-14s windows=%d files=%d" % (name, nwin, len(kept)))

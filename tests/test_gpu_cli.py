@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("name", CASES)
-def test_cli_outputs_byte_identical(name, tmp_path, monkeypatch, engine):
+def test_cli_outputs_byte_identical(name, tmp_path, monkeypatch, engine, capsys):
     from scanfold_b200 import cli
     d = os.path.join(GOLDEN, name)
     case = json.load(open(os.path.join(d, "case.json")))
@@ -22,7 +22,15 @@ def test_cli_outputs_byte_identical(name, tmp_path, monkeypatch, engine):
             shutil.copy(os.path.join(d, f), tmp_path / f)
     args = [a if a != "constraints.dbn" else str(tmp_path / "constraints.dbn") for a in case["args"]]
     monkeypatch.chdir(tmp_path)
-    cli.main(["input.fa"] + args + ["--parity_shuffles", "trace.npz"])
+    argv = ["input.fa"] + args + ["--parity_shuffles", "trace.npz"]
+    if case.get("expect_fail"):             # -c 0: the reference writes the .dp files, then dies opening a dbn file
+        with pytest.raises(FileNotFoundError):
+            cli.main(argv)
+    else:
+        cli.main(argv)
+    if case.get("stdout_lists"):            # --print_random: the energy list of every window, as the reference prints it
+        printed = [ln for ln in capsys.readouterr().out.split("\n") if ln.startswith("[")]
+        assert printed == case["stdout_lists"]
     out = tmp_path / case["record"]
     exp_dir = os.path.join(d, "expected")
     exp = sorted(os.listdir(exp_dir))          # scan, ScanFold-Fold and structure-extraction outputs

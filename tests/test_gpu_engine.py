@@ -413,3 +413,44 @@ def test_blocked_kernel_long_windows(engine, oracle, W):
                 continue
             eo, so = oracle.mfe(seqs[k], **okw)
             assert got[name][0][k] == eo and db_from_pt(got[name][1][k]) == so, (name, W, k)
+
+
+def _nested_constraint(rng, n, n_pairs):
+    """a constraint line with nested / side-by-side enforced pairs '(' ')' plus a few 'x' flags"""
+    hc = ["."] * n
+    free = [(0, n - 1)]
+    for _ in range(n_pairs):
+        if not free:
+            break
+        lo, hi = free.pop(rng.randrange(len(free)))
+        if hi - lo < 12:
+            continue
+        i = rng.randrange(lo, lo + (hi - lo) // 3)
+        j = rng.randrange(hi - (hi - lo) // 3, hi + 1)
+        if j - i < 5:
+            continue
+        hc[i], hc[j] = "(", ")"
+        free += [(lo, i - 1), (i + 1, j - 1), (j + 1, hi)]
+    for k in range(n):
+        if hc[k] == "." and rng.random() < 0.03:
+            hc[k] = "x"
+    return "".join(hc)
+
+
+@pytest.mark.parametrize("n", [70, 700, 2000])
+def test_whole_sequence_fold(engine, oracle, n):
+    """sfb_fold_long (the full-length folds of --global_refold, ScanFold.py:1518-1539): unconstrained and with a dbn-like
+    constraint line of enforced pairs, against the oracle -- energy and structure, 32-bit pair table."""
+    rng = random.Random(n)
+    seq = rand_seqs(31337 + n, 1, n)[0]
+    hc = _nested_constraint(rng, n, 60)
+    for h in (None, hc, hc[:n - 7]):                 # a shorter line constrains the leading positions only
+        e, pt = engine.fold_long(seq, hc=h)
+        full = None if h is None else h + "." * (n - len(h))
+        eo, so = oracle.mfe(seq, hc=full)
+        assert e == eo, (n, h is not None)
+        assert db_from_pt(pt) == so
+        if h is not None:
+            for k, ch in enumerate(full):
+                if ch == "x":
+                    assert pt[k] == 0
