@@ -248,7 +248,7 @@ def result_sha(ptable, table):
     Identical for every N (integer / exact-sum accumulators, shuffles keyed by absolute window index)."""
     import hashlib
     h = hashlib.sha256()
-    for a in (ptable.nt_ptr, ptable.partner, ptable.count, ptable.first_seen, ptable.sums):
+    for a in (ptable.nt_ptr, ptable.coord, ptable.partner, ptable.count, ptable.first_seen, ptable.sums):
         h.update(np.ascontiguousarray(a, dtype=np.int64).tobytes())
     for a, dt in ((table.mfe_dcal, np.int64), (table.native_unconstrained_dcal, np.int64), (table.z, np.float64),
                   (table.p, np.float64), (table.ed, np.float64), (table.pair_tbl, np.int16), (table.centroid_tbl, np.int16)):
@@ -325,7 +325,7 @@ def run_ours(args):
         acc = engine.Accumulator(L, W, step, w0, t.pair_tbl, z100, mfe100, ed100)
         try:        # halo rows go to their owners over NCCL; rank 0 gathers the compact partner lists
             own = multigpu.exchange_halo(acc, W, step, rank, world, grp, total)
-            ptable = foldstep.table_from_compact(*acc.compact(0, own))
+            ptable = foldstep.table_from_compact(*acc.compact(0, own), nt0=acc.nt0)
             launches_e2e[0] = acc.n_launches
         finally:
             acc.close()

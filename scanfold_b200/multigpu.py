@@ -113,16 +113,25 @@ def gather_arrays(arrays, rank, world, dist):
     row_bytes = [int(np.prod(a.shape[1:], dtype=np.int64)) * a.dtype.itemsize for a in arrays]
     if rank != 0:
         if len(payload):
-            dist.send(torch.from_numpy(payload).to(dev), 0)
+            t = torch.from_numpy(payload).to(dev)
+            for req in dist.batch_isend_irecv([dist.P2POp(dist.isend, t, 0)]):
+                req.wait()
+            _sync_device([t])
         return None
-    out = [list(arrays)]
+    bufs, ops = [], []
     for p in range(1, world):
         nbytes = int(sum(int(n) * rb for n, rb in zip(all_lens[p], row_bytes)))
-        buf = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        bufs.append(torch.empty(nbytes, dtype=torch.uint8, device=dev))
         if nbytes:
-            dist.recv(buf, p)
+            ops.append(dist.P2POp(dist.irecv, bufs[-1], p))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+        _sync_device(bufs)
+    out = [list(arrays)]
+    for p in range(1, world):
         header = [(a.dtype.str, (int(n),) + a.shape[1:]) for a, n in zip(arrays, all_lens[p])]
-        out.append(_unpack(buf.cpu().numpy(), header))
+        out.append(_unpack(bufs[p - 1].cpu().numpy(), header))
     return out
 
 
@@ -130,26 +139,26 @@ def gather_tables(table, rank, world, dist):
     """per-rank PartnerTable over consecutive nucleotide ranges -> the whole table on rank 0 (None elsewhere)"""
     if world == 1:
         return table
-    parts = gather_arrays([np.diff(table.nt_ptr), table.partner, table.count, table.first_seen,
+    parts = gather_arrays([np.diff(table.nt_ptr), table.coord, table.partner, table.count, table.first_seen,
                            np.ascontiguousarray(table.sums.T)], rank, world, dist)
     if rank != 0:
         return None
     tabs = []
-    for nparts, partner, count, first, sums_t in parts:
+    for nparts, coord, partner, count, first, sums_t in parts:
         ptr = np.concatenate([[0], np.cumsum(nparts)])
-        tabs.append(foldstep.PartnerTable(ptr, partner, count, first, sums_t.T))
+        tabs.append(foldstep.PartnerTable(ptr, partner, count, first, sums_t.T, coord))
     return foldstep.concat_tables(tabs)
 
 
 def empty_table():
     z = np.zeros(0, dtype=np.int64)
-    return foldstep.PartnerTable(np.zeros(1, dtype=np.int64), z, z, z, np.zeros((6, 0), dtype=np.int64))
+    return foldstep.PartnerTable(np.zeros(1, dtype=np.int64), z, z, z, np.zeros((6, 0), dtype=np.int64), z)
 
 
 def partner_table_distributed(acc, W, step, rank, world, dist, total_windows):
     """halo exchange + compaction of the owned nucleotides + gather on rank 0"""
     own = exchange_halo(acc, W, step, rank, world, dist, total_windows)
-    table = foldstep.table_from_compact(*acc.compact(0, own)) if acc is not None and own > 0 else empty_table()
+    table = foldstep.table_from_compact(*acc.compact(0, own), nt0=acc.nt0) if acc is not None and own > 0 else empty_table()
     return gather_tables(table, rank, world, dist)
 
 

@@ -42,7 +42,7 @@ WORKER = textwrap.dedent("""
             assert np.array_equal(getattr(whole_w, k), getattr(table, k)[:n]), k
         assert whole_w.final == table.final
         whole = foldstep.table_from_compact(*accumulate_numpy(case["L"], W, step, 0, table.pair_tbl, z100, mfe100, ed100))
-        for name in ("nt_ptr", "partner", "count", "first_seen", "sums"):
+        for name in ("nt_ptr", "coord", "partner", "count", "first_seen", "sums"):
             assert np.array_equal(getattr(merged, name), getattr(whole, name)), name
         print("MERGE_OK", len(merged.partner))
     dist.destroy_process_group()
