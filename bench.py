@@ -240,16 +240,20 @@ def workload_config(name, n_gpus):
             "record_nt": L, "window": W, "step": step, "shuffles": r, "shuffle_type": stype,
             "seed": seed, "l2": "flushed between steps (256 MiB write)",
             "parallelism": "windows of the one record sharded by range over %d GPU(s); accumulator halo rows over NCCL "
-                           "send/recv, compact tables gathered on rank 0" % n_gpus}
+                           "send/recv; every rank aggregates the nucleotides it owns, rank 0 gathers the per-nucleotide "
+                           "results and the window columns" % n_gpus}
 
 
-def result_sha(ptable, table):
-    """Digest of what a run produces before the writers: merged per-nucleotide partner table and per-window columns.
+def result_sha(agg, table_digest, table):
+    """Digest of what a run produces before the writers: the per-nucleotide ScanFold-Fold results (best partner and its
+    metrics), an order-independent checksum of the merged partner table, and the per-window columns.
     Identical for every N (integer / exact-sum accumulators, shuffles keyed by absolute window index)."""
     import hashlib
     h = hashlib.sha256()
-    for a in (ptable.nt_ptr, ptable.coord, ptable.partner, ptable.count, ptable.first_seen, ptable.sums):
-        h.update(np.ascontiguousarray(a, dtype=np.int64).tobytes())
+    h.update(np.uint64(table_digest).tobytes())
+    for a, dt in ((agg.coord, np.int64), (agg.part, np.int64), (agg.cov_z, np.float64), (agg.mean_z, np.float64),
+                  (agg.mean_mfe, np.float64), (agg.mean_ed, np.float64), (agg.total_windows, np.int64), (agg.num_bp, np.int64)):
+        h.update(np.ascontiguousarray(a, dtype=dt).tobytes())
     for a, dt in ((table.mfe_dcal, np.int64), (table.native_unconstrained_dcal, np.int64), (table.z, np.float64),
                   (table.p, np.float64), (table.ed, np.float64), (table.pair_tbl, np.int16), (table.centroid_tbl, np.int16)):
         h.update(np.ascontiguousarray(a, dtype=dt).tobytes())
@@ -323,20 +327,20 @@ def run_ours(args):
         tt.append(time.perf_counter())
         z100, mfe100, ed100 = pipeline.fold_inputs(t)
         acc = engine.Accumulator(L, W, step, w0, t.pair_tbl, z100, mfe100, ed100)
-        try:        # halo rows go to their owners over NCCL; rank 0 gathers the compact partner lists
-            own = multigpu.exchange_halo(acc, W, step, rank, world, grp, total)
-            ptable = foldstep.table_from_compact(*acc.compact(0, own), nt0=acc.nt0)
+        try:        # halo rows go to their owners over NCCL; every rank keeps the nucleotides it owns
+            ptable = multigpu.own_partner_table(acc, W, step, rank, world, grp, total)
             launches_e2e[0] = acc.n_launches
         finally:
             acc.close()
         tt.append(time.perf_counter())
-        whole = multigpu.gather_tables(ptable, rank, world, grp)
+        # ScanFold.py:1051-1260 on the owned nucleotides; rank 0 gathers the per-nucleotide results and the window columns
+        agg, _, _ = multigpu.aggregate_distributed(ptable, seq, rank, world, grp)
         wtable = multigpu.gather_window_tables(t, rank, world, grp)
         tt.append(time.perf_counter())
         if trace and rank == 0:
-            sys.stderr.write("e2e step: scan_record %.1f ms (device %.1f), accumulate %.1f ms, gather %.1f ms\n" % (
+            sys.stderr.write("e2e step: scan_record %.1f ms (device %.1f), accumulate %.1f ms, aggregate + gather %.1f ms\n" % (
                 (tt[1] - tt[0]) * 1e3, t.ms_total, (tt[2] - tt[1]) * 1e3, (tt[3] - tt[2]) * 1e3))
-        return t, ptable, whole, wtable, [b - a for a, b in zip(tt, tt[1:])]
+        return t, ptable, agg, wtable, [b - a for a, b in zip(tt, tt[1:])]
 
     launches_e2e = [0]
     e2e_steps = args.e2e_steps if args.e2e_steps else min(args.steps, 6)
@@ -346,10 +350,11 @@ def run_ours(args):
     parts = np.zeros(3)
     for _ in range(e2e_steps):
         flush.zero_()
-        t, own_table, whole, wtable, dts = e2e_step()
+        t, own_table, agg, wtable, dts = e2e_step()
         parts += dts
     barrier()
     ms_e2e = (time.perf_counter() - t0) * 1e3
+    table_digest = multigpu.table_checksum(own_table, rank, world, grp)      # outside the timed region
     n_slots = nwin + (1 if final else 0)
     h2d = L + nwin * W * 2 + nwin * 12
     d2h = n_slots * (4 + 4 + 4 * r + 2 * W + 2 * W + 8 + 8) + len(own_table.partner) * 60 + own_table.n_nt * 4
@@ -388,12 +393,12 @@ def run_ours(args):
             "scaling": "strong", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
             "config": workload_config(args.workload, world),
             "folds_per_s": value * folds_per_window, "dp_cells_per_s": value * folds_per_window * cells,
-            "result_sha": result_sha(whole, wtable),
+            "result_sha": result_sha(agg, table_digest, wtable),
             "e2e": {"value": e2e, "unit": "windows/s", "h2d_bytes_per_step": int(h2d_all), "d2h_bytes_per_step": int(d2h_all),
                     "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps,
                     "rank0_ms_per_step": {"scan_record": parts[0] / e2e_steps * 1e3,
                                           "accumulate_halo_compact": parts[1] / e2e_steps * 1e3,
-                                          "gather_to_rank0": parts[2] / e2e_steps * 1e3}},
+                                          "aggregate_and_gather_to_rank0": parts[2] / e2e_steps * 1e3}},
             "gpu_launches": int(total_launches), "gpu_launches_e2e_per_step": int(t.n_launches + launches_e2e[0]),
             "roofline": {"bound": "int_alu", "kernel": "mfe3_kernel (+ int32 redo of flagged folds)", "achieved": achieved / 1e9,
                          "peak": peak_addmin / 1e9, "unit": "G add-min/s", "frac": achieved / peak_addmin,

@@ -272,10 +272,12 @@ def run_record(args, record_name, raw_seq, original_directory, dist=None):
         else:                  # more ranks than windows: this rank only takes part in the collectives
             shard = scan.empty_table(W, step, r, w0)
         try:
-            ptable = multigpu.partner_table_distributed(acc, W, step, rank, world, dist, total)
+            own_table = multigpu.own_partner_table(acc, W, step, rank, world, dist, total)
         finally:
             if acc is not None:
                 acc.close()
+        # every rank aggregates the nucleotides it owns; rank 0 gets the per-nucleotide results and the log text
+        aggregated = multigpu.aggregate_distributed(own_table, seq, rank, world, dist, by_ed=bool(args.by_ed), with_logs=True)
         table = multigpu.gather_window_tables(shard, rank, world, dist, with_shuffle_energies=bool(args.print_random))
         if rank != 0:
             return
@@ -283,9 +285,9 @@ def run_record(args, record_name, raw_seq, original_directory, dist=None):
         minz = pipeline.write_scan_outputs(seq, table, names, int(args.t), step)   # Sequence column keeps input case (Q11)
         print("Elapsed time: %ss" % round(time.time() - t0, 2))
         print("Determining best base pairs...")
-        pipeline.write_fold_outputs(seq, ptable, names, minz, step, by_ed=bool(args.by_ed), competition=int(args.c),
+        pipeline.write_fold_outputs(seq, None, names, minz, step, by_ed=bool(args.by_ed), competition=int(args.c),
                                     zscores=pipeline.zscore_total(table), filter_value=int(args.f),
-                                    input_filename=args.filename)
+                                    input_filename=args.filename, aggregated=aggregated)
         if args.global_refold:
             global_refold(seq, names, args.name, float(args.t), args.span or 0)
         # structure extraction: refold every top-level helix of the Zavg < -2 structure (ScanFold.py:1557-1781)

@@ -136,8 +136,8 @@ def aggregate(table, seq, log_total=None, sirna_log=None, by_ed=False):
     res.mean_z = mean_z[best]
     res.mean_mfe = mean_mfe[best]
     res.mean_ed = mean_ed[best]
-    res.total_windows = total_windows
-    res.num_bp = num_bp
+    res.total_windows = np.asarray(total_windows, dtype=np.int64)
+    res.num_bp = np.asarray(num_bp, dtype=np.int64)
     return res
 
 

@@ -155,11 +155,65 @@ def empty_table():
     return foldstep.PartnerTable(np.zeros(1, dtype=np.int64), z, z, z, np.zeros((6, 0), dtype=np.int64), z)
 
 
-def partner_table_distributed(acc, W, step, rank, world, dist, total_windows):
-    """halo exchange + compaction of the owned nucleotides + gather on rank 0"""
+def own_partner_table(acc, W, step, rank, world, dist, total_windows):
+    """halo exchange + compaction: the complete partner lists of the nucleotides this rank owns"""
     own = exchange_halo(acc, W, step, rank, world, dist, total_windows)
-    table = foldstep.table_from_compact(*acc.compact(0, own), nt0=acc.nt0) if acc is not None and own > 0 else empty_table()
-    return gather_tables(table, rank, world, dist)
+    return foldstep.table_from_compact(*acc.compact(0, own), nt0=acc.nt0) if acc is not None and own > 0 else empty_table()
+
+
+def partner_table_distributed(acc, W, step, rank, world, dist, total_windows):
+    """halo exchange + compaction of the owned nucleotides + gather of the whole table on rank 0"""
+    return gather_tables(own_partner_table(acc, W, step, rank, world, dist, total_windows), rank, world, dist)
+
+
+_RESULT_FIELDS = ("coord", "part", "cov_z", "mean_z", "mean_mfe", "mean_ed", "total_windows", "num_bp")
+
+
+def aggregate_distributed(table, seq, rank, world, dist, by_ed=False, with_logs=False):
+    """ScanFold.py:1051-1260 sharded: every rank aggregates the nucleotides it owns (their partner lists are complete after
+    the halo exchange) and rank 0 gathers the per-nucleotide results -- 64 bytes per nucleotide instead of the 80-byte
+    entries of the whole partner table -- plus, for the CLI, the log text each rank produced for its rows.
+    -> (NtResult, log text, pair-count text) on rank 0, (None, None, None) elsewhere."""
+    import io
+    log_total, sirna = (io.StringIO(), io.StringIO()) if with_logs else (None, None)
+    res = foldstep.aggregate(table, seq, log_total, sirna, by_ed=by_ed)
+    if world == 1:
+        return res, (log_total.getvalue() if with_logs else None), (sirna.getvalue() if with_logs else None)
+    arrays = [np.asarray(getattr(res, k)) for k in _RESULT_FIELDS]
+    if with_logs:
+        arrays += [np.frombuffer(log_total.getvalue().encode(), dtype=np.uint8),
+                   np.frombuffer(sirna.getvalue().encode(), dtype=np.uint8)]
+    parts = gather_arrays(arrays, rank, world, dist)
+    if rank != 0:
+        return None, None, None
+    out = foldstep.NtResult()
+    for n, k in enumerate(_RESULT_FIELDS):
+        setattr(out, k, np.concatenate([p[n] for p in parts]))
+    out.n_nt = len(out.coord)
+    if not with_logs:
+        return out, None, None
+    return (out, "".join(p[-2].tobytes().decode() for p in parts), "".join(p[-1].tobytes().decode() for p in parts))
+
+
+def table_checksum(table, rank, world, dist):
+    """Order-independent 64-bit digest of a partner table spread over the ranks (sum of per-entry hashes mod 2^64, all-
+    reduced): equal for any sharding iff the merged tables are equal entry by entry.  bench.py prints it in result_sha."""
+    own = np.repeat(table.coord, np.diff(table.nt_ptr)).astype(np.uint64)
+    with np.errstate(over="ignore"):
+        h = own * np.uint64(0x9E3779B97F4A7C15)
+        for k, a in enumerate([table.partner, table.count, table.first_seen] + list(table.sums)):
+            h = (h ^ (h >> np.uint64(29))) * np.uint64(0xBF58476D1CE4E5B9) + np.asarray(a).astype(np.int64).view(np.uint64) * np.uint64(2 * k + 3)
+        h = (h ^ (h >> np.uint64(32))) * np.uint64(0x94D049BB133111EB)
+        total = int(h.sum(dtype=np.uint64)) if len(h) else 0
+    if world > 1:
+        import torch
+        dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+        # two 32-bit halves: int64 all-reduce sums cannot wrap, the wrap is applied afterwards
+        t = torch.tensor([total & 0xFFFFFFFF, total >> 32], dtype=torch.int64, device=dev)
+        dist.all_reduce(t)
+        lo, hi = (int(x) for x in t.tolist())
+        total = (lo + (hi << 32)) & 0xFFFFFFFFFFFFFFFF
+    return total
 
 
 _WINDOW_COLUMNS = ("start1", "end1", "mfe_dcal", "mfe", "z", "p", "ed", "pair_tbl", "centroid_tbl",

@@ -79,16 +79,23 @@ def write_scan_outputs(seq, table, names, temperature, step):
 
 
 def write_fold_outputs(seq, ptable, names, minz, step, by_ed=False, competition=1, zscores=None, filter_value=-2,
-                       input_filename=""):
+                       input_filename="", aggregated=None):
     """ScanFold-Fold: logs, CT / dbn / bp / wig / fasta files (ScanFold.py:1036-1500,1554).  Returns (agg, final).
     by_ed: --by_ed (ED-weighted partner choice and log names, :380-385,1190-1215).  competition = 0: the -c 0 branch
-    (:1454-1466): .dp files instead of CT / dbn / bp, then the reference dies opening the missing dbn file -- so do we."""
+    (:1454-1466): .dp files instead of CT / dbn / bp, then the reference dies opening the missing dbn file -- so do we.
+    aggregated: (NtResult, log text, pair-count text) when the ranks of a multi-GPU run aggregated their own nucleotides
+    (multigpu.aggregate_distributed); ptable is not needed then."""
     import statistics
     o = names.outname
     tag = ".ScanFold.ED-weighted" if by_ed else ".ScanFold"
     with open(o + tag + ".log", "w") as log_total, open(o + ".ntPairCounts.log", "w") as sirna:
         sirna.write("i\tnuc\twindows\tbps\n")
-        agg = foldstep.aggregate(ptable, seq, log_total, sirna, by_ed=by_ed)
+        if aggregated is not None:
+            agg = aggregated[0]
+            log_total.write(aggregated[1])
+            sirna.write(aggregated[2])
+        else:
+            agg = foldstep.aggregate(ptable, seq, log_total, sirna, by_ed=by_ed)
     key = agg.coord
     if competition == 0:
         with open(o + tag + ".FinalPartners.txt", "w") as log_win:

@@ -28,7 +28,10 @@ WORKER = textwrap.dedent("""
     w0, w1 = multigpu.shard_windows(n, world, rank)
     acc = NumpyAccumulator(case["L"], W, step, w0, table.pair_tbl[w0:w1], z100[w0:w1], mfe100[w0:w1], ed100[w0:w1]) \
         if w1 > w0 else None
-    merged = multigpu.partner_table_distributed(acc, W, step, rank, world, dist, n)
+    own_table = multigpu.own_partner_table(acc, W, step, rank, world, dist, n)
+    agg, log_text, cnt_text = multigpu.aggregate_distributed(own_table, case["seq"], rank, world, dist, with_logs=True)
+    digest = multigpu.table_checksum(own_table, rank, world, dist)
+    merged = multigpu.gather_tables(own_table, rank, world, dist)
     # the per-window columns travel as flat byte tensors too (no pickled objects)
     from scanfold_b200 import scan
     shard = scan.empty_table(W, step, table.r, w0)
@@ -44,6 +47,14 @@ WORKER = textwrap.dedent("""
         whole = foldstep.table_from_compact(*accumulate_numpy(case["L"], W, step, 0, table.pair_tbl, z100, mfe100, ed100))
         for name in ("nt_ptr", "coord", "partner", "count", "first_seen", "sums"):
             assert np.array_equal(getattr(merged, name), getattr(whole, name)), name
+        # every rank aggregated its own nucleotides: results and log text equal the single-process aggregation
+        import io
+        lt, st = io.StringIO(), io.StringIO()
+        ref = foldstep.aggregate(whole, case["seq"], lt, st)
+        for name in ("coord", "part", "cov_z", "mean_z", "mean_mfe", "mean_ed", "total_windows", "num_bp"):
+            assert np.array_equal(getattr(agg, name), getattr(ref, name)), name
+        assert log_text == lt.getvalue() and cnt_text == st.getvalue()
+        assert digest == multigpu.table_checksum(whole, 0, 1, None)
         print("MERGE_OK", len(merged.partner))
     dist.destroy_process_group()
 """)
