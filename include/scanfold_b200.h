@@ -32,7 +32,7 @@ extern "C" {
 
 /* RNA.md(): only what the reference sets -- ScanFold.py:212-215, ScanFoldFunctions.py:776-777 */
 typedef struct sfb_model {
-    double temperature; /* md.temperature (C); only 37 is supported by the built-in table */
+    double temperature; /* md.temperature (C); tables are rescaled from the 37 C values and the enthalpies of the file */
     int32_t max_bp_span; /* md.max_bp_span; <=0 = unlimited */
 } sfb_model;
 
@@ -100,6 +100,9 @@ typedef struct sfb_scan_args {
     int32_t first_window, n_windows; /* shard: window indices [first_window, first_window+n_windows) */
     int32_t final_window;            /* 1: also evaluate the extra final-window set (Q5) as slot n_windows */
     int32_t want_pf;                 /* 1: partition function / ED / centroid per window */
+    double background_temperature;   /* md.temperature of the r + 1 background folds (rna_folder, ScanFoldFunctions.py:776-777);
+                                      * 0 = the same as model.temperature.  They differ in the motif step, where the native
+                                      * fold uses the default 37 C compound and energies() gets -t (ScanFold.py:1733,1748) */
 } sfb_scan_args;
 
 typedef struct sfb_scan_out { /* caller-allocated; n = n_windows (+1 if final_window) */

@@ -30,6 +30,7 @@ def lib():
         L = C.CDLL(_SO)
         L.sfo_load_params.argtypes = [C.c_char_p]
         L.sfo_last_error.restype = C.c_char_p
+        L.sfo_set_temperature.argtypes = [C.c_double]
         L.sfo_mfe.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_void_p, C.c_int, C.c_char_p]
         L.sfo_eval.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_void_p]
         L.sfo_pf.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_void_p, C.c_int, C.c_double,
@@ -59,9 +60,16 @@ def _sc_ptr(sc_stack):
     return a, a.ctypes.data
 
 
-def mfe(seq, hc=None, sc_stack=None, max_span=0, structure=True):
+def set_temperature(temperature):
+    """md.temperature for every later call (tables rescaled from the 37 C values and the enthalpies)"""
+    if lib().sfo_set_temperature(float(temperature)) != 0:
+        raise RuntimeError("oracle: " + lib().sfo_last_error().decode())
+
+
+def mfe(seq, hc=None, sc_stack=None, max_span=0, structure=True, temperature=37.0):
     """-> (energy_dcal, dot-bracket or None).  sc_stack: 1-based int array of length n+1."""
     L = lib()
+    set_temperature(temperature)
     n = len(seq)
     buf = C.create_string_buffer(n + 1) if structure else None
     keep, scp = _sc_ptr(sc_stack)
@@ -105,8 +113,9 @@ def deigan(react1, m, b):
     return out
 
 
-def fold_batch(seqs, n_threads=1, fast=False):
+def fold_batch(seqs, n_threads=1, fast=False, temperature=37.0):
     """seqs: uint8/bytes array [n_seq, len] of ASCII -> int32 energies (dcal).  fast: the tuned CPU path."""
+    set_temperature(temperature)
     a = np.ascontiguousarray(seqs, dtype=np.uint8)
     n_seq, ln = a.shape
     out = np.zeros(n_seq, dtype=np.int32)
@@ -117,6 +126,7 @@ def fold_batch(seqs, n_threads=1, fast=False):
 
 
 def pf_batch(seqs, n_threads=1):
+    set_temperature(37.0)
     a = np.ascontiguousarray(seqs, dtype=np.uint8)
     n_seq, ln = a.shape
     ed = np.zeros(n_seq, dtype=np.float64)

@@ -157,6 +157,214 @@ static int read_special(toks_t *t, const char *name, special_loop *dst, int *n) 
     return 1;
 }
 
+/* one table set: suf "" = free energies at 37 C, "_enthalpies" = enthalpies; col 0 / 1 picks the value / its enthalpy in
+ * the blocks that interleave them (ML_params, NINIO, Misc, special loops) */
+static int read_special_col(toks_t *t, int col, const char *name, special_loop *dst, int *n) {
+    *n = 0;
+    if (!seek_block(t, name)) return 1; /* optional */
+    while (t->pos + 2 < t->n + 1 && t->pos < t->n && isalpha((unsigned char)t->tok[t->pos][0]) &&
+           strcmp(t->tok[t->pos], "INF")) {
+        if (*n >= 64) break;
+        strncpy(dst[*n].seq, t->tok[t->pos], 9);
+        dst[*n].seq[9] = 0;
+        dst[*n].e = atoi(t->tok[t->pos + 1 + col]);
+        t->pos += 3;
+        (*n)++;
+    }
+    return 1;
+}
+
+static int read_set(toks_t *t, const char *suf, int col, params_t *Q) {
+    char nmbuf[8][64];
+    int nmi = 0;
+#define nm(x) (snprintf(nmbuf[nmi & 7], 64, "%s%s", x, suf), nmbuf[nmi++ & 7])
+    memset(Q, 0, sizeof *Q);
+    {
+        if (!seek_block(t, nm("stack"))) {
+            set_err("missing stack");
+            return -1;
+        }
+        int ok = 1;
+        for (int a = 1; a <= 7 && ok; a++) ok = read_ints(t, &Q->stack[a][1], 7);
+        if (!ok) {
+            set_err("bad stack");
+            return -1;
+        }
+        if (!read_mm(t, nm("mismatch_hairpin"), Q->mismatchH)) return -1;
+        if (!read_mm(t, nm("mismatch_interior"), Q->mismatchI)) return -1;
+        if (!read_mm(t, nm("mismatch_interior_1n"), Q->mismatch1nI)) return -1;
+        if (!read_mm(t, nm("mismatch_interior_23"), Q->mismatch23I)) return -1;
+        if (!read_mm(t, nm("mismatch_multi"), Q->mismatchM_raw)) return -1;
+        if (!read_mm(t, nm("mismatch_exterior"), Q->mismatchExt_raw)) return -1;
+        if (!seek_block(t, nm("dangle5"))) {
+            set_err("missing dangle5");
+            return -1;
+        }
+        for (int a = 1; a <= 7 && ok; a++) ok = read_ints(t, &Q->dangle5_raw[a][0], 5);
+        if (!seek_block(t, nm("dangle3"))) {
+            set_err("missing dangle3");
+            return -1;
+        }
+        for (int a = 1; a <= 7 && ok; a++) ok = read_ints(t, &Q->dangle3_raw[a][0], 5);
+        if (!seek_block(t, nm("int11"))) {
+            set_err("missing int11");
+            return -1;
+        }
+        for (int a = 1; a <= 7 && ok; a++)
+            for (int b = 1; b <= 7 && ok; b++) ok = read_ints(t, &Q->int11[a][b][0][0], 25);
+        if (!seek_block(t, nm("int21"))) {
+            set_err("missing int21");
+            return -1;
+        }
+        for (int a = 1; a <= 7 && ok; a++)
+            for (int b = 1; b <= 7 && ok; b++)
+                for (int c = 0; c < 5 && ok; c++) ok = read_ints(t, &Q->int21[a][b][c][0][0], 25);
+        if (!seek_block(t, nm("int22"))) {
+            set_err("missing int22");
+            return -1;
+        }
+        for (int a = 1; a <= 6 && ok; a++)
+            for (int b = 1; b <= 6 && ok; b++)
+                for (int c = 1; c <= 4 && ok; c++)
+                    for (int d = 1; d <= 4 && ok; d++)
+                        for (int e = 1; e <= 4 && ok; e++)
+                            ok = read_ints(t, &Q->int22[a][b][c][d][e][1], 4);
+        if (!ok) {
+            set_err("bad int/dangle block");
+            return -1;
+        }
+        if (!seek_block(t, nm("hairpin")) || !read_ints(t, Q->hairpin, 31)) {
+            set_err("bad hairpin");
+            return -1;
+        }
+        if (!seek_block(t, nm("bulge")) || !read_ints(t, Q->bulge, 31)) {
+            set_err("bad bulge");
+            return -1;
+        }
+        if (!seek_block(t, nm("interior")) || !read_ints(t, Q->internal_loop, 31)) {
+            set_err("bad interior");
+            return -1;
+        }
+        int ml[6], nin[3];
+        if (!seek_block(t, "ML_params") || !read_ints(t, ml, 6)) {
+            set_err("bad ML_params");
+            return -1;
+        }
+        Q->MLbase = ml[0 + col];
+        Q->MLclosing = ml[2 + col];
+        Q->MLintern = ml[4 + col];
+        if (!seek_block(t, "NINIO") || !read_ints(t, nin, 3)) {
+            set_err("bad NINIO");
+            return -1;
+        }
+        Q->ninio = nin[col];
+        Q->max_ninio = nin[2];
+        if (!seek_block(t, "Misc")) {
+            set_err("missing Misc");
+            return -1;
+        }
+        int misc[4];
+        if (!read_ints(t, misc, 4)) {
+            set_err("bad Misc");
+            return -1;
+        }
+        Q->DuplexInit = misc[0 + col];
+        Q->TerminalAU = misc[2 + col];
+        Q->lxc = 107.856;
+        if (t->pos < t->n && (isdigit((unsigned char)t->tok[t->pos][0]) || t->tok[t->pos][0] == '-'))
+            Q->lxc = atof(t->tok[t->pos]);
+        read_special_col(t, col, "Hexaloops", Q->hexa, &Q->n_hexa);
+        read_special_col(t, col, "Tetraloops", Q->tetra, &Q->n_tetra);
+        read_special_col(t, col, "Triloops", Q->tri, &Q->n_tri);
+        /* int22 entries touching N (code 0): least favourable of the four nucleotides */
+        for (int a = 1; a <= 6; a++)
+            for (int b = 1; b <= 6; b++)
+                for (int c = 0; c < 5; c++)
+                    for (int d = 0; d < 5; d++)
+                        for (int e = 0; e < 5; e++)
+                            for (int f = 0; f < 5; f++) {
+                                if (c && d && e && f) continue;
+                                int m = -INF;
+                                for (int c2 = (c ? c : 1); c2 <= (c ? c : 4); c2++)
+                                    for (int d2 = (d ? d : 1); d2 <= (d ? d : 4); d2++)
+                                        for (int e2 = (e ? e : 1); e2 <= (e ? e : 4); e2++)
+                                            for (int f2 = (f ? f : 1); f2 <= (f ? f : 4); f2++)
+                                                m = MAX2(m, Q->int22[a][b][c2][d2][e2][f2]);
+                                Q->int22[a][b][c][d][e][f] = m;
+                            }
+    }
+#undef nm
+    return 0;
+}
+
+static params_t P37, PdH; /* what the file holds; P is the working set at g_temperature */
+static double g_temperature = 37.0;
+
+/* ViennaRNA get_scaled_params (md.temperature): E(T) = dH - (dH - E37) * (T + K0) / (37 + K0), truncated to int */
+static void rescale_params(double T) {
+    const int at37 = fabs(T - 37.0) < 1e-9;
+    const double tempf = (T + K0) / (37.0 + K0);
+    P = P37;
+#define RS(field)                                                                                         \
+    do {                                                                                                  \
+        int *d = (int *)&P.field;                                                                         \
+        const int *g = (const int *)&P37.field, *h = (const int *)&PdH.field;                             \
+        for (size_t k = 0; k < sizeof(P.field) / sizeof(int); k++)                                        \
+            d[k] = g[k] >= INF ? INF : (at37 ? g[k] : (int)((double)h[k] - (double)(h[k] - g[k]) * tempf)); \
+    } while (0)
+    RS(stack);
+    RS(hairpin);
+    RS(bulge);
+    RS(internal_loop);
+    RS(mismatchI);
+    RS(mismatchH);
+    RS(mismatch1nI);
+    RS(mismatch23I);
+    RS(mismatchM_raw);
+    RS(mismatchExt_raw);
+    RS(dangle5_raw);
+    RS(dangle3_raw);
+    RS(int11);
+    RS(int21);
+    RS(int22);
+    RS(MLbase);
+    RS(MLclosing);
+    RS(MLintern);
+    RS(ninio);
+    RS(TerminalAU);
+    RS(DuplexInit);
+#undef RS
+    for (int k = 0; k < 64; k++) {
+        if (k < P.n_tetra) P.tetra[k].e = at37 ? P37.tetra[k].e : (int)((double)PdH.tetra[k].e - (double)(PdH.tetra[k].e - P37.tetra[k].e) * tempf);
+        if (k < P.n_tri) P.tri[k].e = at37 ? P37.tri[k].e : (int)((double)PdH.tri[k].e - (double)(PdH.tri[k].e - P37.tri[k].e) * tempf);
+        if (k < P.n_hexa) P.hexa[k].e = at37 ? P37.hexa[k].e : (int)((double)PdH.hexa[k].e - (double)(PdH.hexa[k].e - P37.hexa[k].e) * tempf);
+    }
+    P.max_ninio = P37.max_ninio;
+    P.lxc = at37 ? P37.lxc : P37.lxc * tempf;
+    /* MFE clips multi/exterior mismatches and dangles to <= 0 (A.2) */
+    for (int a = 0; a < 8; a++)
+        for (int b = 0; b < 5; b++) {
+            P.dangle5[a][b] = MIN2(0, P.dangle5_raw[a][b]);
+            P.dangle3[a][b] = MIN2(0, P.dangle3_raw[a][b]);
+            for (int c = 0; c < 5; c++) {
+                P.mismatchM[a][b][c] = MIN2(0, P.mismatchM_raw[a][b][c]);
+                P.mismatchExt[a][b][c] = MIN2(0, P.mismatchExt_raw[a][b][c]);
+            }
+        }
+    P.loaded = 1;
+    g_temperature = T;
+    g_par_gen++;
+}
+
+int sfo_set_temperature(double temperature_c) {
+    if (!P37.loaded) {
+        set_err("parameters not loaded");
+        return -1;
+    }
+    if (temperature_c != g_temperature) rescale_params(temperature_c);
+    return 0;
+}
+
 int sfo_load_params(const char *path) {
     char *buf = read_all(path);
     if (!buf) {
@@ -191,134 +399,11 @@ int sfo_load_params(const char *path) {
         if (*p) *p++ = 0;
     }
     int rc = -1;
-    memset(&P, 0, sizeof P);
-    do {
-        if (!seek_block(&t, "stack")) {
-            set_err("missing stack");
-            break;
-        }
-        int ok = 1;
-        for (int a = 1; a <= 7 && ok; a++) ok = read_ints(&t, &P.stack[a][1], 7);
-        if (!ok) {
-            set_err("bad stack");
-            break;
-        }
-        if (!read_mm(&t, "mismatch_hairpin", P.mismatchH)) break;
-        if (!read_mm(&t, "mismatch_interior", P.mismatchI)) break;
-        if (!read_mm(&t, "mismatch_interior_1n", P.mismatch1nI)) break;
-        if (!read_mm(&t, "mismatch_interior_23", P.mismatch23I)) break;
-        if (!read_mm(&t, "mismatch_multi", P.mismatchM_raw)) break;
-        if (!read_mm(&t, "mismatch_exterior", P.mismatchExt_raw)) break;
-        if (!seek_block(&t, "dangle5")) {
-            set_err("missing dangle5");
-            break;
-        }
-        for (int a = 1; a <= 7 && ok; a++) ok = read_ints(&t, &P.dangle5_raw[a][0], 5);
-        if (!seek_block(&t, "dangle3")) {
-            set_err("missing dangle3");
-            break;
-        }
-        for (int a = 1; a <= 7 && ok; a++) ok = read_ints(&t, &P.dangle3_raw[a][0], 5);
-        if (!seek_block(&t, "int11")) {
-            set_err("missing int11");
-            break;
-        }
-        for (int a = 1; a <= 7 && ok; a++)
-            for (int b = 1; b <= 7 && ok; b++) ok = read_ints(&t, &P.int11[a][b][0][0], 25);
-        if (!seek_block(&t, "int21")) {
-            set_err("missing int21");
-            break;
-        }
-        for (int a = 1; a <= 7 && ok; a++)
-            for (int b = 1; b <= 7 && ok; b++)
-                for (int c = 0; c < 5 && ok; c++) ok = read_ints(&t, &P.int21[a][b][c][0][0], 25);
-        if (!seek_block(&t, "int22")) {
-            set_err("missing int22");
-            break;
-        }
-        for (int a = 1; a <= 6 && ok; a++)
-            for (int b = 1; b <= 6 && ok; b++)
-                for (int c = 1; c <= 4 && ok; c++)
-                    for (int d = 1; d <= 4 && ok; d++)
-                        for (int e = 1; e <= 4 && ok; e++)
-                            ok = read_ints(&t, &P.int22[a][b][c][d][e][1], 4);
-        if (!ok) {
-            set_err("bad int/dangle block");
-            break;
-        }
-        if (!seek_block(&t, "hairpin") || !read_ints(&t, P.hairpin, 31)) {
-            set_err("bad hairpin");
-            break;
-        }
-        if (!seek_block(&t, "bulge") || !read_ints(&t, P.bulge, 31)) {
-            set_err("bad bulge");
-            break;
-        }
-        if (!seek_block(&t, "interior") || !read_ints(&t, P.internal_loop, 31)) {
-            set_err("bad interior");
-            break;
-        }
-        int ml[6], nin[3];
-        if (!seek_block(&t, "ML_params") || !read_ints(&t, ml, 6)) {
-            set_err("bad ML_params");
-            break;
-        }
-        P.MLbase = ml[0];
-        P.MLclosing = ml[2];
-        P.MLintern = ml[4];
-        if (!seek_block(&t, "NINIO") || !read_ints(&t, nin, 3)) {
-            set_err("bad NINIO");
-            break;
-        }
-        P.ninio = nin[0];
-        P.max_ninio = nin[2];
-        if (!seek_block(&t, "Misc")) {
-            set_err("missing Misc");
-            break;
-        }
-        int misc[4];
-        if (!read_ints(&t, misc, 4)) {
-            set_err("bad Misc");
-            break;
-        }
-        P.DuplexInit = misc[0];
-        P.TerminalAU = misc[2];
-        P.lxc = 107.856;
-        if (t.pos < t.n && (isdigit((unsigned char)t.tok[t.pos][0]) || t.tok[t.pos][0] == '-'))
-            P.lxc = atof(t.tok[t.pos]);
-        read_special(&t, "Hexaloops", P.hexa, &P.n_hexa);
-        read_special(&t, "Tetraloops", P.tetra, &P.n_tetra);
-        read_special(&t, "Triloops", P.tri, &P.n_tri);
-        /* int22 entries touching N (code 0): least favourable of the four nucleotides */
-        for (int a = 1; a <= 6; a++)
-            for (int b = 1; b <= 6; b++)
-                for (int c = 0; c < 5; c++)
-                    for (int d = 0; d < 5; d++)
-                        for (int e = 0; e < 5; e++)
-                            for (int f = 0; f < 5; f++) {
-                                if (c && d && e && f) continue;
-                                int m = -INF;
-                                for (int c2 = (c ? c : 1); c2 <= (c ? c : 4); c2++)
-                                    for (int d2 = (d ? d : 1); d2 <= (d ? d : 4); d2++)
-                                        for (int e2 = (e ? e : 1); e2 <= (e ? e : 4); e2++)
-                                            for (int f2 = (f ? f : 1); f2 <= (f ? f : 4); f2++)
-                                                m = MAX2(m, P.int22[a][b][c2][d2][e2][f2]);
-                                P.int22[a][b][c][d][e][f] = m;
-                            }
-        /* MFE clips multi/exterior mismatches and dangles to <= 0 (A.2) */
-        for (int a = 0; a < 8; a++)
-            for (int b = 0; b < 5; b++) {
-                P.dangle5[a][b] = MIN2(0, P.dangle5_raw[a][b]);
-                P.dangle3[a][b] = MIN2(0, P.dangle3_raw[a][b]);
-                for (int c = 0; c < 5; c++) {
-                    P.mismatchM[a][b][c] = MIN2(0, P.mismatchM_raw[a][b][c]);
-                    P.mismatchExt[a][b][c] = MIN2(0, P.mismatchExt_raw[a][b][c]);
-                }
-            }
-        P.loaded = 1;
-        g_par_gen++;
+    if (!read_set(&t, "", 0, &P37) && !read_set(&t, "_enthalpies", 1, &PdH)) {
+        P37.loaded = PdH.loaded = 1;
+        rescale_params(37.0);
         rc = 0;
-    } while (0);
+    }
     free(t.tok);
     free(buf);
     return rc;
@@ -1193,6 +1278,7 @@ static int pf_core(ctx_t *c, double T, double *ensemble_dG, double *ed, char *ce
 int sfo_pf(const char *seq, int n, const char *hc, const int *sc_stack, int max_span, double temperature_c,
            double *ensemble_dG, double *ed, char *centroid, double *bpp) {
     ctx_t c;
+    if (sfo_set_temperature(temperature_c)) return -1;
     if (ctx_init(&c, seq, n, hc, sc_stack, max_span)) return -1;
     if (bpp) memset(bpp, 0, sizeof(double) * (size_t)n * n);
     int rc = pf_core(&c, temperature_c, ensemble_dG, ed, centroid, bpp);

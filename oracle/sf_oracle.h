@@ -21,6 +21,10 @@ extern "C" {
 /* load a ViennaRNA "## RNAfold parameter file v2.0"; returns 0 on success */
 int sfo_load_params(const char *path);
 const char *sfo_last_error(void);
+/* md.temperature (ScanFold.py:213, ScanFoldFunctions.py:777): rescale every table from the 37 C values and the enthalpy
+ * blocks of the file, E(T) = dH - (dH - E37) (T + 273.15) / 310.15 truncated to int.  Process-wide; the
+ * batch functions use whatever was set last.  sfo_pf sets it from its own temperature argument. */
+int sfo_set_temperature(double temperature_c);
 
 /* RNA.fold_compound(seq, md).mfe()  -- ScanFold.py:494-497,513,541; ScanFoldFunctions.py:786-787.
  * seq: n chars (ACGUT, any case).  hc: NULL or n chars of ". x | < > ( )" (fc.hc_add_from_db, ScanFold.py:512).

@@ -135,8 +135,24 @@ std::string default_par_path() {
     return "rna_turner2004_besteffort.par";
 }
 
-void ensure_pf_tables(double temperature) {
-    if (g_ctx.d_pf && g_ctx.pf_temperature == temperature) return;
+void upload_mfe_tables() {
+    CK(cudaMemcpy(g_ctx.d_mfe, &g_ctx.hp.mfe, sizeof(MfeTables), cudaMemcpyHostToDevice));
+    mfe2_upload_tables(g_ctx.hp.mfe);
+    mfe3_upload_tables(g_ctx.hp.mfe);
+    mfe4_upload_tables(g_ctx.hp.mfe);
+    CK(cudaGetLastError());
+}
+
+// md.temperature (ScanFold.py:213, ScanFoldFunctions.py:777): every energy table is rescaled from the 37 C values and
+// the enthalpies of the parameter file, then the device copies (integer tables of the four MFE kernels, Boltzmann
+// factors of the two PF kernels) are replaced.  Work queued on the stream still uses the old tables: drain it first.
+void ensure_temperature(double temperature) {
+    if (g_ctx.d_pf && g_ctx.pf_temperature == temperature && g_ctx.hp.temperature == temperature) return;
+    CK(cudaStreamSynchronize(g_ctx.stream));
+    if (g_ctx.hp.temperature != temperature) {
+        set_temperature(g_ctx.hp, temperature);
+        upload_mfe_tables();
+    }
     static PfTables host_pf;
     make_pf_tables(g_ctx.hp, temperature, host_pf);
     if (!g_ctx.d_pf) CK(cudaMalloc(&g_ctx.d_pf, sizeof(PfTables)));
@@ -144,13 +160,11 @@ void ensure_pf_tables(double temperature) {
     pf2_upload_tables(host_pf);
     g_ctx.pf_temperature = temperature;
 }
+void ensure_pf_tables(double temperature) { ensure_temperature(temperature); }
 
 int check_model(const sfb_model *m) {
     if (!g_ctx.ready) return fail(SFB_E_STATE, "sfb_init has not been called");
-    if (m && std::fabs(m->temperature - 37.0) > 1e-9)
-        return fail(SFB_E_PARAMS,
-                    "temperature != 37 needs enthalpy rescaling of every table, which this build does not do "
-                    "(SURVEY 8f row f3)");
+    if (m && !(m->temperature > -273.0 && m->temperature < 1000.0)) return fail(SFB_E_ARG, "temperature out of range");
     return 0;
 }
 
@@ -318,14 +332,10 @@ int sfb_init(int device_ordinal, const char *par_file_or_null) {
         if (!g_ctx.own_stream) CK(cudaStreamCreateWithFlags(&g_ctx.own_stream, cudaStreamNonBlocking));
         if (!g_ctx.stream) g_ctx.stream = g_ctx.own_stream;
         if (!g_ctx.d_mfe) CK(cudaMalloc(&g_ctx.d_mfe, sizeof(MfeTables)));
-        CK(cudaMemcpy(g_ctx.d_mfe, &g_ctx.hp.mfe, sizeof(MfeTables), cudaMemcpyHostToDevice));
-        mfe2_upload_tables(g_ctx.hp.mfe);
-        mfe3_upload_tables(g_ctx.hp.mfe);
-        mfe4_upload_tables(g_ctx.hp.mfe);
-        CK(cudaGetLastError());
+        upload_mfe_tables();
         g_ctx.pf_temperature = -1e9;
         g_ctx.ready = true;
-        ensure_pf_tables(37.0);
+        ensure_temperature(37.0);
         return 0;
     } catch (const CudaError &e) {
         return fail(SFB_E_CUDA, e.what());
@@ -375,6 +385,7 @@ int sfb_fold_batch(const uint8_t *seqs, int n_seq, int len, const sfb_model *mod
     if (n_seq == 0) return 0;
     try {
         CK(cudaSetDevice(g_ctx.device));
+        ensure_temperature(model ? model->temperature : 37.0);
         std::vector<uint8_t> codes;
         encode_host(seqs, (size_t)n_seq * len, codes);
         DevBuf<uint8_t> d_seq, d_hc;
@@ -435,6 +446,7 @@ int sfb_fold_long(const uint8_t *seq, int n, const sfb_model *model, const uint8
     if (!mfe4_supports(n)) return fail(SFB_E_PARAMS, "the loaded energy table does not fit the blocked kernel's packed fields");
     try {
         CK(cudaSetDevice(g_ctx.device));
+        ensure_temperature(model ? model->temperature : 37.0);
         cudaStream_t st = g_ctx.stream;
         std::vector<uint8_t> codes;
         encode_host(seq, (size_t)n, codes);
@@ -663,6 +675,7 @@ int sfb_scan_plan_run(sfb_scan_plan *P, float *ms_total, float *ms_mfe, int32_t 
         float mfe_ms = 0.f, shuf_ms = 0.f, pf_ms = 0.f;
         CK(cudaEventRecord(ev0, st));
         const int n = P->n_slots, r = a.r, W = a.W;
+        const double t_model = a.model.temperature, t_bg = a.background_temperature != 0. ? a.background_temperature : t_model;
         for (int c0 = 0, cn = 0; c0 < n; c0 += cn) {
             cn = std::min(P->chunk, n - c0);
             if (a.final_window && n - (c0 + cn) == 1) cn++;  // never leave the final-window slot alone
@@ -701,6 +714,7 @@ int sfb_scan_plan_run(sfb_scan_plan *P, float *ms_total, float *ms_mfe, int32_t 
                                        cudaMemcpyDeviceToDevice, st));
             }
             CK(cudaEventRecord(em0, st));
+            ensure_temperature(t_bg);
             // r background folds per window, energy only (ScanFoldFunctions.py:805-814)
             if (r > 0) {
                 MfeLaunch L{};
@@ -712,7 +726,7 @@ int sfb_scan_plan_run(sfb_scan_plan *P, float *ms_total, float *ms_mfe, int32_t 
                 P->fw.launch_energy_only(L, st, &n_launch);
             }
             // energy_list[0]: native without constraints / span (ScanFoldFunctions.py:774-789)
-            const bool need_unc = P->constrained || a.model.max_bp_span > 0;
+            const bool need_unc = P->constrained || a.model.max_bp_span > 0 || t_bg != t_model;
             {
                 MfeLaunch L{};
                 L.seqs = P->nat.p;
@@ -723,6 +737,7 @@ int sfb_scan_plan_run(sfb_scan_plan *P, float *ms_total, float *ms_mfe, int32_t 
                 L.pair_tbl = need_unc ? nullptr : P->pair_tbl.p + (size_t)c0 * W;
                 P->fw.launch_energy_only(L, st, &n_launch);
             }
+            ensure_temperature(t_model);
             // native fold with md / hc / sc and structure (ScanFold.py:494-497,512-513,534-541)
             if (need_unc && cn_regular > 0) {
                 if (a.hc) launch_slice_hc(P->hc.p, a.L, W, a.step, a.first_window + c0, cn_regular, 0, P->hc_win.p, st, &n_launch);

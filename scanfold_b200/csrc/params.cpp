@@ -101,63 +101,43 @@ int loop_key(const std::string &s) {
     return key;
 }
 
-void read_special(const std::map<std::string, Section> &secs, const std::string &name, int &n, int *keys, int *es) {
-    n = 0;
-    auto it = secs.find(name);
-    if (it == secs.end()) return;
-    const auto &t = it->second.tokens;
-    for (size_t k = 0; k + 2 < t.size() + 1 && k + 1 < t.size(); k += 3) {
-        if (n >= MAX_SPECIAL) break;
-        keys[n] = loop_key(t[k]);
-        es[n] = (int)std::strtol(t[k + 1].c_str(), nullptr, 10);
-        n++;
-    }
-}
-
 inline int imin(int a, int b) { return a < b ? a : b; }
 
-}  // namespace
-
-void load_params(const std::string &path, HostParams &hp) {
-    bool be = false;
-    auto secs = read_sections(path, be);
-    std::memset(&hp.mfe, 0, sizeof hp.mfe);
-    hp.besteffort = be;
-    hp.path = path;
-    MfeTables &m = hp.mfe;
-
+// one set of tables: suffix "" = free energies at 37 C, "_enthalpies" = enthalpies; col = 0 / 1 selects the value / its
+// enthalpy in the blocks that interleave them (ML_params, NINIO, Misc, special loops).  Multi / exterior mismatches and
+// dangles are stored raw (unclipped).
+void read_set(const std::map<std::string, Section> &secs, const std::string &suf, int col, MfeTables &m, double *lxc) {
+    std::memset(&m, 0, sizeof m);
     {
-        Cursor c = open(secs, "stack");
+        Cursor c = open(secs, "stack" + suf);
         for (int a = 1; a <= 7; a++)
             for (int b = 1; b <= 7; b++) m.stack[a][b] = c.next();
     }
-    read_mismatch(secs, "mismatch_hairpin", m.mismatchH);
-    read_mismatch(secs, "mismatch_interior", m.mismatchI);
-    read_mismatch(secs, "mismatch_interior_1n", m.mismatch1nI);
-    read_mismatch(secs, "mismatch_interior_23", m.mismatch23I);
-    read_mismatch(secs, "mismatch_multi", hp.mismatchM_raw);
-    read_mismatch(secs, "mismatch_exterior", hp.mismatchExt_raw);
-    std::memset(hp.dangle5_raw, 0, sizeof hp.dangle5_raw);
-    std::memset(hp.dangle3_raw, 0, sizeof hp.dangle3_raw);
+    read_mismatch(secs, "mismatch_hairpin" + suf, m.mismatchH);
+    read_mismatch(secs, "mismatch_interior" + suf, m.mismatchI);
+    read_mismatch(secs, "mismatch_interior_1n" + suf, m.mismatch1nI);
+    read_mismatch(secs, "mismatch_interior_23" + suf, m.mismatch23I);
+    read_mismatch(secs, "mismatch_multi" + suf, m.mismatchM);
+    read_mismatch(secs, "mismatch_exterior" + suf, m.mismatchExt);
     {
-        Cursor c = open(secs, "dangle5");
+        Cursor c = open(secs, "dangle5" + suf);
         for (int t = 1; t <= 7; t++)
-            for (int a = 0; a < 5; a++) hp.dangle5_raw[t][a] = c.next();
+            for (int a = 0; a < 5; a++) m.dangle5[t][a] = c.next();
     }
     {
-        Cursor c = open(secs, "dangle3");
+        Cursor c = open(secs, "dangle3" + suf);
         for (int t = 1; t <= 7; t++)
-            for (int a = 0; a < 5; a++) hp.dangle3_raw[t][a] = c.next();
+            for (int a = 0; a < 5; a++) m.dangle3[t][a] = c.next();
     }
     {
-        Cursor c = open(secs, "int11");
+        Cursor c = open(secs, "int11" + suf);
         for (int t1 = 1; t1 <= 7; t1++)
             for (int t2 = 1; t2 <= 7; t2++)
                 for (int a = 0; a < 5; a++)
                     for (int b = 0; b < 5; b++) m.int11[t1][t2][a][b] = c.next();
     }
     {
-        Cursor c = open(secs, "int21");
+        Cursor c = open(secs, "int21" + suf);
         for (int t1 = 1; t1 <= 7; t1++)
             for (int t2 = 1; t2 <= 7; t2++)
                 for (int a = 0; a < 5; a++)
@@ -165,7 +145,7 @@ void load_params(const std::string &path, HostParams &hp) {
                         for (int d = 0; d < 5; d++) m.int21[t1][t2][a][b][d] = c.next();
     }
     {
-        Cursor c = open(secs, "int22");
+        Cursor c = open(secs, "int22" + suf);
         for (int t1 = 1; t1 <= 6; t1++)
             for (int t2 = 1; t2 <= 6; t2++)
                 for (int a = 1; a <= 4; a++)
@@ -188,44 +168,110 @@ void load_params(const std::string &path, HostParams &hp) {
                 }
     }
     {
-        Cursor c = open(secs, "hairpin");
+        Cursor c = open(secs, "hairpin" + suf);
         for (int i = 0; i <= 30; i++) m.hairpin[i] = c.next();
     }
     {
-        Cursor c = open(secs, "bulge");
+        Cursor c = open(secs, "bulge" + suf);
         for (int i = 0; i <= 30; i++) m.bulge[i] = c.next();
     }
     {
-        Cursor c = open(secs, "interior");
+        Cursor c = open(secs, "interior" + suf);
         for (int i = 0; i <= 30; i++) m.internal_loop[i] = c.next();
     }
     {
-        Cursor c = open(secs, "ML_params");
+        Cursor c = open(secs, "ML_params");   // cu cu_dH cc cc_dH ci ci_dH
         int v[6];
         for (int i = 0; i < 6; i++) v[i] = c.next();
-        m.MLbase = v[0];
-        m.MLclosing = v[2];
-        m.MLintern = v[4];
+        m.MLbase = v[0 + col];
+        m.MLclosing = v[2 + col];
+        m.MLintern = v[4 + col];
     }
     {
-        Cursor c = open(secs, "NINIO");
-        m.ninio = c.next();
-        c.next();
-        m.max_ninio = c.next();
+        Cursor c = open(secs, "NINIO");       // m m_dH max
+        int v[3];
+        for (int i = 0; i < 3; i++) v[i] = c.next();
+        m.ninio = v[col];
+        m.max_ninio = v[2];
     }
-    hp.lxc = 107.856;
     {
-        auto it = secs.find("Misc");
+        auto it = secs.find("Misc");          // DuplexInit dH TerminalAU dH [lxc lxc_dH]
         if (it == secs.end()) throw std::runtime_error("parameter block 'Misc' missing");
         const auto &t = it->second.tokens;
         if (t.size() < 4) throw std::runtime_error("parameter block 'Misc' is too short");
-        m.TerminalAU = (int)std::strtol(t[2].c_str(), nullptr, 10);
-        if (t.size() >= 5) hp.lxc = std::strtod(t[4].c_str(), nullptr);
+        m.TerminalAU = (int)std::strtol(t[2 + col].c_str(), nullptr, 10);
+        if (lxc) *lxc = t.size() >= 5 ? std::strtod(t[4].c_str(), nullptr) : 107.856;
     }
-    read_special(secs, "Tetraloops", m.n_tetra, m.tetra_key, m.tetra_e);
-    read_special(secs, "Triloops", m.n_tri, m.tri_key, m.tri_e);
-    read_special(secs, "Hexaloops", m.n_hexa, m.hexa_key, m.hexa_e);
+    auto special = [&](const std::string &name, int &n, int *keys, int *es) {
+        n = 0;
+        auto it = secs.find(name);
+        if (it == secs.end()) return;
+        const auto &t = it->second.tokens;
+        for (size_t k = 0; k + 2 < t.size() + 1 && k + 1 < t.size(); k += 3) {
+            if (n >= MAX_SPECIAL) break;
+            keys[n] = loop_key(t[k]);
+            const size_t v = k + 1 + col < t.size() ? k + 1 + col : k + 1;
+            es[n] = (int)std::strtol(t[v].c_str(), nullptr, 10);
+            n++;
+        }
+    };
+    special("Tetraloops", m.n_tetra, m.tetra_key, m.tetra_e);
+    special("Triloops", m.n_tri, m.tri_key, m.tri_e);
+    special("Hexaloops", m.n_hexa, m.hexa_key, m.hexa_e);
+}
 
+}  // namespace
+
+void load_params(const std::string &path, HostParams &hp) {
+    bool be = false;
+    auto secs = read_sections(path, be);
+    hp.besteffort = be;
+    hp.path = path;
+    read_set(secs, "", 0, hp.g37, &hp.lxc37);
+    read_set(secs, "_enthalpies", 1, hp.dH, nullptr);
+    set_temperature(hp, 37.0);
+}
+
+void set_temperature(HostParams &hp, double T) {
+    const MfeTables &g = hp.g37, &h = hp.dH;
+    MfeTables &m = hp.mfe;
+    m = g;   // keys, counts, max_ninio; every energy is overwritten below unless T == 37
+    const bool at37 = std::fabs(T - 37.0) < 1e-9;
+    const double tempf = (T + 273.15) / (37.0 + 273.15);
+    auto rs = [&](int g37, int dh) -> int {
+        if (g37 >= INF) return INF;
+        if (at37) return g37;
+        return (int)((double)dh - (double)(dh - g37) * tempf);   // truncation toward zero, as the int assignment in C
+    };
+    auto many = [&](int *dst, const int *a, const int *b, size_t n) {
+        for (size_t k = 0; k < n; k++) dst[k] = rs(a[k], b[k]);
+    };
+    many(&m.stack[0][0], &g.stack[0][0], &h.stack[0][0], 64);
+    many(m.hairpin, g.hairpin, h.hairpin, 31);
+    many(m.bulge, g.bulge, h.bulge, 31);
+    many(m.internal_loop, g.internal_loop, h.internal_loop, 31);
+    many(&m.mismatchI[0][0][0], &g.mismatchI[0][0][0], &h.mismatchI[0][0][0], 200);
+    many(&m.mismatchH[0][0][0], &g.mismatchH[0][0][0], &h.mismatchH[0][0][0], 200);
+    many(&m.mismatch1nI[0][0][0], &g.mismatch1nI[0][0][0], &h.mismatch1nI[0][0][0], 200);
+    many(&m.mismatch23I[0][0][0], &g.mismatch23I[0][0][0], &h.mismatch23I[0][0][0], 200);
+    many(&hp.mismatchM_raw[0][0][0], &g.mismatchM[0][0][0], &h.mismatchM[0][0][0], 200);
+    many(&hp.mismatchExt_raw[0][0][0], &g.mismatchExt[0][0][0], &h.mismatchExt[0][0][0], 200);
+    many(&hp.dangle5_raw[0][0], &g.dangle5[0][0], &h.dangle5[0][0], 40);
+    many(&hp.dangle3_raw[0][0], &g.dangle3[0][0], &h.dangle3[0][0], 40);
+    many(&m.int11[0][0][0][0], &g.int11[0][0][0][0], &h.int11[0][0][0][0], 8 * 8 * 25);
+    many(&m.int21[0][0][0][0][0], &g.int21[0][0][0][0][0], &h.int21[0][0][0][0][0], 8 * 8 * 125);
+    many(&m.int22[0][0][0][0][0][0], &g.int22[0][0][0][0][0][0], &h.int22[0][0][0][0][0][0], 8 * 8 * 625);
+    m.MLbase = rs(g.MLbase, h.MLbase);
+    m.MLclosing = rs(g.MLclosing, h.MLclosing);
+    m.MLintern = rs(g.MLintern, h.MLintern);
+    m.ninio = rs(g.ninio, h.ninio);
+    m.max_ninio = g.max_ninio;
+    m.TerminalAU = rs(g.TerminalAU, h.TerminalAU);
+    many(m.tetra_e, g.tetra_e, h.tetra_e, MAX_SPECIAL);
+    many(m.tri_e, g.tri_e, h.tri_e, MAX_SPECIAL);
+    many(m.hexa_e, g.hexa_e, h.hexa_e, MAX_SPECIAL);
+    hp.lxc = at37 ? hp.lxc37 : hp.lxc37 * tempf;
+    hp.temperature = T;
     for (int t = 0; t < 8; t++)
         for (int a = 0; a < 5; a++) {
             m.dangle5[t][a] = imin(0, hp.dangle5_raw[t][a]);

@@ -46,18 +46,24 @@ struct PfTables {
 };
 
 struct HostParams {
-    MfeTables mfe;
-    // unclipped copies needed for the smoothed PF factors
+    MfeTables mfe;   // the working set at `temperature` (multi / exterior mismatches and dangles clipped to <= 0)
+    // unclipped copies needed for the smoothed PF factors (at `temperature`)
     int mismatchM_raw[8][5][5], mismatchExt_raw[8][5][5], dangle5_raw[8][5], dangle3_raw[8][5];
-    double lxc;
+    double lxc;      // at `temperature`
+    double temperature;
+    // what the file holds: free energies at 37 C and enthalpies (every block has an `_enthalpies` twin), raw
+    MfeTables g37, dH;
+    double lxc37;
     bool besteffort;
     std::string path;
 };
 
-// Parses `path`; throws std::runtime_error with a message on failure.
+// Parses `path` (both the 37 C blocks and their enthalpy twins) and selects 37 C; throws std::runtime_error on failure.
 void load_params(const std::string &path, HostParams &out);
-// Builds Boltzmann factors at temperature T (Celsius) from the 37C tables (valid for T == 37 only
-// when the table set has no usable enthalpies).
+// Rescales every table to `temperature_c` the way ViennaRNA's get_scaled_params does (md.temperature, ScanFold.py:213,
+// ScanFoldFunctions.py:777): E(T) = dH - (dH - E37) * (T + 273.15) / 310.15 truncated to int, lxc proportional to T.
+void set_temperature(HostParams &hp, double temperature_c);
+// Builds Boltzmann factors from the working set (call set_temperature first: hp.temperature is the temperature used).
 void make_pf_tables(const HostParams &hp, double temperature_c, PfTables &out);
 
 // nucleotide / pair encoding

@@ -161,15 +161,23 @@ __global__ void __launch_bounds__(NT, SFB_PF_MINB) pf_kernel(PfLaunch L, const M
     uint8_t *hcf = S + W + 4;
     uint8_t *ctype = hcf + W + 4;
 
+    // qb and P stay diagonal-major triangles (read along diagonals); every matrix an O(W) sum walks lives in the
+    // orientation that makes the walk contiguous, so the lanes that share a cell read one row segment per load:
+    //   qmR [i][k] row-major, qmC [k][i] column-major (both written per cell), qm1C column-major,
+    //   X1C / X2C column-major, PMR row-major.  Entries with j - i <= TURN are never read.
+    const size_t sq = (size_t)W * W;
     double *g = L.gscratch + (long long)blockIdx.x * L.gscratch_per_cta;
     double *qb = g;            g += ntri;
-    double *qm = g;            g += ntri;
-    double *qm1 = g;           g += ntri;
     double *Pm = g;            g += ntri;
-    double *PMm = g;           g += ntri;
-    double *X1 = g;            g += ntri;
-    double *X2 = g;            g += ntri;
+    double *qmR = g;           g += sq;
+    double *qmC = g;           g += sq;
+    double *qm1C = g;          g += sq;
+    double *PMR = g;           g += sq;
+    double *X1C = g;           g += sq;
+    double *X2C = g;           g += sq;
     double *ring = g;          // [3][PRING][W]: generic | 1xn | bulge class copies
+#define RM(i, j) ((size_t)(i) * W + (j))
+#define CM(i, j) ((size_t)(j) * W + (i))
 
     {
         auto cp = [&](double *dst, const double *s, int n) {
@@ -339,9 +347,17 @@ __global__ void __launch_bounds__(NT, SFB_PF_MINB) pf_kernel(PfLaunch L, const M
                             }
                         }
                         // multiloop: sum_k qm[i+1,k-1] * qm1[k,j-1]
-                        double ml = 0.;
-                        for (int k = i + 2 + TURN + 1 + gl; k <= j - 2 - TURN; k += G)
-                            ml += qm[TRI(k - 2 - i, i + 1)] * qm1[TRI(j - 1 - k, k)];
+                        double ml = 0., ml2 = 0.;
+                        {
+                            const double *a = qmR + RM(i + 1, 0) - 1, *b = qm1C + CM(0, j - 1);   // a[k] = qm[i+1][k-1], b[k] = qm1[k][j-1]
+                            int k = i + 2 + TURN + 1 + gl;
+                            for (; k + G <= j - 2 - TURN; k += 2 * G) {
+                                ml = fma(a[k], b[k], ml);
+                                ml2 = fma(a[k + G], b[k + G], ml2);
+                            }
+                            if (k <= j - 2 - TURN) ml = fma(a[k], b[k], ml);
+                        }
+                        ml += ml2;
                         acc += ml * closing * x_mlstem(*st, rtype_of(type), sj1, si1) * scale[2];
                     }
                     acc = group_sum(acc, G);
@@ -376,19 +392,26 @@ __global__ void __launch_bounds__(NT, SFB_PF_MINB) pf_kernel(PfLaunch L, const M
                         i = item >> gsh;
                         j = i + d;
                         // sum_{k=i+1}^{j-TURN-1} (qm[i,k-1] + eMLb[k-i]) * qm1[k,j]
-                        for (int k = i + 1 + (item & (G - 1)); k <= j - TURN - 1; k += G) {
-                            double left = eMLb[k - i];
-                            if (k - 1 - i > TURN) left += qm[TRI(k - 1 - i, i)];
-                            acc += left * qm1[TRI(j - k, k)];
+                        const double *a = qmR + RM(i, 0) - 1, *b = qm1C + CM(0, j);   // a[k] = qm[i][k-1], b[k] = qm1[k][j]
+                        double acc2 = 0.;
+                        int k = i + 1 + (item & (G - 1));
+                        for (; k + G <= j - TURN - 1; k += 2 * G) {
+                            const double l0 = eMLb[k - i] + (k - 1 - i > TURN ? a[k] : 0.);
+                            const double l1 = eMLb[k + G - i] + (k + G - 1 - i > TURN ? a[k + G] : 0.);
+                            acc = fma(l0, b[k], acc);
+                            acc2 = fma(l1, b[k + G], acc2);
                         }
+                        if (k <= j - TURN - 1) acc = fma(eMLb[k - i] + (k - 1 - i > TURN ? a[k] : 0.), b[k], acc);
+                        acc += acc2;
                     }
                     acc = group_sum(acc, G);
                     if (active && (item & (G - 1)) == 0) {
-                        double v = (d - 1 > TURN) ? qm1[TRI(d - 1, i)] * eMLb[1] : 0.;
+                        double v = (d - 1 > TURN) ? qm1C[CM(i, j - 1)] * eMLb[1] : 0.;
                         const int t = ctype[i];
                         if (t) v += qb[tri_d + i] * x_mlstem(*st, t, i > 0 ? S[i - 1] : -1, j < W - 1 ? S[j + 1] : -1);
-                        qm1[tri_d + i] = v;
-                        qm[tri_d + i] = acc + v;
+                        qm1C[CM(i, j)] = v;
+                        qmR[RM(i, j)] = acc + v;
+                        qmC[CM(i, j)] = acc + v;
                     }
                 }
             }
@@ -483,13 +506,24 @@ __global__ void __launch_bounds__(NT, SFB_PF_MINB) pf_kernel(PfLaunch L, const M
                                 }
                             }
                             // multiloop closed by (i,j), i < k, j > l
-                            double ml = 0.;
-                            for (int i = gl; i <= k - 1; i += G) {
-                                const int o = TRI(l - i, i);
-                                const double x1 = X1[o];
-                                ml += x1 * eMLb[k - 1 - i];
-                                if (k - 2 - i > TURN) ml += (x1 + X2[o]) * qm[TRI(k - 2 - i, i + 1)];
+                            double ml = 0., mlb = 0.;
+                            {
+                                const double *x1c = X1C + CM(0, l), *x2c = X2C + CM(0, l), *qc = qmC + CM(1, k - 1);   // qc[i] = qm[i+1][k-1]
+                                int i = gl;
+                                for (; i + G <= k - 1; i += 2 * G) {
+                                    const double a0 = x1c[i], a1 = x1c[i + G];
+                                    ml = fma(a0, eMLb[k - 1 - i], ml);
+                                    mlb = fma(a1, eMLb[k - 1 - i - G], mlb);
+                                    if (k - 2 - i > TURN) ml = fma(a0 + x2c[i], qc[i], ml);
+                                    if (k - 2 - i - G > TURN) mlb = fma(a1 + x2c[i + G], qc[i + G], mlb);
+                                }
+                                if (i <= k - 1) {
+                                    const double a0 = x1c[i];
+                                    ml = fma(a0, eMLb[k - 1 - i], ml);
+                                    if (k - 2 - i > TURN) ml = fma(a0 + x2c[i], qc[i], ml);
+                                }
                             }
+                            ml += mlb;
                             acc += ml * x_mlstem(*st, tkl, sp1, sq1) * scale[2];
                         }
                         if (gl == 0)
@@ -515,7 +549,7 @@ __global__ void __launch_bounds__(NT, SFB_PF_MINB) pf_kernel(PfLaunch L, const M
                     double pm = 0.;
                     if (qkl != 0. && k + 1 < W && l >= 1)
                         pm = acc * closing * x_mlstem(*st, rtype_of(tkl), S[l - 1], S[k + 1]);
-                    PMm[tri_d + k] = pm;
+                    PMR[RM(k, l)] = pm;
                     const double p = acc * qkl;
                     ed_local += p * (1. - p);
                     if (p > 0.5) {
@@ -535,18 +569,22 @@ __global__ void __launch_bounds__(NT, SFB_PF_MINB) pf_kernel(PfLaunch L, const M
                 if (active) {
                     i = item >> gsh;
                     l = i + d;
-                    for (int j = l + 2 + TURN + 1 + (item & (G - 1)); j < W; j += G)
-                        acc += PMm[TRI(j - i, i)] * qm[TRI(j - l - 2, l + 1)];
+                    const double *a = PMR + RM(i, 0), *b = qmR + RM(l + 1, 0) - 1;   // a[j] = PM[i][j], b[j] = qm[l+1][j-1]
+                    double acc2 = 0.;
+                    int j = l + 2 + TURN + 1 + (item & (G - 1));
+                    for (; j + G < W; j += 2 * G) {
+                        acc = fma(a[j], b[j], acc);
+                        acc2 = fma(a[j + G], b[j + G], acc2);
+                    }
+                    if (j < W) acc = fma(a[j], b[j], acc);
+                    acc += acc2;
                 }
                 acc = group_sum(acc, G);
                 if (active && (item & (G - 1)) == 0) {
-                    X1[tri_d + i] = acc;
+                    X1C[CM(i, l)] = acc;
                     double x2 = 0.;
-                    if (l + 1 < W) {
-                        const int o = TRI(d + 1, i);
-                        x2 = X2[o] * eMLb[1] + PMm[o];
-                    }
-                    X2[tri_d + i] = x2;
+                    if (l + 1 < W) x2 = X2C[CM(i, l + 1)] * eMLb[1] + PMR[RM(i, l + 1)];
+                    X2C[CM(i, l)] = x2;
                 }
             }
             __syncthreads();
@@ -566,6 +604,8 @@ __global__ void __launch_bounds__(NT, SFB_PF_MINB) pf_kernel(PfLaunch L, const M
         __syncthreads();
     }
 #undef TRI
+#undef RM
+#undef CM
 }
 
 size_t pf_smem_bytes(int W) {
@@ -579,7 +619,7 @@ size_t pf_smem_bytes(int W) {
 }  // namespace
 
 size_t pf_scratch_doubles_per_cta(int W) {
-    const size_t a = 7 * ((size_t)W * (W + 1) / 2) + 3 * (size_t)PRING * W, b = pf2_scratch_doubles_per_cta();
+    const size_t a = 2 * ((size_t)W * (W + 1) / 2) + 6 * (size_t)W * W + 3 * (size_t)PRING * W, b = pf2_scratch_doubles_per_cta();
     return a > b ? a : b;
 }
 

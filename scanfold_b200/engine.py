@@ -40,7 +40,7 @@ class ScanArgs(C.Structure):
                 ("shuffle_type", C.c_int32), ("seed", C.c_uint64), ("parity_shuffles", C.c_void_p),
                 ("model", Model), ("hc", C.c_void_p), ("react", C.c_void_p), ("shape_m", C.c_double),
                 ("shape_b", C.c_double), ("first_window", C.c_int32), ("n_windows", C.c_int32),
-                ("final_window", C.c_int32), ("want_pf", C.c_int32)]
+                ("final_window", C.c_int32), ("want_pf", C.c_int32), ("background_temperature", C.c_double)]
 
 
 class ScanOut(C.Structure):
@@ -246,7 +246,7 @@ class ScanPlan:
 
     def __init__(self, seq, W, step, r, shuffle_type="mono", seed=42, parity_shuffles=None, temperature=37.0,
                  max_span=0, hc=None, react=None, shape_m=0.8, shape_b=-0.2, first_window=0, n_windows=None,
-                 final_window=True, want_pf=True, keep_shuffles=False):
+                 final_window=True, want_pf=True, keep_shuffles=False, background_temperature=None):
         ensure_init()
         self._lib = load_library()
         self._seq = np.frombuffer(seq.encode() if isinstance(seq, str) else bytes(seq), dtype=np.uint8).copy()
@@ -286,6 +286,7 @@ class ScanPlan:
         a.first_window, a.n_windows = int(first_window), int(n_windows)
         a.final_window = 1 if final_window else 0
         a.want_pf = 1 if want_pf else 0
+        a.background_temperature = float(background_temperature) if background_temperature else 0.0
         self._args = a
         self._plan = C.c_void_p()
         _check(self._lib.sfb_scan_plan_create(C.byref(a), C.byref(self._plan)))

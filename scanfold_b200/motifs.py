@@ -99,8 +99,10 @@ def refold_motif(m, shuffle_type, temperature, seed, parity_shuffles=None):
     par = None
     if parity_shuffles is not None:
         par = np.ascontiguousarray(parity_shuffles, dtype=np.uint8).reshape(1, SUB_RANDOMIZATIONS, W)
+    # the constrained fold and its partition function use a default compound (37 C, ScanFold.py:1733-1741); only the
+    # background energies() call gets the -t temperature (:1748)
     t = scan.scan_record(frag, W, 1, SUB_RANDOMIZATIONS, shuffle_type=shuffle_type, seed=seed, parity_shuffles=par,
-                         temperature=temperature, hc=m.structure, final_window=False)
+                         temperature=37.0, background_temperature=temperature, hc=m.structure, final_window=False)
     return {"structure": t.structure(0), "mfe": float(t.mfe[0]), "z": float(t.z[0]), "p": float(t.p[0]),
             "ed": float(t.ed[0])}
 

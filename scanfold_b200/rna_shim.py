@@ -20,11 +20,11 @@ _backend = None
 class EngineBackend:
     """folds on the GPU through the C-ABI (scanfold_b200.engine)"""
 
-    def mfe(self, seq, hc, sc_stack, max_span):
+    def mfe(self, seq, hc, sc_stack, max_span, temperature=37.0):
         from . import engine
         e, pt = engine.fold_batch([seq], hc=[hc] if hc else None,
                                   sc=np.asarray(sc_stack, dtype=np.int32)[None, :] if sc_stack is not None else None,
-                                  structure=True, max_span=max_span)
+                                  structure=True, max_span=max_span, temperature=temperature)
         return int(e[0]), engine.pair_table_to_dotbracket(pt[0])
 
     def pf(self, seq, hc, sc_stack, max_span, temperature):
@@ -71,8 +71,6 @@ class fold_compound:
         self._temperature = float(model.temperature) if model is not None else 37.0
         span = int(model.max_bp_span) if model is not None else -1
         self._span = span if span > 0 else 0
-        if abs(self._temperature - 37.0) > 1e-9:
-            raise NotImplementedError("temperature != 37 needs enthalpy rescaling of the tables (SURVEY 8f f3)")
         self._hc = None
         self._sc = None
         self._pf = None
@@ -103,7 +101,10 @@ class fold_compound:
 
     # ---- folds
     def mfe(self):
-        e, s = backend().mfe(self.sequence, self._hc, self._sc, self._span)
+        if abs(self._temperature - 37.0) > 1e-9:
+            e, s = backend().mfe(self.sequence, self._hc, self._sc, self._span, temperature=self._temperature)
+        else:
+            e, s = backend().mfe(self.sequence, self._hc, self._sc, self._span)
         return [s, float(np.float32(e / 100.0))]
 
     def pf(self):

@@ -114,7 +114,7 @@ def table_from_result(res, first_window, step, n_regular, final_window):
 
 def scan_record(seq, W=120, step=1, r=100, shuffle_type="mono", seed=42, parity_shuffles=None, temperature=37.0,
                 max_span=0, hc=None, react=None, shape_m=0.8, shape_b=-0.2, first_window=0, n_windows=None,
-                final_window=None, want_pf=True):
+                final_window=None, want_pf=True, background_temperature=None):
     """Scan one record (or the window range [first_window, first_window + n_windows) of it).
 
     seq: RNA string (T already transcribed, ScanFold.py:282).  hc: line 3 of --constraints (one char per
@@ -132,5 +132,5 @@ def scan_record(seq, W=120, step=1, r=100, shuffle_type="mono", seed=42, parity_
     res = engine.scan(seq, W, step, r, shuffle_type=shuffle_type, seed=seed, parity_shuffles=parity_shuffles,
                       temperature=temperature, max_span=max_span, hc=hc, react=react, shape_m=shape_m,
                       shape_b=shape_b, first_window=first_window, n_windows=n_windows, final_window=final_window,
-                      want_pf=want_pf)
+                      want_pf=want_pf, background_temperature=background_temperature)
     return table_from_result(res, first_window, step, n_windows, final_window)

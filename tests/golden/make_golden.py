@@ -66,6 +66,11 @@ CASES = {
     "c0_w40": dict(L=150, seed=22, args=["-w", "40", "-r", "10", "-c", "0"], expect_fail="FileNotFoundError"),
     "refold_w40": dict(L=170, seed=23, args=["-w", "40", "-r", "10", "--global_refold"]),
     "print_random_w40": dict(L=90, seed=24, args=["-w", "40", "-r", "6", "--print_random"], stdout=True),
+    "t25_w40": dict(L=150, seed=27, args=["-w", "40", "-r", "10", "-t", "25"]),      # -t != 37: enthalpy-rescaled tables
+    # the motif step folds at 37 C but scores against a background folded at -t (ScanFold.py:1733,1748)
+    "motifs_t45_w50": dict(L=0, seed=28, args=["-w", "50", "-r", "10", "-t", "45"],
+                           seq="AAUAC" + "GGGGCGCUUCGGCGCCCC" + "AUAAUUAAUA" + "GCCGGAUCGAAAGAUCCGGC" + "AAUAUAAUAAAUUA" +
+                               "GGCACGGCUUUUGCCGUGCC" + "UUAUAAUAUA" + "CCGCGGAGAAAUCCGCGG" + "AUUAAUAUAAUAUUAAAUUAAUAAUAUUAAUA"),
     # Q10: runs of N -- 130 (every nucleotide still covered by partly-N windows) and 260 (22 nucleotides left without a record)
     "q10_n130_w120": dict(L=0, seed=25, args=["-w", "120", "-r", "6"], nrun=(150, 130, 140)),
     "q10_n260_w120": dict(L=0, seed=26, args=["-w", "120", "-r", "6"], nrun=(140, 260, 135)),

@@ -15,8 +15,8 @@ _trace = []
 
 
 class _OracleBackend:
-    def mfe(self, seq, hc, sc_stack, max_span):
-        e, s = _O.mfe(seq, hc=hc, sc_stack=sc_stack, max_span=max_span)
+    def mfe(self, seq, hc, sc_stack, max_span, temperature=37.0):
+        e, s = _O.mfe(seq, hc=hc, sc_stack=sc_stack, max_span=max_span, temperature=temperature)
         _trace.append({"op": "mfe", "seq": seq, "hc": hc, "sc": None if sc_stack is None else [int(x) for x in sc_stack],
                        "e": int(e), "s": s})
         return e, s

@@ -454,3 +454,31 @@ def test_whole_sequence_fold(engine, oracle, n):
             for k, ch in enumerate(full):
                 if ch == "x":
                     assert pt[k] == 0
+
+
+@pytest.mark.parametrize("T", [25.0, 50.0, 10.0])
+def test_temperature_rescaling(engine, oracle, T):
+    """md.temperature != 37 (ScanFold.py:212-213, -t): every table rescaled from the 37 C values and the enthalpy blocks of
+    the parameter file, on all MFE kernels (short, 120-nt, 300-nt, blocked) and both PF kernels, against the oracle."""
+    try:
+        for W, n_seq in ((40, 40), (120, 40), (200, 6), (320, 4)):
+            seqs = rand_seqs(int(T) * 1000 + W, n_seq, W, gc_rich=True)
+            e, pt = engine.fold_batch(seqs, structure=True, temperature=T)
+            e37, _ = engine.fold_batch(seqs, structure=False)
+            assert not np.array_equal(e, e37)
+            for k in range(0, n_seq, 3):
+                eo, so = oracle.mfe(seqs[k], temperature=T)
+                assert e[k] == eo and db_from_pt(pt[k]) == so, (T, W, k)
+            if W <= 200:
+                res = engine.pf_batch(seqs[:6], temperature=T)
+                for k in range(0, 6, 2):
+                    o = oracle.pf(seqs[k], temperature=T)
+                    assert abs(res["dG"][k] - o["dG"]) <= 1e-6 * max(1.0, abs(o["dG"])), (T, W, k)
+                    assert abs(res["ed"][k] - o["ed"]) <= 1e-6 * max(1.0, abs(o["ed"])), (T, W, k)
+                    assert db_from_pt(res["centroid"][k]) == o["centroid"]
+        # back at 37 the tables are the file's own values again
+        s = rand_seqs(5, 3, 90)
+        e, _ = engine.fold_batch(s, structure=False)
+        assert [int(x) for x in e] == [oracle.mfe(x, structure=False)[0] for x in s]
+    finally:
+        oracle.set_temperature(37.0)

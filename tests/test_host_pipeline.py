@@ -74,7 +74,8 @@ def test_outputs_byte_identical(name, tmp_path, monkeypatch):
     names = pipeline.RunNames(case["record"], case["header"].split()[0], case["W"], case["step"], case["r"], stype,
                               name=chrom)
     monkeypatch.chdir(tmp_path)
-    minz = pipeline.write_scan_outputs(case["seq"], table, names, 37, case["step"])
+    temperature = int(args[args.index("-t") + 1]) if "-t" in args else 37
+    minz = pipeline.write_scan_outputs(case["seq"], table, names, temperature, case["step"])
     comp = accumulate_numpy(case["L"], case["W"], case["step"], 0, *accumulate_inputs(table))
     ptable = foldstep.table_from_compact(*comp)
     competition = 0 if "-c" in args and args[args.index("-c") + 1] == "0" else 1
@@ -142,10 +143,11 @@ def test_motif_outputs_byte_identical(name, tmp_path, monkeypatch):
     results = []
     for m in found:
         sh = case["trace"]["motif_shuffles_%d" % m.number]
+        bg_t = float(args[args.index("-t") + 1]) if "-t" in args else 37.0     # only energies() gets -t (ScanFold.py:1748)
         e, s = O.mfe(m.sequence, hc=m.structure)
         pf = O.pf(m.sequence, hc=m.structure)
-        nat = O.mfe(m.sequence, structure=False)[0]
-        she = [O.mfe(bytes(row).decode(), structure=False)[0] for row in sh]
+        nat = O.mfe(m.sequence, structure=False, temperature=bg_t)[0]
+        she = [O.mfe(bytes(row).decode(), structure=False, temperature=bg_t)[0] for row in sh]
         z, p = stats.zscore_pvalue(np.array([nat]), np.array([she]))
         results.append({"structure": s, "mfe": float(stats.round_energy([e])[0]), "z": float(z[0]), "p": float(p[0]),
                         "ed": float(scan.round_ed([pf["ed"]])[0])})
