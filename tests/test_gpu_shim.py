@@ -93,4 +93,13 @@ def test_motif_calls_through_the_shim(RNA):
     fc = RNA.fold_compound(seq)
     fc.hc_add_from_db("((((((((....))))))))........")
     s2, e2 = fc.mfe()
-    assert s2.startswith("((((") and e2 >= e - 1e-6
+    assert len(s2) == len(seq) and e2 >= e - 1e-6          # weak enforcement: conflicting pairs removed, nothing forced
+    pairs, stack = set(), []
+    for k, ch in enumerate(s2):
+        if ch == "(":
+            stack.append(k)
+        elif ch == ")":
+            pairs.add((stack.pop(), k))
+    for i, j in pairs:                                      # no pair may cross an enforced one or steal its partner
+        for a, b in zip(range(0, 8), range(19, 11, -1)):
+            assert not (i < a < j < b or a < i < b < j) and (i not in (a, b) or (i, j) == (a, b)) and (j not in (a, b) or (i, j) == (a, b))
