@@ -40,8 +40,8 @@ CASES = [
     ("C3", 10000, 1003, (1, 1, 1, 1), 200, 50, "di", {"react": True}, 3000),
     ("C5/W40", 100000, 1005, (1, 1, 1, 1), 40, 100, "mono", {"hc": True}, 30000),
     ("C5/W120", 100000, 1005, (1, 1, 1, 1), 120, 100, "mono", {"hc": True}, 6000),
-    ("C5/W300", 100000, 1005, (1, 1, 1, 1), 300, 100, "mono", {"hc": True}, 300),
-    ("C5/W600", 100000, 1005, (1, 1, 1, 1), 600, 100, "mono", {"hc": True}, 60),
+    ("C5/W300", 100000, 1005, (1, 1, 1, 1), 300, 100, "mono", {"hc": True}, 1200),
+    ("C5/W600", 100000, 1005, (1, 1, 1, 1), 600, 100, "mono", {"hc": True}, 300),
 ]
 
 
