@@ -285,6 +285,9 @@ mfe4_block_kernel(Mfe4Launch L, const MfeTables *__restrict__ T, const Tab4 *__r
         const uint8_t *S = L.seqs + (size_t)fold * n;
         const size_t moff = (size_t)fold * NP * NP;
         int32_t *gC = L.C + moff, *gM = L.M + moff, *gD = L.D + moff;
+#ifdef SFB_MFE4_TIMING
+        const long long tm_task0 = clock64();
+#endif
         Perm4 pm;
         pm.S = S;
         pm.hc = L.hc ? L.hc + (size_t)fold * n : nullptr;
@@ -413,10 +416,17 @@ mfe4_block_kernel(Mfe4Launch L, const MfeTables *__restrict__ T, const Tab4 *__r
         // pipelined with ONE barrier per step.  Iteration t runs, side by side,
         //   G  the separable interior loops of the pairable cells of step t, one warp per cell (warps 2..6)
         //   H  their nine table-driven shapes and the hairpin, lane = cell (warps 0 and 1 share the shapes)
-        //   F  for the cells of step t-1: C from the partial minima of iteration t-1 plus the multiloop closing term, the
-        //      window entry, then the splits inside the two diagonal blocks and FML (warp 7, lane = cell)
+        //   F  for the cells of step t-1: C from the partial minima of iteration t-1 plus the multiloop closing term and the
+        //      window entry (warp 7, lane = cell), the splits inside the two diagonal blocks (warps 0 and 1, before their
+        //      shapes), then FML once the three warps met at a named barrier (warp 7)
         // C(t) only reads cells of steps <= t-2 and the split minima of step t-2; FML(t-1) reads FML of steps <= t-2.
+#ifdef SFB_MFE4_TIMING
+        long long tm_busy = 0, tm_loop0 = clock64(), tm_a = 0, tm_b = 0;
+#endif
         for (int t = s_begin; t <= 63; t++) {
+#ifdef SFB_MFE4_TIMING
+            const long long tm_it0 = clock64();
+#endif
             if (warp == NT4 / 32 - 1) {
                 // ---- F: step t - 1, lane = cell
                 if (t > s_begin) {
@@ -449,25 +459,9 @@ mfe4_block_kernel(Mfe4Launch L, const MfeTables *__restrict__ T, const Tab4 *__r
                             gC[(size_t)j * NP + i] = cij;   // transposed copy for the exterior loop
                         }
                     }
-                    // splits inside the two diagonal blocks: m = i0 + c (rows below, 31 - a terms) and m = j0 + c (columns to
-                    // the left, b + 1 terms).  Both loops run over warp-uniform ranges WITHOUT a per-lane test: outside a lane's
-                    // own range one operand is a cell of this block that a later step computes -- still INF in Mb -- so the sum
-                    // stays above INF / 2 whatever the other operand reads (neighbouring entries of the triangles).
+                    // the splits inside the two diagonal blocks come from warps 0 and 1 (below) through Db
+                    asm volatile("bar.sync 1, 96;" ::: "memory");
                     int dec = 2 * INF;
-                    const int a_lo = 31 - s + blo, b_hi = blo + nc - 1;   // smallest a / largest b of the step
-                    if (delta == 0) {   // a < c <= b: FML[i][m-1] + FML[m][j], both inside this block
-                        const int *pa = Mb + a * 34, *pb = Mb + b + 1;
-#pragma unroll 4
-                        for (int c = a_lo + 1; c <= b_hi; c++) dec = __viaddmin_s32(pa[c], pb[c * 34], dec);
-                    } else {
-                        const int *pa = Mii + tri32(a, a) - a - 1, *pb = Mb + b + 1;   // pa[c] = Mii[a][c-1]
-#pragma unroll 4
-                        for (int c = a_lo + 1; c < 32; c++) dec = __viaddmin_s32(pa[c], pb[c * 34], dec);
-                        const int *qa = Mb + a * 34, *qb = Mjj + (b * (b + 1)) / 2;   // Mjj by column: [b][c], c <= b
-#pragma unroll 4
-                        for (int c = 0; c <= b_hi; c++) dec = __viaddmin_s32(qa[c], qb[c], dec);
-                    }
-                    __syncwarp();   // every lane has read the Mb entries of this step's cells (still INF) before anyone writes
                     if (active) {
                         dec = min(dec, Db[a * 34 + b + 1]);
                         if (dec > INF / 2) dec = INF;
@@ -488,7 +482,45 @@ mfe4_block_kernel(Mfe4Launch L, const MfeTables *__restrict__ T, const Tab4 *__r
                         }
                     }
                 }
-            } else if (t < 63) {
+            } else {
+              if (warp < 2 && t > s_begin) {
+                // ---- F, split part: the splits of step t - 1 inside the two diagonal blocks, lane = cell.  m = i0 + c (rows
+                // below, 31 - a terms: warp 0) and m = j0 + c (columns to the left, b + 1 terms: warp 1).  Both loops run over
+                // warp-uniform ranges WITHOUT a per-lane test: outside a lane's own range one operand is a cell of this block
+                // that a later step computes -- still INF in Mb -- so the sum stays above INF / 2 whatever the other operand
+                // reads (neighbouring entries of the triangles).  The minima meet the far splits in Db (shared-memory
+                // atomics, one cell per lane); warp 7 picks them up behind the named barrier.
+                const int s = t - 1;
+                const int blo = max(0, s - 31), nc = min(s, 62 - s) + 1;
+                const int b = blo + min(lane, nc - 1), a = 31 - s + b;
+                const int a_lo = 31 - s + blo, b_hi = blo + nc - 1;   // smallest a / largest b of the step
+                int dec = 2 * INF;
+                if (delta == 0) {   // a < c <= b: FML[i][m-1] + FML[m][j], both inside this block
+                    if (warp == 0) {
+                        const int *pa = Mb + a * 34, *pb = Mb + b + 1;
+#pragma unroll 4
+                        for (int c = a_lo + 1; c <= b_hi; c++) dec = __viaddmin_s32(pa[c], pb[c * 34], dec);
+                    }
+                } else if (warp == 0) {
+                    const int *pa = Mii + tri32(a, a) - a - 1, *pb = Mb + b + 1;   // pa[c] = Mii[a][c-1]
+#pragma unroll 4
+                    for (int c = a_lo + 1; c < 32; c++) dec = __viaddmin_s32(pa[c], pb[c * 34], dec);
+                } else {
+                    const int *qa = Mb + a * 34, *qb = Mjj + (b * (b + 1)) / 2;   // Mjj by column: [b][c], c <= b
+#pragma unroll 4
+                    for (int c = 0; c <= b_hi; c++) dec = __viaddmin_s32(qa[c], qb[c], dec);
+                }
+                if (lane < nc && dec < INF / 2) atomicMin(&Db[a * 34 + b + 1], dec);
+#ifdef SFB_MFE4_TIMING
+                tm_a += clock64() - tm_it0;
+                const long long tm_b0 = clock64();
+#endif
+                asm volatile("bar.sync 1, 96;" ::: "memory");
+#ifdef SFB_MFE4_TIMING
+                tm_b += clock64() - tm_b0;
+#endif
+              }
+              if (t < 63) {
                 const int npair = scnt[t];
                 const unsigned char *lst = slist + t * 32;
                 int *pG = part + (t & 1) * 64, *pS = pG + 32;
@@ -595,9 +627,18 @@ mfe4_block_kernel(Mfe4Launch L, const MfeTables *__restrict__ T, const Tab4 *__r
                     }
                     atomicMin(&pS[b], best);
                 }
+              }
             }
+#ifdef SFB_MFE4_TIMING
+            tm_busy += clock64() - tm_it0;
+#endif
             __syncthreads();
         }
+#ifdef SFB_MFE4_TIMING
+        if (delta == 8 && blockIdx.x < 3 && task == blockIdx.x && lane == 0)
+            printf("mfe4 timing cta %d warp %d: busy %lld of loop %lld cycles (%d iterations), phases 1-2 %lld, splits %lld, named barrier %lld\n",
+                   blockIdx.x, warp, tm_busy, clock64() - tm_loop0, 64 - s_begin, tm_loop0 - tm_task0, tm_a, tm_b);
+#endif
     }
 }
 
