@@ -417,8 +417,8 @@ mfe4_block_kernel(Mfe4Launch L, const MfeTables *__restrict__ T, const Tab4 *__r
         //   G  the separable interior loops of the pairable cells of step t, one warp per cell (warps 2..6)
         //   H  their nine table-driven shapes and the hairpin, lane = cell (warps 0 and 1 share the shapes)
         //   F  for the cells of step t-1: C from the partial minima of iteration t-1 plus the multiloop closing term and the
-        //      window entry (warp 7, lane = cell), the splits inside the two diagonal blocks (warps 0 and 1, before their
-        //      shapes), then FML once the three warps met at a named barrier (warp 7)
+        //      window entry (warp 7, lane = cell), the splits inside the two diagonal blocks (warps 5 and 6, before their
+        //      cells), then FML once the three warps met at a named barrier (warp 7)
         // C(t) only reads cells of steps <= t-2 and the split minima of step t-2; FML(t-1) reads FML of steps <= t-2.
 #ifdef SFB_MFE4_TIMING
         long long tm_busy = 0, tm_loop0 = clock64(), tm_a = 0, tm_b = 0;
@@ -459,7 +459,7 @@ mfe4_block_kernel(Mfe4Launch L, const MfeTables *__restrict__ T, const Tab4 *__r
                             gC[(size_t)j * NP + i] = cij;   // transposed copy for the exterior loop
                         }
                     }
-                    // the splits inside the two diagonal blocks come from warps 0 and 1 (below) through Db
+                    // the splits inside the two diagonal blocks come from warps 5 and 6 (below) through Db
                     asm volatile("bar.sync 1, 96;" ::: "memory");
                     int dec = 2 * INF;
                     if (active) {
@@ -483,9 +483,9 @@ mfe4_block_kernel(Mfe4Launch L, const MfeTables *__restrict__ T, const Tab4 *__r
                     }
                 }
             } else {
-              if (warp < 2 && t > s_begin) {
+              if (warp >= 5 && t > s_begin) {   // the two interior-loop warps with the fewest cells (round robin from warp 2)
                 // ---- F, split part: the splits of step t - 1 inside the two diagonal blocks, lane = cell.  m = i0 + c (rows
-                // below, 31 - a terms: warp 0) and m = j0 + c (columns to the left, b + 1 terms: warp 1).  Both loops run over
+                // below, 31 - a terms: warp 5) and m = j0 + c (columns to the left, b + 1 terms: warp 6).  Both loops run over
                 // warp-uniform ranges WITHOUT a per-lane test: outside a lane's own range one operand is a cell of this block
                 // that a later step computes -- still INF in Mb -- so the sum stays above INF / 2 whatever the other operand
                 // reads (neighbouring entries of the triangles).  The minima meet the far splits in Db (shared-memory
@@ -496,12 +496,12 @@ mfe4_block_kernel(Mfe4Launch L, const MfeTables *__restrict__ T, const Tab4 *__r
                 const int a_lo = 31 - s + blo, b_hi = blo + nc - 1;   // smallest a / largest b of the step
                 int dec = 2 * INF;
                 if (delta == 0) {   // a < c <= b: FML[i][m-1] + FML[m][j], both inside this block
-                    if (warp == 0) {
+                    if (warp == 5) {
                         const int *pa = Mb + a * 34, *pb = Mb + b + 1;
 #pragma unroll 4
                         for (int c = a_lo + 1; c <= b_hi; c++) dec = __viaddmin_s32(pa[c], pb[c * 34], dec);
                     }
-                } else if (warp == 0) {
+                } else if (warp == 5) {
                     const int *pa = Mii + tri32(a, a) - a - 1, *pb = Mb + b + 1;   // pa[c] = Mii[a][c-1]
 #pragma unroll 4
                     for (int c = a_lo + 1; c < 32; c++) dec = __viaddmin_s32(pa[c], pb[c * 34], dec);
