@@ -448,8 +448,19 @@ pf2_kernel(PfLaunch L, const MfeTables *__restrict__ MT, const PfTables *__restr
                 const int i = k, nj = W - l - 6;
                 double acc = 0.;
                 if (nj > 0 && i <= l - TURN - 1) {
+                    // PM streams from L2: four independent loads in flight per lane instead of one per trip
                     const int j0 = l + 6 + nj * s / 4, j1 = l + 6 + nj * (s + 1) / 4;
-                    for (int j = j0; j < j1; j++) acc = fma(pmG[j * P2 + i], sm.qm[qmidx(j - 1, l + 1)], acc);
+                    double acc2 = 0.;
+                    int j = j0;
+                    for (; j + 3 < j1; j += 4) {
+                        const double p0 = pmG[j * P2 + i], p1 = pmG[(j + 1) * P2 + i], p2 = pmG[(j + 2) * P2 + i], p3 = pmG[(j + 3) * P2 + i];
+                        acc = fma(p0, sm.qm[qmidx(j - 1, l + 1)], acc);
+                        acc2 = fma(p1, sm.qm[qmidx(j, l + 1)], acc2);
+                        acc = fma(p2, sm.qm[qmidx(j + 1, l + 1)], acc);
+                        acc2 = fma(p3, sm.qm[qmidx(j + 2, l + 1)], acc2);
+                    }
+                    for (; j < j1; j++) acc = fma(pmG[j * P2 + i], sm.qm[qmidx(j - 1, l + 1)], acc);
+                    acc += acc2;
                 }
                 if (i < P2) sm.partC[s][i] = acc;
                 if (warp == 15) {   // q3[l] for the next column
