@@ -38,16 +38,21 @@ constexpr int QROWS = (P2 + 3) / 2 + 1;
 constexpr int NT2 = 512, NW2 = NT2 / 32;
 constexpr int NG = 8;            // inside: partial sums of the multiloop product (one warp each)
 constexpr int NH = 7;            // outside: partial sums of H
-constexpr int NX = 3;            // outside: partial sums of X1
 constexpr int PP = 128;          // pitch of the per-cell arrays
+constexpr int PRW = 10;          // doubles per cell parameter row
+enum { PR_MMI = 0, PR_MM1, PR_TAU, PR_MLC, PR_FI, PR_F1, PR_FB, PR_FM, PR_ONE, PR_ZERO };
 
 __device__ double g_K2[32 * 32];  // [u2][u1]: size factor of the separable candidate (u1, u2), 0 for the table-driven ones
 
-// the small Boltzmann-factor tables the per-cell code looks up (same member names as PfTables): a shared-memory copy
+// the small Boltzmann-factor tables the per-cell code looks up: a shared-memory copy per CTA.  Neighbour codes of the
+// stem tables run 0..5, 5 = no neighbour (window border)
 struct PfHead {
-    double expmismatchI[8][5][5], expmismatch1nI[8][5][5], expmismatchM[8][5][5], expmismatchExt[8][5][5];
-    double expdangle5[8][5], expdangle3[8][5];
-    double expMLintern, expTermAU;
+    double expmismatchI[8][5][5], expmismatch1nI[8][5][5], expmismatch23I[8][5][5], expmismatchH[8][5][5];
+    double mlstem[8][6][6];   // E_MLstem factor: mismatchM / dangle5 / dangle3, TerminalAU, MLintern
+    double ext[8][6][6];      // exterior stem factor likewise (no MLintern)
+    double expstack[8][8];
+    double tau[8];            // TerminalAU factor by pair type
+    double one, zero, expbulge1, il5;   // il5 = expinternal[5] * expninio[1]  (2x3 loops)
 };
 
 struct Smem2 {
@@ -56,27 +61,35 @@ struct Smem2 {
     double ringq[8][P2];        // raw qb (inside) / raw P (outside) of the last columns: table-driven shapes
     double qm[QROWS * PQ];      // folded: row = 3' end k', entries i <= k'-4
     double partC[NG][PP];       // partial multiloop sums (inside: qq; outside: H)
-    double partX[NX][PP];       // outside: partial X1 of the next column
+    double prm[PP][PRW];        // per listed cell: the outer factors the candidate walk's reduction and stores need
     double partA[PP];           // outside: interior-loop sum of the listed cells
-    double partS[PP];           // table-driven shapes (+ hairpin) of the coming column
-    double qm1[2][PP];
+    double partS1a[4][PP];      // table-driven shapes with u2 >= 1 and the hairpin of even columns, by computing warp
+    union {
+        struct {
+            double partS1b[4][PP];   // the same for odd columns
+            double partS0[2][PP];    // the two shapes with u2 = 0 (they need the column just finished)
+            double qm1[2][PP];
+        } in;                        // inside pass only
+        double x1buf[2][4][PP];      // outside pass: X1 of a column (partial sums of the four streaming warps), by parity
+    } u;
     double ecol[PP];
-    double x1[PP], x2[PP], x12[PP], g1[PP];
+    double x2[PP], x12[PP], g1[PP];
     double q5[PP], q3[PP];
     double qcol[PP];            // outside: qb of the current column
     double scale[P2 + 40], emlb[PP], ainv[PP];
     double red[32];
+    double junk[32];            // store target of the lanes that have nothing to write
     short cen[PP];
     unsigned char S[PP];
-    unsigned char ty[2][PP];    // pair type of the cells of a column (0: not pairable)
-    unsigned char list[2][PP];  // 5' ends of the cells the candidate walk visits
+    unsigned char Sx[PP + 8];   // Sx[k+1] = code of nucleotide k, Sx[0] = Sx[W+1] = 5
+    unsigned char ty[4][PP];    // pair type of the cells of a column (0: not pairable), by column & 3
+    unsigned char list[4][PP];  // 5' ends of the cells the candidate walk visits
     unsigned char can5[PP], can3[PP];   // hard constraints: may be the 5' / 3' partner of a pair
-    int cnt[2];
+    int cnt[4];
 #ifdef SFB_PF2_TIMING
     long long tstamp[2][16];
 #endif
 };
-
 static_assert(sizeof(Smem2) <= 227 * 1024, "one window per SM");
 
 template <int A, int B, class F>
@@ -89,9 +102,10 @@ __device__ __forceinline__ void sfor2(F &&f) {
 
 // Separable candidates of one cell: lane = u2, u1 = 0 .. u1max.  pB / p1 / pM point at position u1 = 0 of the bulge /
 // 1xn / lane-class copy in this lane's column; inside steps up the positions, outside down.  Returns the lane-class sum
-// (u1 >= 2); accB (u1 = 0: bulges) and acc1 (u1 = 1: 1xn loops) take their own outer factor.
+// (u1 >= 2); accB (u1 = 0: bulges) and acc1 (u1 = 1: 1xn loops) take their own outer factor.  From u1 = 15 on only
+// lanes 0..15 have candidates (u1 + u2 <= 30): the upper half warp skips the load (one wavefront instead of two).
 template <bool OUT>
-__device__ __forceinline__ double cand_walk(const double *pB, const double *p1, const double *pM, int u1max,
+__device__ __forceinline__ double cand_walk(const double *pB, const double *p1, const double *pM, int u1max, bool lo,
                                             const double (&K)[MAXLOOP + 1], double &accB, double &acc1) {
     constexpr int ST = OUT ? -PT : PT;
     accB = pB[0] * K[0];
@@ -103,85 +117,17 @@ __device__ __forceinline__ double cand_walk(const double *pB, const double *p1, 
             sfor2<0, 3>([&](auto V) {
                 constexpr int u1 = g + decltype(V)::value;
                 if constexpr (u1 <= MAXLOOP) {
-                    if constexpr (u1 & 1)
-                        a1 = fma(pM[u1 * ST], K[u1], a1);
-                    else
-                        a0 = fma(pM[u1 * ST], K[u1], a0);
+                    if (u1 < 15 || lo) {
+                        if constexpr (u1 & 1)
+                            a1 = fma(pM[u1 * ST], K[u1], a1);
+                        else
+                            a0 = fma(pM[u1 * ST], K[u1], a0);
+                    }
                 }
             });
         }
     });
     return a0 + a1;
-}
-
-struct Ctx2 {
-    const PfTables *T;
-    const MfeTables *M;
-    const unsigned char *S;
-    const double *scale;
-    int W;
-};
-
-__device__ double hairpin2(const Ctx2 &c, int i, int j, int type) {
-    const int u = j - i - 1;
-    const double z = c.T->exphairpin_len[u];
-    if (u < 3) return z;
-    if (u == 4) {
-        const int key = loop_key_dev(c.S, i, 6);
-        for (int k = 0; k < c.M->n_tetra; k++)
-            if (c.M->tetra_key[k] == key) return c.T->exptetra[k];
-    } else if (u == 6) {
-        const int key = loop_key_dev(c.S, i, 8);
-        for (int k = 0; k < c.M->n_hexa; k++)
-            if (c.M->hexa_key[k] == key) return c.T->exphexa[k];
-    } else if (u == 3) {
-        const int key = loop_key_dev(c.S, i, 5);
-        for (int k = 0; k < c.M->n_tri; k++)
-            if (c.M->tri_key[k] == key) return c.T->exptri[k];
-        return type > 2 ? z * c.T->expTermAU : z;
-    }
-    return z * c.T->expmismatchH[type][c.S[i + 1]][c.S[j - 1]];
-}
-
-// the nine table-driven shapes, Boltzmann factor without the length scaling
-__device__ __forceinline__ double shape2(const PfTables *T, int u1, int u2, int type, int t2, int si1, int sj1, int sp1,
-                                         int sq1) {
-    const int ul = max(u1, u2), us = min(u1, u2);
-    if (ul == 0) return T->expstack[type][t2];
-    if (us == 0) return T->expbulge[1] * T->expstack[type][t2];   // bulge of one
-    if (us == 1) {
-        if (ul == 1) return T->expint11[type][t2][si1][sj1];
-        if (u1 == 1) return T->expint21[type][t2][si1][sq1][sj1];
-        return T->expint21[t2][type][sq1][si1][sp1];
-    }
-    if (ul == 2) return T->expint22[type][t2][si1][sp1][sq1][sj1];
-    return T->expinternal[5] * T->expmismatch23I[type][si1][sj1] * T->expmismatch23I[t2][sq1][sp1] * T->expninio[1];
-}
-
-template <class TT>
-__device__ __forceinline__ double mlstem2(const TT *T, int type, int si1, int sj1) {
-    double z = 1.;
-    if (si1 >= 0 && sj1 >= 0)
-        z = T->expmismatchM[type][si1][sj1];
-    else if (si1 >= 0)
-        z = T->expdangle5[type][si1];
-    else if (sj1 >= 0)
-        z = T->expdangle3[type][sj1];
-    if (type > 2) z *= T->expTermAU;
-    return z * T->expMLintern;
-}
-
-template <class TT>
-__device__ __forceinline__ double extloop2(const TT *T, int type, int si1, int sj1) {
-    double z = 1.;
-    if (si1 >= 0 && sj1 >= 0)
-        z = T->expmismatchExt[type][si1][sj1];
-    else if (si1 >= 0)
-        z = T->expdangle5[type][si1];
-    else if (sj1 >= 0)
-        z = T->expdangle3[type][sj1];
-    if (type > 2) z *= T->expTermAU;
-    return z;
 }
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -193,39 +139,45 @@ __device__ __forceinline__ double warp_sum(double v) {
 __host__ __device__ constexpr int shape_u1(int z) { return (int)((0x322211100ull >> (4 * z)) & 15); }
 __host__ __device__ constexpr int shape_u2(int z) { return (int)((0x232121010ull >> (4 * z)) & 15); }
 
-// the nine table-driven shapes closed by (i,j) plus the hairpin, lane = cell; every load is unconditional (a cell that
-// is no pair carries weight 0), so the table loads of all shapes are in flight together
-__device__ __forceinline__ double shapes_inside(const Smem2 &sm, const PfTables *T, const Ctx2 &c, int i, int j, int t) {
-    const unsigned char *S = sm.S;
-    const int si1 = S[i + 1], sj1 = S[j - 1];
-    double acc = 0.;
-    sfor2<0, 8>([&](auto Z) {
-        constexpr int z = decltype(Z)::value, u1 = shape_u1(z), u2 = shape_u2(z);
-        const int p = i + 1 + u1, q = j - 1 - u2;
-        const double qpq = sm.ringq[q & 7][p];
-        const int t2 = rtype_of(pair_type(S[p], S[q]));
-        const double f = shape2(T, u1, u2, t, t2, si1, sj1, S[p - 1], S[q + 1]) * sm.scale[u1 + u2 + 2];
-        acc += qpq != 0. ? qpq * f : 0.;
-    });
-    return acc + hairpin2(c, i, j, t) * sm.scale[j - i + 1];
+// Boltzmann factor of table-driven shape Z (closing pair type t with neighbours si1 = S[i+1], sj1 = S[j-1]; inner pair
+// type t2 -- as seen from inside the loop -- with sp1 = S[p-1], sq1 = S[q+1]) without the length scaling
+template <int Z>
+__device__ __forceinline__ double shape_f(const PfHead *TH, const PfTables *T, int t, int t2, int si1, int sj1, int sp1, int sq1) {
+    constexpr int u1 = shape_u1(Z), u2 = shape_u2(Z);
+    constexpr int ul = u1 > u2 ? u1 : u2, us = u1 > u2 ? u2 : u1;
+    if constexpr (ul == 0) return TH->expstack[t][t2];
+    else if constexpr (us == 0) return TH->expbulge1 * TH->expstack[t][t2];   // bulge of one
+    else if constexpr (us == 1 && ul == 1) return T->expint11[t][t2][si1][sj1];
+    else if constexpr (us == 1 && u1 == 1) return T->expint21[t][t2][si1][sq1][sj1];
+    else if constexpr (us == 1) return T->expint21[t2][t][sq1][si1][sp1];
+    else if constexpr (ul == 2) return T->expint22[t][t2][si1][sp1][sq1][sj1];
+    else return TH->il5 * TH->expmismatch23I[t][si1][sj1] * TH->expmismatch23I[t2][sq1][sp1];
 }
 
-// the same for the outside pass: (k,l) is the inner pair, (i,j) = (k-1-u1, l+1+u2) the closing one
-__device__ __forceinline__ double shapes_outside(const Smem2 &sm, const PfTables *T, int k, int l, int t2, int W) {
+// shape Z closed by (i,j) from inside: weight of the inner pair times the factor; a cell that is no pair has weight 0
+template <int Z>
+__device__ __forceinline__ double shape_in(const Smem2 &sm, const PfTables *T, int i, int j, int t) {
+    constexpr int u1 = shape_u1(Z), u2 = shape_u2(Z);
     const unsigned char *S = sm.S;
-    const int sp1 = S[k - 1], sq1 = S[l + 1];
-    double acc = 0.;
-    sfor2<0, 8>([&](auto Z) {
-        constexpr int z = decltype(Z)::value, u1 = shape_u1(z), u2 = shape_u2(z);
-        const int i = k - 1 - u1, j = l + 1 + u2;
-        const bool ok = i >= 0 && j <= W - 1;
-        const int ic = max(i, 0), jc = min(j, W - 1);
-        const double pij = ok ? sm.ringq[jc & 7][ic] : 0.;
-        const int tij = pair_type(S[ic], S[jc]);
-        const double f = shape2(T, u1, u2, tij, t2, S[ic + 1], S[jc - 1], sp1, sq1) * sm.scale[u1 + u2 + 2];
-        acc += pij > 0. ? pij * f : 0.;
-    });
-    return acc;
+    const int p = i + 1 + u1, q = j - 1 - u2;
+    const double qpq = sm.ringq[q & 7][p];
+    const int t2 = rtype_of(pair_type(S[p], S[q]));
+    const double f = shape_f<Z>(&sm.th, T, t, t2, S[i + 1], S[j - 1], S[p - 1], S[q + 1]) * sm.scale[u1 + u2 + 2];
+    return qpq != 0. ? qpq * f : 0.;
+}
+
+// shape Z around the inner pair (k,l) from outside: (i,j) = (k-1-u1, l+1+u2) is the closing pair
+template <int Z>
+__device__ __forceinline__ double shape_out(const Smem2 &sm, const PfTables *T, int k, int l, int t2, int W) {
+    constexpr int u1 = shape_u1(Z), u2 = shape_u2(Z);
+    const unsigned char *S = sm.S;
+    const int i = k - 1 - u1, j = l + 1 + u2;
+    const bool ok = i >= 0 && j <= W - 1;
+    const int ic = max(i, 0), jc = min(j, W - 1);
+    const double pij = ok ? sm.ringq[jc & 7][ic] : 0.;
+    const int tij = pair_type(S[ic], S[jc]);
+    const double f = shape_f<Z>(&sm.th, T, tij, t2, S[ic + 1], S[jc - 1], S[k - 1], S[l + 1]) * sm.scale[u1 + u2 + 2];
+    return pij > 0. ? pij * f : 0.;
 }
 
 #ifdef SFB_PF2_TIMING
@@ -251,10 +203,8 @@ __device__ __forceinline__ double shapes_outside(const Smem2 &sm, const PfTables
         tprobe[k] += now_ - tp_;                                        \
         tp_ = now_;                                                     \
     }
-#define PF2_PROBE0 asm volatile("mov.u64 %0, %%clock64;" : "=l"(tp_)::"memory");
 #else
 #define PF2_PROBE(k)
-#define PF2_PROBE0
 #define PF2_SYNC(slot) __syncthreads();
 #define PF2_RESET
 #endif
@@ -280,19 +230,33 @@ pf2_kernel(PfLaunch L, const MfeTables *__restrict__ MT, const PfTables *__restr
     for (int k = tid; k < 200; k += NT2) {
         (&sm.th.expmismatchI[0][0][0])[k] = (&T->expmismatchI[0][0][0])[k];
         (&sm.th.expmismatch1nI[0][0][0])[k] = (&T->expmismatch1nI[0][0][0])[k];
-        (&sm.th.expmismatchM[0][0][0])[k] = (&T->expmismatchM[0][0][0])[k];
-        (&sm.th.expmismatchExt[0][0][0])[k] = (&T->expmismatchExt[0][0][0])[k];
-        if (k < 40) {
-            (&sm.th.expdangle5[0][0])[k] = (&T->expdangle5[0][0])[k];
-            (&sm.th.expdangle3[0][0])[k] = (&T->expdangle3[0][0])[k];
-        }
+        (&sm.th.expmismatch23I[0][0][0])[k] = (&T->expmismatch23I[0][0][0])[k];
+        (&sm.th.expmismatchH[0][0][0])[k] = (&T->expmismatchH[0][0][0])[k];
+        if (k < 64) (&sm.th.expstack[0][0])[k] = (&T->expstack[0][0])[k];
+        if (k < 8) sm.th.tau[k] = k > 2 ? T->expTermAU : 1.;
     }
-    if (tid == 0) {
-        sm.th.expMLintern = T->expMLintern;
-        sm.th.expTermAU = T->expTermAU;
+    for (int k = tid; k < 8 * 36; k += NT2) {
+        const int t = k / 36, a = (k / 6) % 6, b = k % 6;
+        double z = 1.;
+        double ze = 1.;
+        if (a < 5 && b < 5) {
+            z = T->expmismatchM[t][a][b];
+            ze = T->expmismatchExt[t][a][b];
+        } else if (a < 5) {
+            z = ze = T->expdangle5[t][a];
+        } else if (b < 5) {
+            z = ze = T->expdangle3[t][b];
+        }
+        const double au = t > 2 ? T->expTermAU : 1.;
+        sm.th.mlstem[t][a][b] = z * au * T->expMLintern;
+        sm.th.ext[t][a][b] = ze * au;
     }
     const PfHead *TH = &sm.th;
     if (tid == 0) {
+        sm.th.one = 1.;
+        sm.th.zero = 0.;
+        sm.th.expbulge1 = T->expbulge[1];
+        sm.th.il5 = T->expinternal[5] * T->expninio[1];
         sm.scale[0] = 1.;
         sm.emlb[0] = 1.;
         sm.ainv[0] = 1.;
@@ -308,157 +272,247 @@ pf2_kernel(PfLaunch L, const MfeTables *__restrict__ MT, const PfTables *__restr
     for (int u1 = 0; u1 <= MAXLOOP; u1++) K[u1] = g_K2[lane * 32 + u1];
     __syncthreads();
     const double sc1 = sm.scale[1], sc2 = sm.scale[2], eml1 = sm.emlb[1];
-    const double closing = T->expMLclosing, tAU = T->expTermAU;
-    Ctx2 c;
-    c.T = T;
-    c.M = MT;
-    c.S = sm.S;
-    c.scale = sm.scale;
-    c.W = W;
-    const unsigned char *S = sm.S;
-    auto nb = [&](int k) { return (k >= 0 && k < W) ? (int)S[k] : -1; };   // neighbour code or -1
+    const double closing = T->expMLclosing;
+    const unsigned char *S = sm.S, *Sx = sm.Sx;
     const int cls = lane == 0 ? 2 : (lane == 1 ? 1 : 0);   // ring copy of this lane's candidates with u1 >= 2
+    const bool lo = lane < 16;
 
-    // pairable cells of inside column j -> ty / list / cnt of parity j & 1 (one warp)
+    // pairable cells of inside column j -> ty / list / cnt of slot j & 3 (one warp)
     auto build_list_inside = [&](int j) {
-        int n = 0;
-        const bool c3 = j < W && sm.can3[j];
+        const bool c3 = j < W && sm.can3[min(j, PP - 1)];
+        const int sj = S[min(j, PP - 1)];
+        int t[PP / 32];
+#pragma unroll
         for (int b = 0; b < PP / 32; b++) {
             const int i = b * 32 + lane;
-            const int t = (c3 && i <= j - TURN - 1 && sm.can5[i]) ? pair_type(S[i], S[j]) : 0;
-            sm.ty[j & 1][i] = (unsigned char)t;
-            const unsigned m = __ballot_sync(full, t != 0);
-            if (t) sm.list[j & 1][n + __popc(m & ((1u << lane) - 1))] = (unsigned char)i;
+            t[b] = (c3 && i <= j - TURN - 1 && sm.can5[i]) ? pair_type(S[i], sj) : 0;
+        }
+        int n = 0;
+#pragma unroll
+        for (int b = 0; b < PP / 32; b++) {
+            const int i = b * 32 + lane;
+            sm.ty[j & 3][i] = (unsigned char)t[b];
+            const unsigned m = __ballot_sync(full, t[b] != 0);
+            if (t[b]) sm.list[j & 3][n + __popc(m & ((1u << lane) - 1))] = (unsigned char)i;
             n += __popc(m);
         }
-        if (lane == 0) sm.cnt[j & 1] = n;
+        if (lane == 0) sm.cnt[j & 3] = n;
     };
-    // table-driven shapes + hairpin of inside column j, cells 32 b .. 32 b + 31 (one warp)
-    auto shapes_unit_inside = [&](int j, int b) {
-        const int i = b * 32 + lane;
-        double v = 0.;
-        if (j < W && i <= j - TURN - 1 && sm.can5[i] && sm.can3[j]) {
-            const int t = pair_type(S[i], S[j]);
-            if (t) v = shapes_inside(sm, T, c, i, j, t);
+    // outer factors of the listed cells of inside column j (lane = listed cell): what the walk multiplies its class sums
+    // with, the multiloop closing factor, the factors of the ring copies / qm1 the cell's qb is stored with
+    auto cell_params_inside = [&](int j) {
+        if (j >= W) return;
+        const int n = sm.cnt[j & 3];
+        for (int cc = lane; cc < n; cc += 32) {
+            const int i = sm.list[j & 3][cc], t = sm.ty[j & 3][i], t2 = rtype_of(t);
+            const int si1 = S[i + 1], sj1 = S[j - 1];
+            const bool inner = i > 0 && j < W - 1;   // (i,j) can be the inner pair of an enclosing loop
+            const int a = Sx[j + 2] % 5, b = Sx[i] % 5;
+            double *r = sm.prm[cc];
+            r[PR_MMI] = TH->expmismatchI[t][si1][sj1];
+            r[PR_MM1] = TH->expmismatch1nI[t][si1][sj1];
+            r[PR_TAU] = TH->tau[t];
+            r[PR_MLC] = closing * TH->mlstem[t2][sj1][si1] * sc2;
+            r[PR_FI] = inner ? TH->expmismatchI[t2][a][b] : 0.;
+            r[PR_F1] = inner ? TH->expmismatch1nI[t2][a][b] : 0.;
+            r[PR_FB] = inner ? TH->tau[t2] : 0.;
+            r[PR_FM] = TH->mlstem[t][Sx[i]][Sx[j + 2]];
+            r[PR_ONE] = 1.;
+            r[PR_ZERO] = 0.;
         }
-        sm.partS[i] = v;
+    };
+    // hairpin closed by (i,j): the general formula per lane; loops of 3, 4 and 6 nucleotides are left to
+    // special_hairpins (tabulated tri- / tetra- / hexaloops)
+    auto hairpin_f = [&](int i, int j, int t) {
+        const int u = j - i - 1;
+        if (u == 3 || u == 4 || u == 6) return 0.;
+        return T->exphairpin_len[u] * TH->expmismatchH[t][S[i + 1]][S[j - 1]];
+    };
+    // the three cells of column j that close a loop of 3, 4 or 6: the key tables are searched by the whole warp (first
+    // match in table order wins, as in the serial search); adds the hairpin term to the cell's slice
+    auto special_hairpins = [&](int j, double(*ps)[PP]) {
+        double val[3];
+        bool have[3];
+#pragma unroll
+        for (int z = 0; z < 3; z++) {
+            const int u = z == 0 ? 3 : (z == 1 ? 4 : 6), i = j - u - 1;
+            const int t = i >= 0 ? sm.ty[j & 3][i] : 0;
+            have[z] = t != 0;
+            val[z] = 0.;
+            if (have[z]) {   // warp-uniform
+                const int key = loop_key_dev(S, i, u + 2);
+                const int n = z == 0 ? MT->n_tri : (z == 1 ? MT->n_tetra : MT->n_hexa);
+                const int *keys = z == 0 ? MT->tri_key : (z == 1 ? MT->tetra_key : MT->hexa_key);
+                const unsigned m0 = __ballot_sync(full, lane < n && keys[lane] == key);
+                const unsigned m1 = __ballot_sync(full, lane + 32 < n && keys[lane + 32] == key);
+                const int hit = m0 ? __ffs(m0) - 1 : (m1 ? 32 + __ffs(m1) - 1 : -1);
+                const double z0 = T->exphairpin_len[u];
+                if (hit >= 0)
+                    val[z] = z == 0 ? T->exptri[hit] : (z == 1 ? T->exptetra[hit] : T->exphexa[hit]);
+                else
+                    val[z] = z == 0 ? z0 * TH->tau[t] : z0 * TH->expmismatchH[t][S[i + 1]][S[j - 1]];
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int z = 0; z < 3; z++) {
+            const int u = z == 0 ? 3 : (z == 1 ? 4 : 6), i = j - u - 1;
+            if (have[z] && lane == 0) ps[3][i] += val[z] * sm.scale[u + 2];
+        }
+    };
+    // shapes with u2 >= 1 and the hairpin of inside column j, two items per warp w = 0..3, lane = listed cell
+    auto shapes1_unit = [&](int j, int w) {
+        if (j >= W) return;
+        const int n = sm.cnt[j & 3];
+        for (int cc = lane; cc < n; cc += 32) {
+            const int i = sm.list[j & 3][cc], t = sm.ty[j & 3][i];
+            double v;
+            if (w == 0)
+                v = shape_in<6>(sm, T, i, j, t) + shape_in<1>(sm, T, i, j, t);
+            else if (w == 1)
+                v = shape_in<4>(sm, T, i, j, t) + shape_in<7>(sm, T, i, j, t);
+            else if (w == 2)
+                v = shape_in<5>(sm, T, i, j, t) + shape_in<8>(sm, T, i, j, t);
+            else
+                v = shape_in<3>(sm, T, i, j, t) + hairpin_f(i, j, t) * sm.scale[j - i + 1];
+            (j & 1 ? sm.u.in.partS1b : sm.partS1a)[w][i] = v;
+        }
+        if (w == 3) {
+            __syncwarp();
+            special_hairpins(j, j & 1 ? sm.u.in.partS1b : sm.partS1a);
+        }
+    };
+    // the two shapes with u2 = 0 (stack, bulge of one on the 5' side) of inside column j, w = 0 / 1
+    auto shapes0_unit = [&](int j, int w) {
+        if (j >= W) return;
+        const int n = sm.cnt[j & 3];
+        for (int cc = lane; cc < n; cc += 32) {
+            const int i = sm.list[j & 3][cc], t = sm.ty[j & 3][i];
+            sm.u.in.partS0[w][i] = w == 0 ? shape_in<0>(sm, T, i, j, t) : shape_in<2>(sm, T, i, j, t);
+        }
     };
 
     for (int fold = blockIdx.x; fold < L.n_fold; fold += gridDim.x) {
         __syncthreads();
         for (int k = tid; k < PP; k += NT2) {
             const bool in = k < W;
-            sm.S[k] = in ? L.seqs[(long long)fold * W + k] : 4;
+            const int code = in ? L.seqs[(long long)fold * W + k] : 4;
+            sm.S[k] = (unsigned char)code;
+            if (k + 1 < PP + 8) sm.Sx[k + 1] = (unsigned char)(in ? code : 5);
+            if (k == 0) sm.Sx[0] = 5;
             const char ch = (L.hc && in) ? (char)L.hc[(long long)fold * W + k] : '.';
             sm.can5[k] = in && !(ch == 'x' || ch == '>');
             sm.can3[k] = in && !(ch == 'x' || ch == '<');
             sm.cen[k] = 0;
-            sm.qm1[0][k] = 0.;
-            sm.qm1[1][k] = 0.;
+            sm.u.in.qm1[0][k] = 0.;
+            sm.u.in.qm1[1][k] = 0.;
             sm.ecol[k] = 0.;
-            sm.x1[k] = 0.;
             sm.x2[k] = 0.;
             sm.x12[k] = 0.;
             sm.g1[k] = 0.;
             sm.partA[k] = 0.;
-            sm.partS[k] = 0.;
+            sm.u.in.partS0[0][k] = 0.;
+            sm.u.in.partS0[1][k] = 0.;
         }
         for (int k = tid; k < 3 * RING; k += NT2) sm.ring[k] = 0.;
         for (int k = tid; k < 8 * P2; k += NT2) (&sm.ringq[0][0])[k] = 0.;
         for (int k = tid; k < NG * PP; k += NT2) (&sm.partC[0][0])[k] = 0.;
-        for (int k = tid; k < NX * PP; k += NT2) (&sm.partX[0][0])[k] = 0.;
+        for (int k = tid; k < 4 * PP; k += NT2) {
+            (&sm.partS1a[0][0])[k] = 0.;
+            (&sm.u.in.partS1b[0][0])[k] = 0.;
+        }
         if (tid == 0) {
             sm.q5[0] = 1.;
             for (int k = 1; k <= min(W, TURN + 1); k++) sm.q5[k] = sm.q5[k - 1] * sc1;
         }
         __syncthreads();
-        if (warp == 15) build_list_inside(TURN + 1);
-        if (warp >= 8 && warp < 12) shapes_unit_inside(TURN + 1, warp - 8);
+        if (warp == 14) build_list_inside(TURN + 1);
+        if (warp == 15) build_list_inside(TURN + 2);
         __syncthreads();
-
+        if (warp >= 8 && warp < 12) shapes1_unit(TURN + 1, warp - 8);   // hairpins: all the first column can close
+        if (warp == 14) cell_params_inside(TURN + 1);
+        __syncthreads();
         PF2_RESET
         // ================= inside, column j =================
         for (int j = TURN + 1; j < W; j++) {
-            const int par = j & 1;
-            // ---- phase 1: the candidate walk of the pairable cells; beside it (warps 0-3, lane = cell) the cells that
-            // are no pair and qm of the previous column
-            if (warp < 4) {
-                const int i = tid;
-                if (!sm.ty[par][i] && i < P2) {
+            const int par = j & 1, sl = j & 3;
+            // ---- phase 1: the candidate walk of the pairable cells (all warps); first, beside it: shapes with u2 >= 1
+            // of the next column (warps 8-11), the cells that are no pair and qm of the previous column (warps 12-15)
+            if (warp >= 12) {
+                const int i = tid - 12 * 32;
+                if (!sm.ty[sl][i] && i < P2) {
                     sm.ringq[j & 7][i] = 0.;
                     if (i < W) qbG[j * P2 + i] = 0.;
-                    sm.qm1[par][i] = i <= j - TURN - 2 ? sm.qm1[par ^ 1][i] * eml1 : 0.;
+                    sm.u.in.qm1[par][i] = i <= j - TURN - 2 ? sm.u.in.qm1[par ^ 1][i] * eml1 : 0.;
                 }
                 if (j - 1 > TURN && i <= j - TURN - 2) {
                     double qq = 0.;
 #pragma unroll
                     for (int g = 0; g < NG; g++) qq += sm.partC[g][i];
-                    sm.qm[qmrow(j - 1) + i] = sm.qm1[par ^ 1][i] + sm.ecol[i] + qq;
+                    sm.qm[qmrow(j - 1) + i] = sm.u.in.qm1[par ^ 1][i] + sm.ecol[i] + qq;
                 }
+            } else if (warp >= 8) {
+                shapes1_unit(j + 1, warp - 8);
             }
             {
-                const int n = sm.cnt[par];
-                const double *qm1p = sm.qm1[par ^ 1];
-                PF2_PROBE0
-                for (int cc = (warp + NW2 - 4) & (NW2 - 1); cc < n; cc += NW2) {
-                    PF2_PROBE(3)
-                    const int i = sm.list[par][cc];
-                    const int t = sm.ty[par][i];
-                    const int si1 = S[i + 1], sj1 = S[j - 1];
-                    const double mmI = TH->expmismatchI[t][si1][sj1], mm1 = TH->expmismatch1nI[t][si1][sj1];
-                    const double tau = t > 2 ? tAU : 1.;
+                const int n = sm.cnt[sl];
+                const double *qm1p = sm.u.in.qm1[par ^ 1];
+                // per-lane roles (no divergence inside the cell loop): what the lane adds to the reduction beside its
+                // candidates -- lanes 0..NG-1 a partial sum of the multiloop closed by (i,j) (previous column's products),
+                // the next six a slice of the table-driven shapes -- and what it stores once qb is known: ring copies
+                // (lanes 0-2), the raw copy (3), qm1 (4)
+                const double *ebase = lane < NG ? &sm.partC[lane][1]
+                                                : (lane < NG + 4 ? &(par ? sm.u.in.partS1b : sm.partS1a)[lane - NG][0]
+                                                                 : (lane < NG + 6 ? &sm.u.in.partS0[lane - NG - 4][0] : &sm.prm[0][PR_ZERO]));
+                const int estride = lane < NG + 6 ? 1 : 0;
+                const int ixE = lane < NG ? PR_MLC : PR_ONE;
+                const int ixM = lane == 0 ? PR_TAU : (lane == 1 ? PR_MM1 : PR_MMI);
+                const int ixF = lane < 3 ? PR_FI + lane : (lane == 3 ? PR_ONE : (lane == 4 ? PR_FM : PR_ZERO));
+                double *dbase = lane < 3 ? &sm.ring[lane * RING + RPAD * PT + (j & 31)]
+                                         : (lane == 3 ? &sm.ringq[j & 7][0] : (lane == 4 ? &sm.u.in.qm1[par][0] : &sm.junk[lane]));
+                const int dstride = lane < 3 ? PT : (lane < 5 ? 1 : 0);
+                const double emlL = lane == 4 ? eml1 : 0.;
+                // warps 0-7 have no other unit in this phase: they take two of every 24 cells, the others one
+                for (int c0 = warp < 8 ? warp : warp + 8; c0 < n; c0 = (warp < 8 && c0 % 24 < 8) ? c0 + 8 : c0 + (warp < 8 ? 16 : 24)) {
+                    const int cc = c0;
+                    const int i = sm.list[sl][cc];
+                    const double *r = sm.prm[cc];
+                    const double tau = r[PR_TAU], mm1 = r[PR_MM1];
+                    const double mulM = r[ixM], ext = ebase[i * estride] * r[ixE], fm = r[ixF];
+                    const double fa = i <= j - TURN - 2 ? qm1p[i] * emlL : 0.;
                     const double *pb = sm.ring + (i + 1 + RPAD) * PT + ((j - 1 - lane) & 31);
                     double accB, acc1;
-                    const double aM = cand_walk<false>(pb + 2 * RING, pb + RING, pb + cls * RING, min(MAXLOOP, j - i - 6), K, accB, acc1);
-                    PF2_PROBE(0)
-                    double v = aM * (lane == 0 ? tau : (lane == 1 ? mm1 : mmI)) + accB * tau + acc1 * mm1;
-                    if (lane < NG)   // multiloop closed by (i,j): the partial sums of the previous column join the reduction
-                        v = fma(sm.partC[lane][i + 1], closing * mlstem2(TH, rtype_of(t), sj1, si1) * sc2, v);
-                    else if (lane == NG)
-                        v += sm.partS[i];
+                    const double aM = cand_walk<false>(pb + 2 * RING, pb + RING, pb + cls * RING, min(MAXLOOP, j - i - 6), lo, K, accB, acc1);
+                    double v = aM * mulM + accB * tau + acc1 * mm1 + ext;
                     v = warp_sum(v);
-                    PF2_PROBE(1)
-                    // qb of the cell is known to every lane: ring copies, raw copy, qm1
-                    if (lane < 3) {
-                        double m = 0.;
-                        if (i > 0 && j < W - 1) {   // (i,j) as the inner pair of an enclosing loop
-                            const int t2 = rtype_of(t), a = S[j + 1], b = S[i - 1];
-                            m = lane == 0 ? TH->expmismatchI[t2][a][b] : (lane == 1 ? TH->expmismatch1nI[t2][a][b] : (t2 > 2 ? tAU : 1.));
-                        }
-                        sm.ring[lane * RING + (i + RPAD) * PT + (j & 31)] = v * m;
-                    } else if (lane == 3) {
-                        sm.ringq[j & 7][i] = v;
-                        qbG[j * P2 + i] = v;
-                    } else if (lane == 4) {
-                        const double m1 = i <= j - TURN - 2 ? qm1p[i] * eml1 : 0.;
-                        sm.qm1[par][i] = m1 + v * mlstem2(TH, t, nb(i - 1), nb(j + 1));
-                    }
-                    PF2_PROBE(2)
+                    dbase[i * dstride] = fma(v, fm, fa);
+                    if (lane == 3) qbG[j * P2 + i] = v;
                 }
             }
             PF2_SYNC(0)
             // ---- phase 2: one unit per warp
-            const double *qm1c = sm.qm1[par];
+            const double *qm1c = sm.u.in.qm1[par];
             if (warp < NG) {
                 // qq[i] = sum_k' qm[i,k'-1] qm1[k',j]: rows k' = 4 + warp, + NG, ..; lane = cell in four blocks
                 double a0 = 0., a1 = 0., a2 = 0., a3 = 0.;
-#pragma unroll 2
+#pragma unroll 4
                 for (int kk = 4 + warp; kk <= j - 5; kk += NG) {
                     const double w = qm1c[kk + 1];
                     const double *row = sm.qm + qmrow(kk) + lane;
                     const int lim = kk - 4 - lane;   // cell i = 32 b + lane takes part if 32 b <= lim
-                    if (lim >= 0) a0 = fma(row[0], w, a0);
-                    if (lim >= 32) a1 = fma(row[32], w, a1);
-                    if (lim >= 64) a2 = fma(row[64], w, a2);
-                    if (lim >= 96) a3 = fma(row[96], w, a3);
+                    const double v0 = row[0], v1 = row[32], v2 = row[64], v3 = row[96];
+                    a0 = fma(lim >= 0 ? v0 : 0., w, a0);
+                    a1 = fma(lim >= 32 ? v1 : 0., w, a1);
+                    a2 = fma(lim >= 64 ? v2 : 0., w, a2);
+                    a3 = fma(lim >= 96 ? v3 : 0., w, a3);
                 }
                 sm.partC[warp][lane] = a0;
                 sm.partC[warp][lane + 32] = a1;
                 sm.partC[warp][lane + 64] = a2;
                 sm.partC[warp][lane + 96] = a3;
-            } else if (warp < NG + 4) {
-                shapes_unit_inside(j + 1, warp - NG);
-            } else if (warp == 12) {
+            } else if (warp < NG + 2) {
+                shapes0_unit(j + 1, warp - NG);
+            } else if (warp == 10) {
                 // E[i] = sum_{k=i+1}^{j-4} eMLb[k-i] qm1[k,j] = ainv[i] * (suffix sum of eMLb[k] qm1[k,j])
                 double tk[4], tot = 0.;
 #pragma unroll
@@ -480,15 +534,16 @@ pf2_kernel(PfLaunch L, const MfeTables *__restrict__ MT, const PfTables *__restr
                     if (k < P2) sm.ecol[k] = run * sm.ainv[k];
                     run += tk[z];
                 }
-            } else if (warp == 13) {
+            } else if (warp == 11) {
                 double acc = 0.;
-                for (int i = lane; i <= j - TURN - 1; i += 32) {
-                    const int t = sm.ty[par][i];
-                    if (t) acc += sm.q5[i] * sm.ringq[j & 7][i] * extloop2(TH, t, nb(i - 1), nb(j + 1));
+                const int n = sm.cnt[sl];
+                for (int cc = lane; cc < n; cc += 32) {
+                    const int i = sm.list[sl][cc];
+                    acc += sm.q5[i] * sm.ringq[j & 7][i] * TH->ext[sm.ty[sl][i]][Sx[i]][Sx[j + 2]];
                 }
                 acc = warp_sum(acc);
                 if (lane == 0) sm.q5[j + 1] = sm.q5[j] * sc1 + acc;
-            } else if (warp == 14) {
+            } else if (warp == 12) {
                 // the ring column the next column writes: its last reader (column j) is done
                 const int slot = (j + 1) & 31;
                 for (int p = lane; p < RPOS; p += 32) {
@@ -496,89 +551,86 @@ pf2_kernel(PfLaunch L, const MfeTables *__restrict__ MT, const PfTables *__restr
                     sm.ring[RING + p * PT + slot] = 0.;
                     sm.ring[2 * RING + p * PT + slot] = 0.;
                 }
-            } else {
-                build_list_inside(j + 1);
+            } else if (warp == 13) {
+                build_list_inside(j + 2);
+            } else if (warp == 14) {
+                cell_params_inside(j + 1);
             }
             PF2_SYNC(2)
         }
-        const double Z = sm.q5[W];
+        const double Z = sm.q5[W], invZ = 1. / Z;
 
         // ================= outside, column l =================
         for (int k = tid; k < 3 * RING; k += NT2) sm.ring[k] = 0.;
         for (int k = tid; k < 8 * P2; k += NT2) (&sm.ringq[0][0])[k] = 0.;
         for (int k = tid; k < NG * PP; k += NT2) (&sm.partC[0][0])[k] = 0.;
-        if (tid < PP) {
-            // qm of the last column is never read; qb of the first outside column
-            sm.qcol[tid] = (tid <= W - 1 - TURN - 1) ? qbG[(W - 1) * P2 + tid] : 0.;
-            sm.partS[tid] = 0.;
-        }
+        for (int k = tid; k < 4 * PP; k += NT2) (&sm.partS1a[0][0])[k] = 0.;
+        for (int k = tid; k < 2 * 4 * PP; k += NT2) (&sm.u.x1buf[0][0][0])[k] = 0.;
+        if (tid < PP) sm.qcol[tid] = (tid <= W - 1 - TURN - 1) ? qbG[(W - 1) * P2 + tid] : 0.;   // qb of the first outside column
         if (tid == 0) {
             sm.q3[W] = 1.;
             for (int k = W - 1; k >= max(0, W - TURN - 1); k--) sm.q3[k] = sm.q3[k + 1] * sc1;
-            sm.cnt[(W - 1) & 1] = 0;   // cells of the last column have no enclosing pair
+            sm.cnt[(W - 1) & 3] = 0;   // cells of the last column have no enclosing pair
         }
         double ed_local = 0.;
         __syncthreads();
         PF2_RESET
         for (int l = W - 1; l > TURN; l--) {
-            const int par = l & 1;
-            // ---- phase 1: one unit per warp, then the candidate walk of the listed cells
-            if (warp < 4) {
-                // table-driven shapes closed outside (k,l)
-                const int k = warp * 32 + lane;
-                double v = 0.;
-                if (l <= W - 2 && k >= 1 && k <= l - TURN - 1 && sm.qcol[k] != 0.)
-                    v = shapes_outside(sm, T, k, l, rtype_of(pair_type(S[k], S[l])), W);
-                sm.partS[k] = v;
-            } else if (warp < 4 + NH) {
-                // H[k] = sum_{i <= k-6} (X1+X2)[i] qm[i+1,k-1]: i = g, g + NH, ..; lane = cell in four blocks
-                const int g = warp - 4;
-                double a0 = 0., a1 = 0., a2 = 0., a3 = 0.;
-                const double *r0 = sm.qm + qmrow(max(lane - 1, 0)) + 1, *r1 = sm.qm + qmrow(lane + 31) + 1;
-                const double *r2 = sm.qm + qmrow(min(lane + 63, W)) + 1, *r3 = sm.qm + qmrow(min(lane + 95, W)) + 1;
-                const int kmax = l - TURN - 1;   // cells k <= kmax
-#pragma unroll 2
-                for (int i = g; i <= l - 10; i += NH) {
-                    const double w = sm.x12[i];
-                    if (i <= lane - 6 && lane <= kmax) a0 = fma(r0[i], w, a0);
-                    if (i <= lane + 26 && lane + 32 <= kmax) a1 = fma(r1[i], w, a1);
-                    if (i <= lane + 58 && lane + 64 <= kmax) a2 = fma(r2[i], w, a2);
-                    if (i <= lane + 90 && lane + 96 <= kmax) a3 = fma(r3[i], w, a3);
-                }
-                sm.partC[g][lane] = a0;
-                sm.partC[g][lane + 32] = a1;
-                sm.partC[g][lane + 64] = a2;
-                sm.partC[g][lane + 96] = a3;
-            } else if (warp < 4 + NH + NX) {
-                // X1[i,l-1] = sum_{j >= l+5} PM[i,j] qm[l,j-1] of the NEXT column (PM of those columns is final): the j
-                // range cut in NX, PM streams from L2 with four independent loads in flight per lane
-                const int g = warp - 4 - NH, lx = l - 1;
-                const int nj = W - lx - 6;
-                double a0 = 0., a1 = 0., a2 = 0., a3 = 0.;
-                if (nj > 0 && lx > TURN) {
-                    const int j0 = lx + 6 + nj * g / NX, j1 = lx + 6 + nj * (g + 1) / NX;
-                    const int imax = lx - TURN - 1;
-#pragma unroll 2
-                    for (int j = j0; j < j1; j++) {
-                        const double w = sm.qm[qmrow(j - 1) + lx + 1];
-                        const double *pr = pmG + j * P2 + lane;
-                        if (lane <= imax) a0 = fma(pr[0], w, a0);
-                        if (lane + 32 <= imax) a1 = fma(pr[32], w, a1);
-                        if (lane + 64 <= imax) a2 = fma(pr[64], w, a2);
-                        if (lane + 96 <= imax) a3 = fma(pr[96], w, a3);
+            const int sl = l & 3;
+            // X1[i,l-2] = sum_{j >= l+4} PM[i,j] qm[l-1,j-1] two columns ahead (PM of those columns is final): warps 12-15
+            // take the rows j = l+4+w, +4, .. of all cells (lane = cell in up to four blocks), streamed from L2 with two
+            // rows (up to eight loads) in flight; most rows before the barrier, the rest after it; partial sums per warp
+            const int lx = l - 2, xw = warp - 12;
+            const int xj0 = lx + 6, xjm = xj0 + (max(W - xj0, 0) * 3 / 4 & ~3);
+            double xa[4] = {0., 0., 0., 0.};
+            auto x1_rows = [&](int ja, int jb) {
+                if (lx <= TURN) return;
+                const int imax = lx - TURN - 1;
+                const int nb4 = imax / 32 + 1;   // blocks of cells that exist
+                const double *pr = pmG + lane;
+                const double *qv = sm.qm + lx + 1;
+                int j = ja + xw;
+                for (; j + 4 < jb; j += 8) {
+                    double pv[8];
+#pragma unroll
+                    for (int z = 0; z < 4; z++) {
+                        pv[z] = z < nb4 ? pr[j * P2 + 32 * z] : 0.;
+                        pv[4 + z] = z < nb4 ? pr[(j + 4) * P2 + 32 * z] : 0.;
                     }
+                    const double w0 = qv[qmrow(j - 1)], w1 = qv[qmrow(j + 3)];
+#pragma unroll
+                    for (int z = 0; z < 4; z++) xa[z] = fma(pv[4 + z], w1, fma(pv[z], w0, xa[z]));
                 }
-                sm.partX[g][lane] = a0;
-                sm.partX[g][lane + 32] = a1;
-                sm.partX[g][lane + 64] = a2;
-                sm.partX[g][lane + 96] = a3;
-            } else if (warp == 14) {
+                for (; j < jb; j += 4) {
+                    const double w0 = qv[qmrow(j - 1)];
+#pragma unroll
+                    for (int z = 0; z < 4; z++) xa[z] = fma(z < nb4 ? pr[j * P2 + 32 * z] : 0., w0, xa[z]);
+                }
+            };
+            // ---- phase 1: one unit per warp, then (warps 0-11) the candidate walk of the listed cells
+            if (warp < 3) {
+                // table-driven shapes closed outside (k,l), three per warp, lane = listed cell
+                const int n = sm.cnt[sl];
+                for (int cc = lane; cc < n; cc += 32) {
+                    const int k = sm.list[sl][cc];
+                    const int t2 = rtype_of(pair_type(S[k], S[l]));
+                    double v;
+                    if (warp == 0)
+                        v = shape_out<6>(sm, T, k, l, t2, W) + shape_out<0>(sm, T, k, l, t2, W) + shape_out<1>(sm, T, k, l, t2, W);
+                    else if (warp == 1)
+                        v = shape_out<4>(sm, T, k, l, t2, W) + shape_out<2>(sm, T, k, l, t2, W) + shape_out<7>(sm, T, k, l, t2, W);
+                    else
+                        v = shape_out<5>(sm, T, k, l, t2, W) + shape_out<3>(sm, T, k, l, t2, W) + shape_out<8>(sm, T, k, l, t2, W);
+                    sm.partS1a[warp][k] = v;
+                }
+            } else if (warp == 3) {
                 // G1[k] = sum_{i<k} X1[i] eMLb[k-1-i] = eMLb[k-1] * (prefix sum of X1[i] ainv[i])
+                const double(*x1c)[PP] = sm.u.x1buf[l & 1];
                 double tk[4], tot = 0.;
 #pragma unroll
                 for (int z = 0; z < 4; z++) {
                     const int i = 4 * lane + z;
-                    tk[z] = (i <= l - TURN - 1 && i < P2) ? sm.x1[i] * sm.ainv[i] : 0.;
+                    tk[z] = (i <= l - TURN - 1 && i < P2) ? (x1c[0][i] + x1c[1][i] + x1c[2][i] + x1c[3][i]) * sm.ainv[i] : 0.;
                     tot += tk[z];
                 }
                 double inc = tot;
@@ -594,33 +646,60 @@ pf2_kernel(PfLaunch L, const MfeTables *__restrict__ MT, const PfTables *__restr
                     if (k < P2) sm.g1[k] = k >= 1 ? run * sm.emlb[k - 1] : 0.;
                     run += tk[z];
                 }
-            } else {
+            } else if (warp == 4) {
                 // q3[l] for the next column
                 double a3 = 0.;
                 for (int j = l + TURN + 1 + lane; j < W; j += 32) {
                     const double q = qbG[j * P2 + l];
-                    if (q != 0.) a3 += q * sm.q3[j + 1] * extloop2(TH, pair_type(S[l], S[j]), nb(l - 1), nb(j + 1));
+                    a3 += q * sm.q3[j + 1] * TH->ext[pair_type(S[l], S[j])][Sx[l]][Sx[j + 2]];
                 }
                 a3 = warp_sum(a3);
                 if (lane == 0) sm.q3[l] = sm.q3[l + 1] * sc1 + a3;
+            } else if (warp < 5 + NH) {
+                // H[k] = sum_{i <= k-6} (X1+X2)[i] qm[i+1,k-1]: i = g, g + NH, ..; lane = cell in four blocks
+                const int g = warp - 5;
+                double a0 = 0., a1 = 0., a2 = 0., a3 = 0.;
+                const int kmax = l - TURN - 1;   // cells k <= kmax
+                const double *r0 = sm.qm + qmrow(max(lane - 1, 0)) + 1, *r1 = sm.qm + qmrow(lane + 31) + 1;
+                const double *r2 = sm.qm + qmrow(min(lane + 63, W - 1)) + 1, *r3 = sm.qm + qmrow(min(lane + 95, W - 1)) + 1;
+                const int l0 = min(lane, kmax + 0 >= lane ? lane : -100) - 6;   // cell k = lane + 32 b: terms i <= k - 6
+                const int m0 = lane <= kmax ? lane - 6 : -1, m1 = lane + 32 <= kmax ? lane + 26 : -1;
+                const int m2 = lane + 64 <= kmax ? lane + 58 : -1, m3 = lane + 96 <= kmax ? lane + 90 : -1;
+                (void)l0;
+#pragma unroll 4
+                for (int i = g; i <= l - 10; i += NH) {
+                    const double w = sm.x12[i];
+                    const double v0 = r0[i], v1 = r1[i], v2 = r2[i], v3 = r3[i];
+                    a0 = fma(i <= m0 ? v0 : 0., w, a0);
+                    a1 = fma(i <= m1 ? v1 : 0., w, a1);
+                    a2 = fma(i <= m2 ? v2 : 0., w, a2);
+                    a3 = fma(i <= m3 ? v3 : 0., w, a3);
+                }
+                sm.partC[g][lane] = a0;
+                sm.partC[g][lane + 32] = a1;
+                sm.partC[g][lane + 64] = a2;
+                sm.partC[g][lane + 96] = a3;
+            } else {
+                x1_rows(xj0, xjm);
             }
-            {
-                const int n = sm.cnt[par];
-                for (int cc = (warp + 2) & (NW2 - 1); cc < n; cc += NW2) {
-                    const int k = sm.list[par][cc];
+            if (warp < 12) {
+                const int n = sm.cnt[sl];
+                const int ixM = lane == 0 ? PR_TAU : (lane == 1 ? PR_MM1 : PR_MMI);
+                for (int cc = warp; cc < n; cc += 12) {
+                    const int k = sm.list[sl][cc];
                     const int t2 = rtype_of(pair_type(S[k], S[l])), a = S[l + 1], b = S[k - 1];
-                    const double mmI = TH->expmismatchI[t2][a][b], mm1 = TH->expmismatch1nI[t2][a][b];
-                    const double tau = t2 > 2 ? tAU : 1.;
+                    const double mmI = TH->expmismatchI[t2][a][b], mm1 = TH->expmismatch1nI[t2][a][b], tau = TH->tau[t2];
+                    const double mulM = ixM == PR_TAU ? tau : (ixM == PR_MM1 ? mm1 : mmI);
                     const double *pb = sm.ring + (k - 1 + RPAD) * PT + ((l + 1 + lane) & 31);
                     double accB, acc1;
-                    const double aM = cand_walk<true>(pb + 2 * RING, pb + RING, pb + cls * RING, min(MAXLOOP, k - 1), K, accB, acc1);
-                    double v = aM * (lane == 0 ? tau : (lane == 1 ? mm1 : mmI)) + accB * tau + acc1 * mm1;
+                    const double aM = cand_walk<true>(pb + 2 * RING, pb + RING, pb + cls * RING, min(MAXLOOP, k - 1), lo, K, accB, acc1);
+                    double v = aM * mulM + accB * tau + acc1 * mm1;
                     v = warp_sum(v);
                     if (lane == 0) sm.partA[k] = v;
                 }
             }
             PF2_SYNC(4)
-            // ---- phase 2: P of the column, ring copies, PM, probabilities; X1, X2 and qb of the next column
+            // ---- phase 2: P of the column, ring copies, PM, probabilities; X2 and qb of the next column
             if (tid < PP) {
                 const int k = tid;
                 double Pv = 0., vG = 0., v1 = 0., vB = 0., pm = 0.;
@@ -628,22 +707,22 @@ pf2_kernel(PfLaunch L, const MfeTables *__restrict__ MT, const PfTables *__restr
                     const double qkl = sm.qcol[k];
                     if (qkl != 0.) {
                         const int t = pair_type(S[k], S[l]);
+                        const double fx = TH->ext[t][Sx[k]][Sx[l + 2]];
                         if (k >= 1 && l <= W - 2) {
-                            const int sp1 = S[k - 1], sq1 = S[l + 1];
-                            Pv = sm.partA[k] + sm.partS[k];
+                            Pv = sm.partA[k] + sm.partS1a[0][k] + sm.partS1a[1][k] + sm.partS1a[2][k];
                             double ml = sm.g1[k];
 #pragma unroll
                             for (int g = 0; g < NH; g++) ml += sm.partC[g][k];
-                            Pv += ml * mlstem2(TH, t, sp1, sq1) * sc2;
+                            Pv += ml * TH->mlstem[t][Sx[k]][Sx[l + 2]] * sc2;
                         }
-                        Pv += sm.q5[k] * sm.q3[l + 1] / Z * extloop2(TH, t, nb(k - 1), nb(l + 1));
+                        Pv += sm.q5[k] * sm.q3[l + 1] * invZ * fx;
                         if (Pv != 0.) {
                             const int a = S[k + 1], b = S[l - 1];
                             vG = Pv * TH->expmismatchI[t][a][b];
                             v1 = Pv * TH->expmismatch1nI[t][a][b];
-                            vB = t > 2 ? Pv * tAU : Pv;
+                            vB = Pv * TH->tau[t];
                         }
-                        pm = Pv * closing * mlstem2(TH, rtype_of(t), S[l - 1], S[k + 1]);
+                        pm = Pv * closing * TH->mlstem[rtype_of(t)][S[l - 1]][S[k + 1]];
                         const double p = Pv * qkl;
                         ed_local += p * (1. - p);
                         if (p > 0.5) {
@@ -661,30 +740,41 @@ pf2_kernel(PfLaunch L, const MfeTables *__restrict__ MT, const PfTables *__restr
                     sm.ring[2 * RING + o] = vB;
                     sm.ringq[l & 7][k] = Pv;
                 }
-                // the next column l-1: X1 from the partial sums, X2 by its recurrence, qb
-                const int lx = l - 1;
+                // the next column l-1: X1 (streamed two columns ago), X2 by its recurrence, qb
+                const int ln = l - 1;
                 double x1 = 0., x2 = 0., qn = 0.;
-                if (lx > TURN && k <= lx - TURN - 1) {
-                    x1 = sm.partX[0][k] + sm.partX[1][k] + sm.partX[2][k];
+                if (ln > TURN && k <= ln - TURN - 1) {
+                    x1 = sm.u.x1buf[ln & 1][0][k] + sm.u.x1buf[ln & 1][1][k] + sm.u.x1buf[ln & 1][2][k] + sm.u.x1buf[ln & 1][3][k];
                     x2 = sm.x2[k] * eml1 + pm;
-                    qn = qbG[lx * P2 + k];
+                    qn = qbG[ln * P2 + k];
                 }
-                sm.x1[k] = x1;
                 sm.x2[k] = x2;
                 sm.x12[k] = x1 + x2;
                 sm.qcol[k] = qn;
-            } else if (warp == 5) {
-                // cells of the next column the candidate walk visits: qb != 0, an enclosing pair exists
-                const int lx = l - 1;
-                int n = 0;
+            } else if (warp == 4) {
+                // cells of the next column the candidate walk visits (qb != 0, an enclosing pair exists) and their outer
+                // factors
+                const int ln = l - 1;
+                double q[PP / 32];
+#pragma unroll
                 for (int b = 0; b < PP / 32; b++) {
                     const int k = b * 32 + lane;
-                    const bool on = lx > TURN && k >= 1 && k <= lx - TURN - 1 && qbG[lx * P2 + k] != 0.;
+                    q[b] = (ln > TURN && k >= 1 && k <= ln - TURN - 1) ? qbG[ln * P2 + k] : 0.;
+                }
+                int n = 0;
+#pragma unroll
+                for (int b = 0; b < PP / 32; b++) {
+                    const bool on = q[b] != 0.;
                     const unsigned m = __ballot_sync(full, on);
-                    if (on) sm.list[lx & 1][n + __popc(m & ((1u << lane) - 1))] = (unsigned char)k;
+                    if (on) sm.list[ln & 3][n + __popc(m & ((1u << lane) - 1))] = (unsigned char)(b * 32 + lane);
                     n += __popc(m);
                 }
-                if (lane == 0) sm.cnt[lx & 1] = n;
+                if (lane == 0) sm.cnt[ln & 3] = n;
+            } else if (warp >= 12) {
+                x1_rows(xjm, W);
+                const int imax = lx - TURN - 1;   // cells beyond the column's last one read stale PM: dropped here
+#pragma unroll
+                for (int z = 0; z < 4; z++) sm.u.x1buf[lx & 1][xw][32 * z + lane] = (lx > TURN && 32 * z + lane <= imax) ? xa[z] : 0.;
             }
             PF2_SYNC(6)
         }
@@ -705,7 +795,7 @@ pf2_kernel(PfLaunch L, const MfeTables *__restrict__ MT, const PfTables *__restr
             printf("pf2 timing warp %2d: inside p1 %lld wait %lld p2 %lld wait %lld | outside p1 %lld wait %lld p2 %lld wait %lld\n", warp,
                    tacc[0], tacc[1], tacc[2], tacc[3], tacc[4], tacc[5], tacc[6], tacc[7]);
         if (blockIdx.x == 0 && fold == 0 && lane == 0)
-            printf("pf2 probes warp %2d: walk %lld reduce %lld finalize %lld loop %lld\n", warp, tprobe[0], tprobe[1], tprobe[2], tprobe[3]);
+            printf("pf2 probes warp %2d: outside setup+other %lld walk %lld tail %lld\n", warp, tprobe[0], tprobe[1], tprobe[2]);
 #endif
     }
 }
