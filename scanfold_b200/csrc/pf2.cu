@@ -300,7 +300,7 @@ pf2_kernel(PfLaunch L, const MfeTables *__restrict__ MT, const PfTables *__restr
     };
     // outer factors of the listed cells of inside column j (lane = listed cell): what the walk multiplies its class sums
     // with, the multiloop closing factor, the factors of the ring copies / qm1 the cell's qb is stored with
-    auto cell_params_inside = [&](int j) {
+    auto cell_params_inside = [&](int j, int half) {
         if (j >= W) return;
         const int n = sm.cnt[j & 3];
         for (int cc = lane; cc < n; cc += 32) {
@@ -309,16 +309,19 @@ pf2_kernel(PfLaunch L, const MfeTables *__restrict__ MT, const PfTables *__restr
             const bool inner = i > 0 && j < W - 1;   // (i,j) can be the inner pair of an enclosing loop
             const int a = Sx[j + 2] % 5, b = Sx[i] % 5;
             double *r = sm.prm[cc];
-            r[PR_MMI] = TH->expmismatchI[t][si1][sj1];
-            r[PR_MM1] = TH->expmismatch1nI[t][si1][sj1];
-            r[PR_TAU] = TH->tau[t];
-            r[PR_MLC] = closing * TH->mlstem[t2][sj1][si1] * sc2;
-            r[PR_FI] = inner ? TH->expmismatchI[t2][a][b] : 0.;
-            r[PR_F1] = inner ? TH->expmismatch1nI[t2][a][b] : 0.;
-            r[PR_FB] = inner ? TH->tau[t2] : 0.;
-            r[PR_FM] = TH->mlstem[t][Sx[i]][Sx[j + 2]];
-            r[PR_ONE] = 1.;
-            r[PR_ZERO] = 0.;
+            if (half == 0) {
+                r[PR_MMI] = TH->expmismatchI[t][si1][sj1];
+                r[PR_MM1] = TH->expmismatch1nI[t][si1][sj1];
+                r[PR_TAU] = TH->tau[t];
+                r[PR_MLC] = closing * TH->mlstem[t2][sj1][si1] * sc2;
+                r[PR_ONE] = 1.;
+            } else {
+                r[PR_FI] = inner ? TH->expmismatchI[t2][a][b] : 0.;
+                r[PR_F1] = inner ? TH->expmismatch1nI[t2][a][b] : 0.;
+                r[PR_FB] = inner ? TH->tau[t2] : 0.;
+                r[PR_FM] = TH->mlstem[t][Sx[i]][Sx[j + 2]];
+                r[PR_ZERO] = 0.;
+            }
         }
     };
     // hairpin closed by (i,j): the general formula per lane; loops of 3, 4 and 6 nucleotides are left to
@@ -430,7 +433,7 @@ pf2_kernel(PfLaunch L, const MfeTables *__restrict__ MT, const PfTables *__restr
         if (warp == 15) build_list_inside(TURN + 2);
         __syncthreads();
         if (warp >= 8 && warp < 12) shapes1_unit(TURN + 1, warp - 8);   // hairpins: all the first column can close
-        if (warp == 14) cell_params_inside(TURN + 1);
+        if (warp == 14 || warp == 15) cell_params_inside(TURN + 1, warp - 14);
         __syncthreads();
         PF2_RESET
         // ================= inside, column j =================
@@ -451,6 +454,7 @@ pf2_kernel(PfLaunch L, const MfeTables *__restrict__ MT, const PfTables *__restr
                     for (int g = 0; g < NG; g++) qq += sm.partC[g][i];
                     sm.qm[qmrow(j - 1) + i] = sm.u.in.qm1[par ^ 1][i] + sm.ecol[i] + qq;
                 }
+                if (warp == 15) build_list_inside(j + 2);
             } else if (warp >= 8) {
                 shapes1_unit(j + 1, warp - 8);
             }
@@ -472,8 +476,10 @@ pf2_kernel(PfLaunch L, const MfeTables *__restrict__ MT, const PfTables *__restr
                                          : (lane == 3 ? &sm.ringq[j & 7][0] : (lane == 4 ? &sm.u.in.qm1[par][0] : &sm.junk[lane]));
                 const int dstride = lane < 3 ? PT : (lane < 5 ? 1 : 0);
                 const double emlL = lane == 4 ? eml1 : 0.;
-                // warps 0-7 have no other unit in this phase: they take two of every 24 cells, the others one
-                for (int c0 = warp < 8 ? warp : warp + 8; c0 < n; c0 = (warp < 8 && c0 % 24 < 8) ? c0 + 8 : c0 + (warp < 8 ? 16 : 24)) {
+                // of every 28 cells the warps without a unit in this phase (0-7) and the ones with the short one (12-15) take
+                // two, the shape warps (8-11) one
+                const int cfirst = warp < 8 ? warp : (warp >= 12 ? warp - 4 : warp + 16);
+                for (int c0 = cfirst; c0 < n; c0 = ((warp < 8 || warp >= 12) && (c0 - cfirst) % 28 == 0) ? c0 + 12 : c0 + ((warp < 8 || warp >= 12) ? 16 : 28)) {
                     const int cc = c0;
                     const int i = sm.list[sl][cc];
                     const double *r = sm.prm[cc];
@@ -551,10 +557,8 @@ pf2_kernel(PfLaunch L, const MfeTables *__restrict__ MT, const PfTables *__restr
                     sm.ring[RING + p * PT + slot] = 0.;
                     sm.ring[2 * RING + p * PT + slot] = 0.;
                 }
-            } else if (warp == 13) {
-                build_list_inside(j + 2);
-            } else if (warp == 14) {
-                cell_params_inside(j + 1);
+            } else if (warp == 13 || warp == 14) {
+                cell_params_inside(j + 1, warp - 13);
             }
             PF2_SYNC(2)
         }
@@ -581,7 +585,7 @@ pf2_kernel(PfLaunch L, const MfeTables *__restrict__ MT, const PfTables *__restr
             // take the rows j = l+4+w, +4, .. of all cells (lane = cell in up to four blocks), streamed from L2 with two
             // rows (up to eight loads) in flight; most rows before the barrier, the rest after it; partial sums per warp
             const int lx = l - 2, xw = warp - 12;
-            const int xj0 = lx + 6, xjm = xj0 + (max(W - xj0, 0) * 3 / 4 & ~3);
+            const int xj0 = lx + 6, xjm = W;   // (all rows before the barrier: that phase is the longer one)
             double xa[4] = {0., 0., 0., 0.};
             auto x1_rows = [&](int ja, int jb) {
                 if (lx <= TURN) return;
@@ -685,7 +689,9 @@ pf2_kernel(PfLaunch L, const MfeTables *__restrict__ MT, const PfTables *__restr
             if (warp < 12) {
                 const int n = sm.cnt[sl];
                 const int ixM = lane == 0 ? PR_TAU : (lane == 1 ? PR_MM1 : PR_MMI);
-                for (int cc = warp; cc < n; cc += 12) {
+                // of every 21 cells the three shape warps (the longest unit) take one, the other nine two
+                const int cfirst = warp >= 3 ? warp - 3 : warp + 18;
+                for (int cc = cfirst; cc < n; cc = (warp >= 3 && (cc - cfirst) % 21 == 0) ? cc + 9 : cc + (warp >= 3 ? 12 : 21)) {
                     const int k = sm.list[sl][cc];
                     const int t2 = rtype_of(pair_type(S[k], S[l])), a = S[l + 1], b = S[k - 1];
                     const double mmI = TH->expmismatchI[t2][a][b], mm1 = TH->expmismatch1nI[t2][a][b], tau = TH->tau[t2];
