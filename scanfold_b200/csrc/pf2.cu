@@ -476,10 +476,11 @@ pf2_kernel(PfLaunch L, const MfeTables *__restrict__ MT, const PfTables *__restr
                                          : (lane == 3 ? &sm.ringq[j & 7][0] : (lane == 4 ? &sm.u.in.qm1[par][0] : &sm.junk[lane]));
                 const int dstride = lane < 3 ? PT : (lane < 5 ? 1 : 0);
                 const double emlL = lane == 4 ? eml1 : 0.;
-                // of every 28 cells the warps without a unit in this phase (0-7) and the ones with the short one (12-15) take
-                // two, the shape warps (8-11) one
-                const int cfirst = warp < 8 ? warp : (warp >= 12 ? warp - 4 : warp + 16);
-                for (int c0 = cfirst; c0 < n; c0 = ((warp < 8 || warp >= 12) && (c0 - cfirst) % 28 == 0) ? c0 + 12 : c0 + ((warp < 8 || warp >= 12) ? 16 : 28)) {
+                // the cells are dealt in rounds of 27, by what else the warp does in this phase: warps 0-7 (no unit) and 12-14
+                // (the short one) take two, the shape warps 8-11 and the list builder 15 one
+                const int o1 = warp < 8 ? warp : (warp < 12 ? warp + 11 : (warp < 15 ? warp - 4 : 23));
+                const int o2 = warp < 8 ? warp + 11 : ((warp >= 12 && warp < 15) ? warp + 12 : 1 << 20);
+                for (int c0 = o1; c0 < n; c0 = (c0 % 27 == o1 && o2 < 27) ? c0 - o1 + o2 : c0 - c0 % 27 + 27 + o1) {
                     const int cc = c0;
                     const int i = sm.list[sl][cc];
                     const double *r = sm.prm[cc];
@@ -686,12 +687,13 @@ pf2_kernel(PfLaunch L, const MfeTables *__restrict__ MT, const PfTables *__restr
             } else {
                 x1_rows(xj0, xjm);
             }
-            if (warp < 12) {
+            {
                 const int n = sm.cnt[sl];
                 const int ixM = lane == 0 ? PR_TAU : (lane == 1 ? PR_MM1 : PR_MMI);
-                // of every 21 cells the three shape warps (the longest unit) take one, the other nine two
-                const int cfirst = warp >= 3 ? warp - 3 : warp + 18;
-                for (int cc = cfirst; cc < n; cc = (warp >= 3 && (cc - cfirst) % 21 == 0) ? cc + 9 : cc + (warp >= 3 ? 12 : 21)) {
+                // the cells are dealt in rounds of 23: one to every warp, the warps with the shortest unit (H) first and again
+                const int o1 = warp >= 5 && warp < 12 ? warp - 5 : (warp < 3 ? warp + 7 : (warp == 3 ? 10 : (warp == 4 ? 15 : warp - 1)));
+                const int o2 = warp >= 5 && warp < 12 ? warp + 11 : 1 << 20;
+                for (int cc = o1; cc < n; cc = (cc % 23 == o1 && o2 < 23) ? cc - o1 + o2 : cc - cc % 23 + 23 + o1) {
                     const int k = sm.list[sl][cc];
                     const int t2 = rtype_of(pair_type(S[k], S[l])), a = S[l + 1], b = S[k - 1];
                     const double mmI = TH->expmismatchI[t2][a][b], mm1 = TH->expmismatch1nI[t2][a][b], tau = TH->tau[t2];
