@@ -39,6 +39,7 @@
 #include <cstddef>
 #include <cstdio>
 #include <cstdlib>
+#include <type_traits>
 
 #include "device_common.cuh"
 
@@ -106,6 +107,7 @@ struct Smem3 {
     unsigned char sx5[P + 8], sx3[P + 8];   // the same, 5 (never pairs) where hard constraints forbid the nucleotide
                                             // as 5' / 3' partner ('x' both, '>' 5', '<' 3')
     alignas(16) int cnt[4];   // pairable cells of the diagonals d with d & 3 = slot (0 beyond the last diagonal)
+    int wq[2];                // FMG: work-queue heads of the current / next phase (units are handed out dynamically)
     short scp[P + 8];   // soft constraints: scp[k] = sc[k] + sc[k+1] (0-based), the stack (i,j)-(i+1,j-1) adds scp[i] + scp[j-1]
     int minv[32];
     int fbest[32];   // per-length partial minima of an exterior-loop round (8 lengths x up to 4 slices)
@@ -684,6 +686,7 @@ mfe3_kernel(MfeLaunch L, const MfeTables *__restrict__ T, const Tab3 *__restrict
             }
         }
         minv = 0;
+        if (tid < 2) sm.wq[tid] = 0;
         for (int k = tid; k < W + 2; k += NT) {
             int v = 0;
             if (L.sc && k < W) {   // L.sc is 1-based: nucleotide k sits at index k + 1
@@ -717,31 +720,105 @@ mfe3_kernel(MfeLaunch L, const MfeTables *__restrict__ T, const Tab3 *__restrict
         }
         __syncthreads();
 
-        for (int d0 = TURN + 2; d0 - 2 < W; d0 += 2) {
+        // ---- C (queue variant): interior loops of size >= 2 of the pairable cells c .. n-1 of diagonal d (d0+2 or d0+3;
+        // rows <= d0-1): one cell per pass, lane = loop size U with its seven taps (see the header)
+        auto unit_C = [&](int d, int c, int n) {
+            constexpr int stride = 1;
+            const int slot = (d - 2 - UB) & (R32 - 1);
+            const short *qA = smb + kA + ((d - 2 - UA) & (R32 - 1)) * PR;
+            const short *qB10 = smb + O_M8 + 10 + ((d - 2 - UB10) & (R32 - 1)) * PR;
+            const short *qB18 = smb + O_M8 + 18 + ((d - 2 - UB18) & (R32 - 1)) * PR;
+            const short *qB26 = smb + O_M8 + 26 + ((d - 2 - UB26) & (R32 - 1)) * PR;
+            const short *qC = smb + kC + ((d - 2 - UC) & (R32 - 1)) * PR;
+            const unsigned *qR = sm.rpa + slot * PRW + 1;        // inner pair (i+1, j-1-U) and 1xn neighbour
+            const unsigned *qL = sm.rpq + slot * PRW + d - 1;    // inner pair (i+1+U, j-1) and 1xn neighbour
+            short *qP = sm.partc + (d & 3) * PR;
+            const int4 *lst = reinterpret_cast<const int4 *>(sm.list) + (d & 3) * LP;
+            int4 en = lst[c];
+            for (; c < n; c += stride) {
+                const int i = en.x, eI = en.y, e1 = en.z, eB = en.w;
+                en = lst[c + stride];   // next entry (at most `stride` past the list end: still inside sm.list)
+                const unsigned wr = qR[i], wl = qL[i];
+                const short *pa = qA + i, *pc = qC + i;
+                const int xa = pa[0], xb10 = qB10[i], xb18 = qB18[i], xb26 = qB26[i], xc = pc[0];
+                const unsigned wm = __vmins2(wr, wl);
+                const int xb = (int)(short)(wm & 0xffffu), x1 = (int)wm >> 16;
+                int g = xa + cA;
+                g = __viaddmin_s32(xb10, cB10, g);
+                int g2 = xb18 + cB18;
+                g2 = __viaddmin_s32(xb26, cB26, g2);
+                g = __viaddmin_s32(xc, cC, g);
+                const int aB = xb + cSB, a1 = x1 + cS1;
+                int v = min(g, g2) + eI;
+                v = __viaddmin_s32(a1, e1, v);
+                v = __viaddmin_s32(aB, eB, v);
+                v = __reduce_min_sync(full, v);
+                if (lane == 0) qP[i] = (short)v;   // <= INF16 + size and mismatch terms: fits
+            }
+        };
+
+        for (int d0 = TURN + 2, ph = 0; d0 - 2 < W; d0 += 2, ph ^= 1) {
             const int2 si = reinterpret_cast<const int2 *>(sm.stepinfo)[(d0 - TURN - 2) >> 1];
             const int nseg0 = si.x & 255, nS = (si.x >> 8) & 255, nF = si.x >> 16;
             const int ntile = si.y & 255, ksh = (si.y >> 8) & 15, kwsh = (si.y >> 12) & 15, nT = si.y >> 16;
             const int n2 = sm.cnt[(d0 + 2) & 3], n3 = sm.cnt[(d0 + 3) & 3];   // (the other two slots are being rewritten)
             const int nch2 = (n2 + 31) >> 5, nP = nch2 + ((n3 + 31) >> 5);
-            const int uP = nS, uT = uP + nP, uF = uT + nT, uL = uF + nF, nH = uL + 2;
-            for (int u = warp; u < nH; u += NW) {
-                if (u < uP) {
-                    unit_S(u >= nseg0 ? d0 + 1 : d0, u >= nseg0 ? u - nseg0 : u);
-                } else if (u < uT) {
-                    const int it = u - uP;
-                    unit_P(it < nch2 ? d0 + 2 : d0 + 3, it < nch2 ? it : it - nch2);
-                } else if (u < uF) {
-                    unit_T(d0 + 1, u - uT, ntile, ksh, kwsh);
-                } else if (u < uL) {
-                    unit_F(d0 - 2, u - uF);
-                } else {
-                    build_list(d0 + 4 + (u - uL));
+            if constexpr (FMG) {
+                // One CTA per SM and long split loops over L2: the units of a phase differ in length by an order of
+                // magnitude, so the warps draw them from a queue (one shared-memory atomic per draw, the next draw in
+                // flight while a unit runs), longest first: T | P | S | L | F, then the interior-loop cells in chunks of CH
+                // (+7 % at 300 nt; in shared-memory configurations the static deal below is faster).
+                constexpr int CH = 4;
+                const int uP = nT, uS = uP + nP, uL = uS + nS, uF = uL + 2, uC = uF + nF;
+                const int nc2 = (n2 + CH - 1) / CH, total = uC + nc2 + (n3 + CH - 1) / CH;
+                int *head = &sm.wq[ph];
+                if (tid == 0) sm.wq[ph ^ 1] = 0;
+                auto draw = [&]() {
+                    int v = 0;
+                    if (lane == 0) v = atomicAdd(head, 1);
+                    return __shfl_sync(full, v, 0);
+                };
+                int my = draw();
+                while (my < total) {
+                    const int nx = draw();
+                    if (my < uP) {
+                        unit_T(d0 + 1, my, ntile, ksh, kwsh);
+                    } else if (my < uS) {
+                        const int it = my - uP;
+                        unit_P(it < nch2 ? d0 + 2 : d0 + 3, it < nch2 ? it : it - nch2);
+                    } else if (my < uL) {
+                        const int u = my - uS;
+                        unit_S(u >= nseg0 ? d0 + 1 : d0, u >= nseg0 ? u - nseg0 : u);
+                    } else if (my < uF) {
+                        build_list(d0 + 4 + (my - uL));
+                    } else if (my < uC) {
+                        unit_F(d0 - 2, my - uF);
+                    } else {
+                        const int ci = my - uC, ds = ci >= nc2;
+                        const int c = (ds ? ci - nc2 : ci) * CH;
+                        unit_C(d0 + 2 + ds, c, min(c + CH, ds ? n3 : n2));
+                    }
+                    my = nx;
                 }
-            }
-            // ---- C: interior loops of size >= 2 of the pairable cells of diagonals d0+2, d0+3 (rows <= d0-1): one
-            // cell per pass, lane = loop size U with its seven taps (see the header).  The cells continue the round
-            // robin of the units above.
-            {
+            } else {
+                const int uP = nS, uT = uP + nP, uF = uT + nT, uL = uF + nF, nH = uL + 2;
+                for (int u = warp; u < nH; u += NW) {
+                    if (u < uP) {
+                        unit_S(u >= nseg0 ? d0 + 1 : d0, u >= nseg0 ? u - nseg0 : u);
+                    } else if (u < uT) {
+                        const int it = u - uP;
+                        unit_P(it < nch2 ? d0 + 2 : d0 + 3, it < nch2 ? it : it - nch2);
+                    } else if (u < uF) {
+                        unit_T(d0 + 1, u - uT, ntile, ksh, kwsh);
+                    } else if (u < uL) {
+                        unit_F(d0 - 2, u - uF);
+                    } else {
+                        build_list(d0 + 4 + (u - uL));
+                    }
+                }
+                // ---- C: interior loops of size >= 2 of the pairable cells of diagonals d0+2, d0+3 (rows <= d0-1): one
+                // cell per pass, lane = loop size U with its seven taps (see the header).  The cells continue the round
+                // robin of the units above.  (Same walk as unit_C; kept inline: as a lambda it costs 2.6 % at 120 nt.)
                 int c = warp - nH % NW;
                 if (c < 0) c += NW;
 #pragma unroll 1
