@@ -37,7 +37,7 @@ constexpr int PQ = 121;          // pitch of the folded qm matrix (odd)
 constexpr int QROWS = (P2 + 3) / 2 + 1;
 constexpr int NT2 = 512, NW2 = NT2 / 32;
 constexpr int NG = 8;            // inside: partial sums of the multiloop product (one warp each)
-constexpr int NH = 7;            // outside: partial sums of H
+constexpr int NH = 5;            // outside: partial sums of H
 constexpr int PP = 128;          // pitch of the per-cell arrays
 constexpr int PRW = 10;          // doubles per cell parameter row
 enum { PR_MMI = 0, PR_MM1, PR_TAU, PR_MLC, PR_FI, PR_F1, PR_FB, PR_FM, PR_ONE, PR_ZERO };
@@ -111,6 +111,19 @@ __device__ __forceinline__ double cand_walk(const double *pB, const double *p1, 
     accB = pB[0] * K[0];
     acc1 = p1[ST] * K[1];
     double a0 = 0., a1 = 0.;
+    if (u1max >= MAXLOOP) {
+        // the full walk (most cells): straight-line code, so the loads run ahead of the DFMAs as far as registers allow
+        sfor2<2, MAXLOOP>([&](auto V) {
+            constexpr int u1 = decltype(V)::value;
+            if (u1 < 15 || lo) {
+                if constexpr (u1 & 1)
+                    a1 = fma(pM[u1 * ST], K[u1], a1);
+                else
+                    a0 = fma(pM[u1 * ST], K[u1], a0);
+            }
+        });
+        return a0 + a1;
+    }
     sfor2<0, 7>([&](auto Q) {
         constexpr int g = 2 + 4 * decltype(Q)::value;
         if (g <= u1max) {   // warp-uniform
@@ -203,8 +216,15 @@ __device__ __forceinline__ double shape_out(const Smem2 &sm, const PfTables *T, 
         tprobe[k] += now_ - tp_;                                        \
         tp_ = now_;                                                     \
     }
+#define PF2_UNIT(k)                                                     \
+    {                                                                   \
+        long long now_;                                                 \
+        asm volatile("mov.u64 %0, %%clock64;" : "=l"(now_)::"memory"); \
+        tunit[k] += now_ - tlast;                                       \
+    }
 #else
 #define PF2_PROBE(k)
+#define PF2_UNIT(k)
 #define PF2_SYNC(slot) __syncthreads();
 #define PF2_RESET
 #endif
@@ -223,6 +243,7 @@ pf2_kernel(PfLaunch L, const MfeTables *__restrict__ MT, const PfTables *__restr
 #ifdef SFB_PF2_TIMING
     long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tlast;
     int tpar = 0;
+    long long tunit[2] = {0, 0};
     long long tprobe[4] = {0, 0, 0, 0}, tp_ = 0;
     asm volatile("mov.u64 %0, %%clock64;" : "=l"(tlast)::"memory");
 #endif
@@ -363,7 +384,8 @@ pf2_kernel(PfLaunch L, const MfeTables *__restrict__ MT, const PfTables *__restr
             if (have[z] && lane == 0) ps[3][i] += val[z] * sm.scale[u + 2];
         }
     };
-    // shapes with u2 >= 1 and the hairpin of inside column j, two items per warp w = 0..3, lane = listed cell
+    // shapes with u2 >= 1 and the hairpin of inside column j: w = 0..2 two shapes each, 3 the hairpin, 4 the 1x1 loops;
+    // lane = listed cell
     auto shapes1_unit = [&](int j, int w) {
         if (j >= W) return;
         const int n = sm.cnt[j & 3];
@@ -376,9 +398,14 @@ pf2_kernel(PfLaunch L, const MfeTables *__restrict__ MT, const PfTables *__restr
                 v = shape_in<4>(sm, T, i, j, t) + shape_in<7>(sm, T, i, j, t);
             else if (w == 2)
                 v = shape_in<5>(sm, T, i, j, t) + shape_in<8>(sm, T, i, j, t);
+            else if (w == 3)
+                v = hairpin_f(i, j, t) * sm.scale[j - i + 1];
             else
-                v = shape_in<3>(sm, T, i, j, t) + hairpin_f(i, j, t) * sm.scale[j - i + 1];
-            (j & 1 ? sm.u.in.partS1b : sm.partS1a)[w][i] = v;
+                v = shape_in<3>(sm, T, i, j, t);
+            if (w < 4)
+                (j & 1 ? sm.u.in.partS1b : sm.partS1a)[w][i] = v;
+            else
+                (j & 1 ? sm.g1 : sm.x12)[i] = v;   // fifth slice: two arrays only the outside pass uses
         }
         if (w == 3) {
             __syncwarp();
@@ -432,7 +459,7 @@ pf2_kernel(PfLaunch L, const MfeTables *__restrict__ MT, const PfTables *__restr
         if (warp == 14) build_list_inside(TURN + 1);
         if (warp == 15) build_list_inside(TURN + 2);
         __syncthreads();
-        if (warp >= 8 && warp < 12) shapes1_unit(TURN + 1, warp - 8);   // hairpins: all the first column can close
+        if (warp >= 8 && warp < 13) shapes1_unit(TURN + 1, warp - 8);   // hairpins: all the first column can close
         if (warp == 14 || warp == 15) cell_params_inside(TURN + 1, warp - 14);
         __syncthreads();
         PF2_RESET
@@ -455,20 +482,23 @@ pf2_kernel(PfLaunch L, const MfeTables *__restrict__ MT, const PfTables *__restr
                     sm.qm[qmrow(j - 1) + i] = sm.u.in.qm1[par ^ 1][i] + sm.ecol[i] + qq;
                 }
                 if (warp == 15) build_list_inside(j + 2);
+                if (warp == 12) shapes1_unit(j + 1, 4);
             } else if (warp >= 8) {
                 shapes1_unit(j + 1, warp - 8);
             }
+            PF2_UNIT(0)
             {
                 const int n = sm.cnt[sl];
                 const double *qm1p = sm.u.in.qm1[par ^ 1];
                 // per-lane roles (no divergence inside the cell loop): what the lane adds to the reduction beside its
                 // candidates -- lanes 0..NG-1 a partial sum of the multiloop closed by (i,j) (previous column's products),
-                // the next six a slice of the table-driven shapes -- and what it stores once qb is known: ring copies
+                // the next seven a slice of the table-driven shapes -- and what it stores once qb is known: ring copies
                 // (lanes 0-2), the raw copy (3), qm1 (4)
                 const double *ebase = lane < NG ? &sm.partC[lane][1]
                                                 : (lane < NG + 4 ? &(par ? sm.u.in.partS1b : sm.partS1a)[lane - NG][0]
-                                                                 : (lane < NG + 6 ? &sm.u.in.partS0[lane - NG - 4][0] : &sm.prm[0][PR_ZERO]));
-                const int estride = lane < NG + 6 ? 1 : 0;
+                                                                 : (lane == NG + 4 ? (par ? sm.g1 : sm.x12)
+                                                                                   : (lane < NG + 7 ? &sm.u.in.partS0[lane - NG - 5][0] : &sm.prm[0][PR_ZERO])));
+                const int estride = lane < NG + 7 ? 1 : 0;
                 const int ixE = lane < NG ? PR_MLC : PR_ONE;
                 const int ixM = lane == 0 ? PR_TAU : (lane == 1 ? PR_MM1 : PR_MMI);
                 const int ixF = lane < 3 ? PR_FI + lane : (lane == 3 ? PR_ONE : (lane == 4 ? PR_FM : PR_ZERO));
@@ -476,11 +506,11 @@ pf2_kernel(PfLaunch L, const MfeTables *__restrict__ MT, const PfTables *__restr
                                          : (lane == 3 ? &sm.ringq[j & 7][0] : (lane == 4 ? &sm.u.in.qm1[par][0] : &sm.junk[lane]));
                 const int dstride = lane < 3 ? PT : (lane < 5 ? 1 : 0);
                 const double emlL = lane == 4 ? eml1 : 0.;
-                // the cells are dealt in rounds of 27, by what else the warp does in this phase: warps 0-7 (no unit) and 12-14
-                // (the short one) take two, the shape warps 8-11 and the list builder 15 one
-                const int o1 = warp < 8 ? warp : (warp < 12 ? warp + 11 : (warp < 15 ? warp - 4 : 23));
-                const int o2 = warp < 8 ? warp + 11 : ((warp >= 12 && warp < 15) ? warp + 12 : 1 << 20);
-                for (int c0 = o1; c0 < n; c0 = (c0 % 27 == o1 && o2 < 27) ? c0 - o1 + o2 : c0 - c0 % 27 + 27 + o1) {
+                // the cells are dealt in rounds of 26, by what else the warp does in this phase: warps 0-7 (no unit) and 13-14
+                // (the short one) take two, the shape warps 8-12 and the list builder 15 one
+                const int o1 = warp < 8 ? warp : (warp < 13 ? warp + 12 : (warp < 15 ? warp - 5 : 25));
+                const int o2 = warp < 8 ? warp + 10 : ((warp == 13 || warp == 14) ? warp + 5 : 1 << 20);
+                for (int c0 = o1; c0 < n; c0 = (c0 % 26 == o1 && o2 < 26) ? c0 - o1 + o2 : c0 - c0 % 26 + 26 + o1) {
                     const int cc = c0;
                     const int i = sm.list[sl][cc];
                     const double *r = sm.prm[cc];
@@ -571,6 +601,7 @@ pf2_kernel(PfLaunch L, const MfeTables *__restrict__ MT, const PfTables *__restr
         for (int k = tid; k < NG * PP; k += NT2) (&sm.partC[0][0])[k] = 0.;
         for (int k = tid; k < 4 * PP; k += NT2) (&sm.partS1a[0][0])[k] = 0.;
         for (int k = tid; k < 2 * 4 * PP; k += NT2) (&sm.u.x1buf[0][0][0])[k] = 0.;
+        if (tid < PP) sm.x12[tid] = sm.ecol[tid] = 0.;   // x12: the inside pass used it as a shape slice; ecol: fifth slice here
         if (tid < PP) sm.qcol[tid] = (tid <= W - 1 - TURN - 1) ? qbG[(W - 1) * P2 + tid] : 0.;   // qb of the first outside column
         if (tid == 0) {
             sm.q3[W] = 1.;
@@ -613,22 +644,26 @@ pf2_kernel(PfLaunch L, const MfeTables *__restrict__ MT, const PfTables *__restr
                 }
             };
             // ---- phase 1: one unit per warp, then (warps 0-11) the candidate walk of the listed cells
-            if (warp < 3) {
-                // table-driven shapes closed outside (k,l), three per warp, lane = listed cell
+            if (warp < 5) {
+                // table-driven shapes closed outside (k,l), two per warp (the last one), lane = listed cell
                 const int n = sm.cnt[sl];
                 for (int cc = lane; cc < n; cc += 32) {
                     const int k = sm.list[sl][cc];
                     const int t2 = rtype_of(pair_type(S[k], S[l]));
                     double v;
                     if (warp == 0)
-                        v = shape_out<6>(sm, T, k, l, t2, W) + shape_out<0>(sm, T, k, l, t2, W) + shape_out<1>(sm, T, k, l, t2, W);
+                        v = shape_out<6>(sm, T, k, l, t2, W) + shape_out<1>(sm, T, k, l, t2, W);
                     else if (warp == 1)
-                        v = shape_out<4>(sm, T, k, l, t2, W) + shape_out<2>(sm, T, k, l, t2, W) + shape_out<7>(sm, T, k, l, t2, W);
+                        v = shape_out<4>(sm, T, k, l, t2, W) + shape_out<7>(sm, T, k, l, t2, W);
+                    else if (warp == 2)
+                        v = shape_out<5>(sm, T, k, l, t2, W) + shape_out<8>(sm, T, k, l, t2, W);
+                    else if (warp == 3)
+                        v = shape_out<3>(sm, T, k, l, t2, W) + shape_out<0>(sm, T, k, l, t2, W);
                     else
-                        v = shape_out<5>(sm, T, k, l, t2, W) + shape_out<3>(sm, T, k, l, t2, W) + shape_out<8>(sm, T, k, l, t2, W);
-                    sm.partS1a[warp][k] = v;
+                        v = shape_out<2>(sm, T, k, l, t2, W);
+                    (warp < 4 ? sm.partS1a[warp] : sm.ecol)[k] = v;
                 }
-            } else if (warp == 3) {
+            } else if (warp == 5) {
                 // G1[k] = sum_{i<k} X1[i] eMLb[k-1-i] = eMLb[k-1] * (prefix sum of X1[i] ainv[i])
                 const double(*x1c)[PP] = sm.u.x1buf[l & 1];
                 double tk[4], tot = 0.;
@@ -651,7 +686,7 @@ pf2_kernel(PfLaunch L, const MfeTables *__restrict__ MT, const PfTables *__restr
                     if (k < P2) sm.g1[k] = k >= 1 ? run * sm.emlb[k - 1] : 0.;
                     run += tk[z];
                 }
-            } else if (warp == 4) {
+            } else if (warp == 6) {
                 // q3[l] for the next column
                 double a3 = 0.;
                 for (int j = l + TURN + 1 + lane; j < W; j += 32) {
@@ -660,9 +695,9 @@ pf2_kernel(PfLaunch L, const MfeTables *__restrict__ MT, const PfTables *__restr
                 }
                 a3 = warp_sum(a3);
                 if (lane == 0) sm.q3[l] = sm.q3[l + 1] * sc1 + a3;
-            } else if (warp < 5 + NH) {
+            } else if (warp < 7 + NH) {
                 // H[k] = sum_{i <= k-6} (X1+X2)[i] qm[i+1,k-1]: i = g, g + NH, ..; lane = cell in four blocks
-                const int g = warp - 5;
+                const int g = warp - 7;
                 double a0 = 0., a1 = 0., a2 = 0., a3 = 0.;
                 const int kmax = l - TURN - 1;   // cells k <= kmax
                 const double *r0 = sm.qm + qmrow(max(lane - 1, 0)) + 1, *r1 = sm.qm + qmrow(lane + 31) + 1;
@@ -687,12 +722,14 @@ pf2_kernel(PfLaunch L, const MfeTables *__restrict__ MT, const PfTables *__restr
             } else {
                 x1_rows(xj0, xjm);
             }
+            PF2_UNIT(1)
             {
                 const int n = sm.cnt[sl];
                 const int ixM = lane == 0 ? PR_TAU : (lane == 1 ? PR_MM1 : PR_MMI);
-                // the cells are dealt in rounds of 23: one to every warp, the warps with the shortest unit (H) first and again
-                const int o1 = warp >= 5 && warp < 12 ? warp - 5 : (warp < 3 ? warp + 7 : (warp == 3 ? 10 : (warp == 4 ? 15 : warp - 1)));
-                const int o2 = warp >= 5 && warp < 12 ? warp + 11 : 1 << 20;
+                // the cells are dealt in rounds of 23 by the length of the warp's unit, shortest first (4 5 6 8 9 10 11 | 7 0 1 2 3
+                // | X1 streamers 12-15); the first seven take a second one
+                const int o1 = warp == 4 ? 0 : (warp == 5 ? 1 : (warp == 6 ? 2 : (warp >= 8 && warp < 12 ? warp - 5 : (warp == 7 ? 7 : (warp < 4 ? warp + 8 : warp)))));
+                const int o2 = o1 < 7 ? o1 + 16 : 1 << 20;
                 for (int cc = o1; cc < n; cc = (cc % 23 == o1 && o2 < 23) ? cc - o1 + o2 : cc - cc % 23 + 23 + o1) {
                     const int k = sm.list[sl][cc];
                     const int t2 = rtype_of(pair_type(S[k], S[l])), a = S[l + 1], b = S[k - 1];
@@ -717,7 +754,7 @@ pf2_kernel(PfLaunch L, const MfeTables *__restrict__ MT, const PfTables *__restr
                         const int t = pair_type(S[k], S[l]);
                         const double fx = TH->ext[t][Sx[k]][Sx[l + 2]];
                         if (k >= 1 && l <= W - 2) {
-                            Pv = sm.partA[k] + sm.partS1a[0][k] + sm.partS1a[1][k] + sm.partS1a[2][k];
+                            Pv = sm.partA[k] + sm.partS1a[0][k] + sm.partS1a[1][k] + sm.partS1a[2][k] + sm.partS1a[3][k] + sm.ecol[k];
                             double ml = sm.g1[k];
 #pragma unroll
                             for (int g = 0; g < NH; g++) ml += sm.partC[g][k];
@@ -802,6 +839,8 @@ pf2_kernel(PfLaunch L, const MfeTables *__restrict__ MT, const PfTables *__restr
         if (blockIdx.x == 0 && fold == 0 && lane == 0)
             printf("pf2 timing warp %2d: inside p1 %lld wait %lld p2 %lld wait %lld | outside p1 %lld wait %lld p2 %lld wait %lld\n", warp,
                    tacc[0], tacc[1], tacc[2], tacc[3], tacc[4], tacc[5], tacc[6], tacc[7]);
+        if (blockIdx.x == 0 && fold == 0 && lane == 0)
+            printf("pf2 units  warp %2d: inside p1 unit %lld | outside p1 unit %lld\n", warp, tunit[0], tunit[1]);
         if (blockIdx.x == 0 && fold == 0 && lane == 0)
             printf("pf2 probes warp %2d: outside setup+other %lld walk %lld tail %lld\n", warp, tprobe[0], tprobe[1], tprobe[2]);
 #endif
