@@ -39,9 +39,9 @@ WORKLOADS = {
     "C2x4": (4 * 29903, 120, 1, 100, "mono", (0.299, 0.184, 0.196, 0.321), 1002),
 }
 # DRAM bytes per 120-nt fold of mfe3_kernel, from the ncu --set full capture named below (not measured in the run)
-MFE3_DRAM_BYTES_PER_FOLD = 125.0
+MFE3_DRAM_BYTES_PER_FOLD = 123.0
 MFE3_TRAFFIC_SOURCE = ("dram__bytes_read.sum + dram__bytes_write.sum per fold from the ncu capture "
-                       "profiles/r01t_mfe3_kernel_ncu.txt (25.0 MB per 200,000 folds), x folds per step")
+                       "profiles/r02y_mfe3_kernel_ncu.txt (24.8 MB per 202,000 folds), x folds per step")
 
 
 def synth_record(name):
