@@ -129,8 +129,45 @@ def scan_record(seq, W=120, step=1, r=100, shuffle_type="mono", seed=42, parity_
         n_windows = total - first_window
     if final_window is None:
         final_window = first_window + n_windows == total
-    res = engine.scan(seq, W, step, r, shuffle_type=shuffle_type, seed=seed, parity_shuffles=parity_shuffles,
-                      temperature=temperature, max_span=max_span, hc=hc, react=react, shape_m=shape_m,
-                      shape_b=shape_b, first_window=first_window, n_windows=n_windows, final_window=final_window,
-                      want_pf=want_pf, background_temperature=background_temperature)
-    return table_from_result(res, first_window, step, n_windows, final_window)
+    kw = dict(shuffle_type=shuffle_type, seed=seed, temperature=temperature, max_span=max_span, hc=hc, react=react,
+              shape_m=shape_m, shape_b=shape_b, want_pf=want_pf, background_temperature=background_temperature)
+    if n_windows <= PIPELINE_WINDOWS:
+        res = engine.scan(seq, W, step, r, parity_shuffles=parity_shuffles, first_window=first_window,
+                          n_windows=n_windows, final_window=final_window, **kw)
+        return table_from_result(res, first_window, step, n_windows, final_window)
+    # Long shards go through the engine in parts of PIPELINE_WINDOWS windows: while the GPU folds part k+1 (the ctypes
+    # call releases the GIL) a worker thread turns part k into its table (z / p statistics, rounding).  Philox shuffles are
+    # keyed by the absolute window index, so the result does not depend on the split.
+    from concurrent.futures import ThreadPoolExecutor
+    tables, fut, done = [], None, 0
+    with ThreadPoolExecutor(max_workers=1) as pool:
+        while done < n_windows:
+            n = min(PIPELINE_WINDOWS, n_windows - done)
+            fin = bool(final_window) and done + n == n_windows
+            par = None if parity_shuffles is None else parity_shuffles[done:done + n + (1 if fin else 0)]
+            res = engine.scan(seq, W, step, r, parity_shuffles=par, first_window=first_window + done, n_windows=n,
+                              final_window=fin, **kw)
+            if fut is not None:
+                tables.append(fut.result())
+            fut = pool.submit(table_from_result, res, first_window + done, step, n, fin)
+            done += n
+        tables.append(fut.result())
+    return concat_tables(tables)
+
+
+PIPELINE_WINDOWS = 32768
+
+
+def concat_tables(tables):
+    """window tables of consecutive parts of one shard -> one table"""
+    t = WindowTable()
+    a = tables[0]
+    t.W, t.r, t.step, t.first_window = a.W, a.r, a.step, a.first_window
+    for f in ("start1", "end1", "mfe_dcal", "mfe", "z", "p", "ed", "native_unconstrained_dcal", "shuffle_dcal",
+              "pair_tbl", "centroid_tbl"):
+        setattr(t, f, np.concatenate([getattr(x, f) for x in tables]))
+    t.final = tables[-1].final
+    t.ms_total = sum(x.ms_total for x in tables)
+    t.ms_mfe = sum(x.ms_mfe for x in tables)
+    t.n_launches = sum(x.n_launches for x in tables)
+    return t

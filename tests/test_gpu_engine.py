@@ -482,3 +482,27 @@ def test_temperature_rescaling(engine, oracle, T):
         assert [int(x) for x in e] == [oracle.mfe(x, structure=False)[0] for x in s]
     finally:
         oracle.set_temperature(37.0)
+
+
+def test_scan_record_in_pipelined_parts_equals_one_call(engine, monkeypatch):
+    """scan.scan_record splits long shards into parts (host statistics of part k overlap the folds of part k+1): same
+    table as one engine call, device shuffles (Philox by absolute window) and parity shuffles alike, final-window set
+    included, also for a window range that starts inside the record"""
+    from scanfold_b200 import scan
+    rng = np.random.default_rng(17)
+    seq = "".join("ACGU"[k] for k in rng.integers(0, 4, 420))
+    W, step, r = 40, 3, 6
+    total = scan.n_windows_of(len(seq), W, step)
+    par = rng.integers(0, 4, (total + 1, r, W)).astype(np.uint8)
+    par = np.frombuffer(b"ACGU", dtype=np.uint8)[par]
+    fields = ("start1", "end1", "mfe_dcal", "mfe", "z", "p", "ed", "native_unconstrained_dcal", "shuffle_dcal", "pair_tbl", "centroid_tbl")
+    for kw in (dict(), dict(parity_shuffles=par), dict(first_window=7, n_windows=total - 7, shuffle_type="di"),
+               dict(first_window=5, n_windows=60)):
+        monkeypatch.setattr(scan, "PIPELINE_WINDOWS", 1 << 30)
+        one = scan.scan_record(seq, W, step, r, seed=9, **kw)
+        monkeypatch.setattr(scan, "PIPELINE_WINDOWS", 37)
+        parts = scan.scan_record(seq, W, step, r, seed=9, **kw)
+        assert len(parts) == len(one)
+        for f in fields:
+            assert np.array_equal(getattr(one, f), getattr(parts, f)), (f, kw.keys())
+        assert one.final == parts.final
