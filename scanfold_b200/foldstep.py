@@ -85,7 +85,8 @@ def _exact_mean(a, b, n):
     x100 = m * 100.0
     x1e6 = m * 1e6
     risky = (np.abs(x100 - np.floor(x100) - 0.5) < 1e-6) | (np.abs(x1e6 - np.floor(x1e6) - 0.5) < 1e-3)
-    risky |= (np.abs(m[:, None] - _THRESHOLDS[None, :]) < 1e-9).any(axis=1)
+    for t in _THRESHOLDS:
+        risky |= np.abs(m - t) < 1e-9
     for k in np.nonzero(risky)[0]:
         num = (int(a[k]) << 39) + int(b[k])
         m[k] = num / (int(n[k]) << 59)          # int / int is correctly rounded in Python
@@ -112,9 +113,11 @@ def aggregate(table, seq, log_total=None, sirna_log=None, by_ed=False):
     own = np.repeat(table.coord, np.diff(ptr))
     cnt = table.count
     sum_z = _exact_sum(table.sums[4], table.sums[5]) if by_ed else _exact_sum(table.sums[0], table.sums[1])
-    mean_z = _exact_mean(table.sums[0], table.sums[1], cnt)
-    mean_mfe = _exact_mean(table.sums[2], table.sums[3], cnt)
-    mean_ed = _exact_mean(table.sums[4], table.sums[5], cnt)
+    want_logs = log_total is not None or sirna_log is not None
+    if want_logs:      # the log prints the means of every partner entry; otherwise only the best partner's are needed
+        mean_z = _exact_mean(table.sums[0], table.sums[1], cnt)
+        mean_mfe = _exact_mean(table.sums[2], table.sums[3], cnt)
+        mean_ed = _exact_mean(table.sums[4], table.sums[5], cnt)
     total_windows = np.add.reduceat(cnt, ptr[:-1]) if M else np.zeros(0, dtype=np.int64)
     num_bp = np.add.reduceat((table.partner != own).astype(np.int64), ptr[:-1])
     cov_z = sum_z / np.repeat(total_windows, np.diff(ptr))
@@ -124,7 +127,7 @@ def aggregate(table, seq, log_total=None, sirna_log=None, by_ed=False):
     idx = np.arange(M, dtype=np.int64)
     best = np.minimum.reduceat(np.where(is_min, idx, M), ptr[:-1])
 
-    if log_total is not None or sirna_log is not None:
+    if want_logs:
         _write_logs(table, seq, own, cnt, sum_z, mean_z, mean_mfe, mean_ed, cov_z, total_windows, num_bp,
                     log_total, sirna_log, by_ed)
 
@@ -133,9 +136,13 @@ def aggregate(table, seq, log_total=None, sirna_log=None, by_ed=False):
     res.coord = table.coord
     res.part = table.partner[best]
     res.cov_z = cov_z[best]
-    res.mean_z = mean_z[best]
-    res.mean_mfe = mean_mfe[best]
-    res.mean_ed = mean_ed[best]
+    if want_logs:
+        res.mean_z, res.mean_mfe, res.mean_ed = mean_z[best], mean_mfe[best], mean_ed[best]
+    else:
+        cb = cnt[best]
+        res.mean_z = _exact_mean(table.sums[0][best], table.sums[1][best], cb)
+        res.mean_mfe = _exact_mean(table.sums[2][best], table.sums[3][best], cb)
+        res.mean_ed = _exact_mean(table.sums[4][best], table.sums[5][best], cb)
     res.total_windows = np.asarray(total_windows, dtype=np.int64)
     res.num_bp = np.asarray(num_bp, dtype=np.int64)
     return res
