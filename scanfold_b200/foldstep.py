@@ -152,27 +152,56 @@ def _r2(x):
     return str(round(float(x), 2))
 
 
+def _r2_list(values):
+    """[str(round(float(x), 2)) for x in values], vectorised: the two-decimal value is an integer number of hundredths
+    (a few thousand distinct ones per record), formatted once each by Python itself; anything close to a rounding
+    boundary, not finite or large goes through round() directly"""
+    v = np.asarray(values, dtype=np.float64)
+    with np.errstate(invalid="ignore", over="ignore"):
+        x = v * 100.0
+        k = np.rint(x)
+        slow = ~np.isfinite(v) | (np.abs(v) > 1e9) | (np.abs(x - np.floor(x) - 0.5) < 1e-6)
+    ki = np.where(slow, 0, k).astype(np.int64)
+    neg0 = (ki == 0) & (np.signbit(v) | np.signbit(k))      # round(-0.001, 2) is -0.0 and prints "-0.0"
+    uniq, inv = np.unique(ki, return_inverse=True)
+    table = np.array([str(u / 100.0) for u in uniq.tolist()], dtype=object)
+    out = table[inv]
+    out[neg0] = "-0.0"
+    for m in np.nonzero(slow)[0]:
+        out[m] = str(round(float(v[m]), 2))
+    return out.tolist()
+
+
 def _write_logs(table, seq, own, cnt, sum_z, mean_z, mean_mfe, mean_ed, cov_z, total_windows, num_bp, log_total,
                 sirna_log, by_ed=False):
     """log lines of ScanFold.py:1150-1184; --by_ed: :1155-1159,1190-1212 (sum_z / cov_z then hold the ED sums; the column
-    order avgMFE, avgZ, avgED is the same in both modes)"""
-    ptr = table.nt_ptr
+    order avgMFE, avgZ, avgED is the same in both modes).  One string per partner entry is assembled column-wise (the
+    record's log has a line per entry: 10^6 for a 30-kb genome), then cut per nucleotide."""
+    ptr = table.nt_ptr.tolist()
     partner = table.partner
-    out = []
-    sirna = []
     head = "SumED\tSumED/#TotalWindows" if by_ed else "SumZ\tSumZ/#TotalWindows"
     coord = table.coord.tolist()
+    sq = np.frombuffer(seq.encode(), dtype="S1")
+    own_s = list(map(str, np.asarray(own).tolist()))
+    part_l = partner.tolist()
+    bp_s = ["NoBP" if j == k else str(j) for j, k in zip(part_l, np.asarray(own).tolist())]
+    nuc_j = sq[partner - 1].astype("U1").tolist()
+    cols = (own_s, bp_s, nuc_j, list(map(str, np.asarray(cnt).tolist())), _r2_list(mean_mfe), _r2_list(mean_z),
+            _r2_list(mean_ed), _r2_list(sum_z), _r2_list(cov_z))
+    lines = list(map("\t".join, zip(*cols)))
+    out = []
+    sirna = []
+    tw = np.asarray(total_windows).tolist()
+    nb = np.asarray(num_bp).tolist()
     for k0 in range(table.n_nt):
         k = coord[k0]
         nuc = seq[k - 1]
-        out.append("\ni-nuc\tBP(j)\tNuc\t#BP_Win\tavgMFE\tavgZ\tavgED\t%s\tBPs= %d\n" % (head, num_bp[k0]))
-        out.append("nt-%d\t-\t%s\t%d\t-\t-\t-\t-\t-\n" % (k, nuc, total_windows[k0]))
-        sirna.append("%d\t%s\t%d\t%d\n" % (k, nuc, total_windows[k0], num_bp[k0]))
-        for m in range(ptr[k0], ptr[k0 + 1]):
-            j = int(partner[m])
-            tail = "%s\t%d\t%s\t%s\t%s\t%s\t%s\n" % (seq[j - 1], cnt[m], _r2(mean_mfe[m]), _r2(mean_z[m]),
-                                                     _r2(mean_ed[m]), _r2(sum_z[m]), _r2(cov_z[m]))
-            out.append(("%d\tNoBP\t" % k if j == k else "%d\t%d\t" % (k, j)) + tail)
+        out.append("\ni-nuc\tBP(j)\tNuc\t#BP_Win\tavgMFE\tavgZ\tavgED\t%s\tBPs= %d\n" % (head, nb[k0]))
+        out.append("nt-%d\t-\t%s\t%d\t-\t-\t-\t-\t-\n" % (k, nuc, tw[k0]))
+        sirna.append("%d\t%s\t%d\t%d\n" % (k, nuc, tw[k0], nb[k0]))
+        if ptr[k0 + 1] > ptr[k0]:
+            out.append("\n".join(lines[ptr[k0]:ptr[k0 + 1]]))
+            out.append("\n")
     if log_total is not None:
         log_total.write("".join(out))
     if sirna_log is not None:
