@@ -16,8 +16,12 @@
 //   the bulge / 1xn copy, every other lane the generic one; u1 = 0, 1 are peeled the same way.
 // * everything else of a column runs beside that walk or in ONE second phase as warp-sized units (two barriers per
 //   column): the multiloop sums as row-sliced matrix-vector products with four independent accumulators per lane,
-//   the nine table-driven shapes and the hairpin of the NEXT column (lane = cell, all table loads issued together),
-//   the geometric sums as warp scans, the exterior sums, the ring bookkeeping.
+//   the nine table-driven shapes and the hairpin of the NEXT column by item (lane = listed cell, the table loads of an
+//   item pair issued together; tabulated tri- / tetra- / hexaloops by a warp-wide key search), the geometric sums as warp
+//   scans, the exterior sums, the per-cell outer factors (`prm` rows), the ring bookkeeping; X1 streams PM from L2 two
+//   columns ahead on four warps.  Cells are dealt to the warps in weighted rounds by the length of the unit the warp
+//   also runs in that phase.  A lone warp in dependent code advances at 10-25 cycles per instruction (LDS 30, a double
+//   warp_sum 191, L2 369 cycles: tools/scratch/lat.cu), so the longest per-warp chain of a phase is what is balanced.
 // qm lives in a folded triangular matrix with an odd pitch (row and column walks are both bank-conflict free).
 // Only qb (read back once per cell) and the multiloop closing weights PM (read as rows) stream through L2.
 #include <cstdlib>
@@ -209,13 +213,6 @@ __device__ __forceinline__ double shape_out(const Smem2 &sm, const PfTables *T, 
         tpar ^= 1;                                                                         \
     }
 #define PF2_RESET asm volatile("mov.u64 %0, %%clock64;" : "=l"(tlast)::"memory");
-#define PF2_PROBE(k)                                                    \
-    {                                                                   \
-        long long now_;                                                 \
-        asm volatile("mov.u64 %0, %%clock64;" : "=l"(now_)::"memory"); \
-        tprobe[k] += now_ - tp_;                                        \
-        tp_ = now_;                                                     \
-    }
 #define PF2_UNIT(k)                                                     \
     {                                                                   \
         long long now_;                                                 \
@@ -223,7 +220,6 @@ __device__ __forceinline__ double shape_out(const Smem2 &sm, const PfTables *T, 
         tunit[k] += now_ - tlast;                                       \
     }
 #else
-#define PF2_PROBE(k)
 #define PF2_UNIT(k)
 #define PF2_SYNC(slot) __syncthreads();
 #define PF2_RESET
@@ -244,7 +240,6 @@ pf2_kernel(PfLaunch L, const MfeTables *__restrict__ MT, const PfTables *__restr
     long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tlast;
     int tpar = 0;
     long long tunit[2] = {0, 0};
-    long long tprobe[4] = {0, 0, 0, 0}, tp_ = 0;
     asm volatile("mov.u64 %0, %%clock64;" : "=l"(tlast)::"memory");
 #endif
 
@@ -841,8 +836,6 @@ pf2_kernel(PfLaunch L, const MfeTables *__restrict__ MT, const PfTables *__restr
                    tacc[0], tacc[1], tacc[2], tacc[3], tacc[4], tacc[5], tacc[6], tacc[7]);
         if (blockIdx.x == 0 && fold == 0 && lane == 0)
             printf("pf2 units  warp %2d: inside p1 unit %lld | outside p1 unit %lld\n", warp, tunit[0], tunit[1]);
-        if (blockIdx.x == 0 && fold == 0 && lane == 0)
-            printf("pf2 probes warp %2d: outside setup+other %lld walk %lld tail %lld\n", warp, tprobe[0], tprobe[1], tprobe[2]);
 #endif
     }
 }
