@@ -63,7 +63,8 @@ struct Smem2 {
     PfHead th;
     double ring[3 * RING];      // generic | 1xn | bulge copies, [position + RPAD][column & 31]
     double ringq[8][P2];        // raw qb (inside) / raw P (outside) of the last columns: table-driven shapes
-    double qm[QROWS * PQ];      // folded: row = 3' end k', entries i <= k'-4
+    double qm[QROWS * PQ + 128]; // folded: row = 3' end k', entries i <= k'-4; the row walks of the matrix-vector units load
+                                // up to 65 doubles past the last row's last entry (masked): the pad keeps them inside the array
     double partC[NG][PP];       // partial multiloop sums (inside: qq; outside: H)
     double prm[PP][PRW];        // per listed cell: the outer factors the candidate walk's reduction and stores need
     double partA[PP];           // outside: interior-loop sum of the listed cells
@@ -512,7 +513,7 @@ pf2_kernel(PfLaunch L, const MfeTables *__restrict__ MT, const PfTables *__restr
                     const double tau = r[PR_TAU], mm1 = r[PR_MM1];
                     const double mulM = r[ixM], ext = ebase[i * estride] * r[ixE], fm = r[ixF];
                     const double fa = i <= j - TURN - 2 ? qm1p[i] * emlL : 0.;
-                    const double *pb = sm.ring + (i + 1 + RPAD) * PT + ((j - 1 - lane) & 31);
+                    const double *pb = sm.ring + (i + 1 + RPAD) * PT + ((j - 1 - min(lane, MAXLOOP)) & 31);   // (lane 31 has no candidate: not the column being written)
                     double accB, acc1;
                     const double aM = cand_walk<false>(pb + 2 * RING, pb + RING, pb + cls * RING, min(MAXLOOP, j - i - 6), lo, K, accB, acc1);
                     double v = aM * mulM + accB * tau + acc1 * mm1 + ext;
@@ -730,7 +731,7 @@ pf2_kernel(PfLaunch L, const MfeTables *__restrict__ MT, const PfTables *__restr
                     const int t2 = rtype_of(pair_type(S[k], S[l])), a = S[l + 1], b = S[k - 1];
                     const double mmI = TH->expmismatchI[t2][a][b], mm1 = TH->expmismatch1nI[t2][a][b], tau = TH->tau[t2];
                     const double mulM = ixM == PR_TAU ? tau : (ixM == PR_MM1 ? mm1 : mmI);
-                    const double *pb = sm.ring + (k - 1 + RPAD) * PT + ((l + 1 + lane) & 31);
+                    const double *pb = sm.ring + (k - 1 + RPAD) * PT + ((l + 1 + min(lane, MAXLOOP)) & 31);
                     double accB, acc1;
                     const double aM = cand_walk<true>(pb + 2 * RING, pb + RING, pb + cls * RING, min(MAXLOOP, k - 1), lo, K, accB, acc1);
                     double v = aM * mulM + accB * tau + acc1 * mm1;
