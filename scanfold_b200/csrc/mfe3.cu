@@ -79,6 +79,28 @@ bool g_mfe3_ok = false;
 constexpr int BIG = 1 << 20;  // size term of a disabled tap: the sum never wins whatever the load returns
 
 
+// shared-memory accesses by 32-bit byte address: the interior-loop cell pass keeps one byte address per tap (row and
+// offset folded in once per diagonal) and adds the cell's scaled index -- one integer instruction per load instead of the
+// multiply-add + add the compiler emits when it rematerialises row * pitch + i per cell
+__device__ __forceinline__ int lds_s16(unsigned a) {
+    int v;
+    asm volatile("ld.shared.s16 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ unsigned lds_u32(unsigned a) {
+    unsigned v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ int4 lds_v4(unsigned a) {
+    int4 v;
+    asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts_u16(unsigned a, int v) {
+    asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((short)v));
+}
+
 template <int P, bool FMG = false>
 struct Smem3 {
     static constexpr int KSM = FMG ? 4 : 2;   // copies of the split-minimum ring
@@ -723,24 +745,26 @@ mfe3_kernel(MfeLaunch L, const MfeTables *__restrict__ T, const Tab3 *__restrict
         // ---- C (queue variant): interior loops of size >= 2 of the pairable cells c .. n-1 of diagonal d (d0+2 or d0+3;
         // rows <= d0-1): one cell per pass, lane = loop size U with its seven taps (see the header)
         auto unit_C = [&](int d, int c, int n) {
-            constexpr int stride = 1;
             const int slot = (d - 2 - UB) & (R32 - 1);
-            const short *qA = smb + kA + ((d - 2 - UA) & (R32 - 1)) * PR;
-            const short *qB10 = smb + O_M8 + 10 + ((d - 2 - UB10) & (R32 - 1)) * PR;
-            const short *qB18 = smb + O_M8 + 18 + ((d - 2 - UB18) & (R32 - 1)) * PR;
-            const short *qB26 = smb + O_M8 + 26 + ((d - 2 - UB26) & (R32 - 1)) * PR;
-            const short *qC = smb + kC + ((d - 2 - UC) & (R32 - 1)) * PR;
-            const unsigned *qR = sm.rpa + slot * PRW + 1;        // inner pair (i+1, j-1-U) and 1xn neighbour
-            const unsigned *qL = sm.rpq + slot * PRW + d - 1;    // inner pair (i+1+U, j-1) and 1xn neighbour
-            short *qP = sm.partc + (d & 3) * PR;
-            const int4 *lst = reinterpret_cast<const int4 *>(sm.list) + (d & 3) * LP;
-            int4 en = lst[c];
-            for (; c < n; c += stride) {
+            const unsigned sb = (unsigned)__cvta_generic_to_shared(smb);
+            const unsigned aA = sb + 2 * (kA + ((d - 2 - UA) & (R32 - 1)) * PR);
+            const unsigned aB10 = sb + 2 * (O_M8 + 10 + ((d - 2 - UB10) & (R32 - 1)) * PR);
+            const unsigned aB18 = sb + 2 * (O_M8 + 18 + ((d - 2 - UB18) & (R32 - 1)) * PR);
+            const unsigned aB26 = sb + 2 * (O_M8 + 26 + ((d - 2 - UB26) & (R32 - 1)) * PR);
+            const unsigned aC = sb + 2 * (kC + ((d - 2 - UC) & (R32 - 1)) * PR);
+            const unsigned aR = (unsigned)__cvta_generic_to_shared(sm.rpa + slot * PRW + 1);       // inner pair (i+1, j-1-U) and 1xn neighbour
+            const unsigned aL = (unsigned)__cvta_generic_to_shared(sm.rpq + slot * PRW + d - 1);   // inner pair (i+1+U, j-1) and 1xn neighbour
+            const unsigned aP = (unsigned)__cvta_generic_to_shared(sm.partc + (d & 3) * PR);
+            unsigned aLst = (unsigned)__cvta_generic_to_shared(reinterpret_cast<const int4 *>(sm.list) + (d & 3) * LP + c);
+            int4 en = lds_v4(aLst);
+            for (; c < n; c++) {
                 const int i = en.x, eI = en.y, e1 = en.z, eB = en.w;
-                en = lst[c + stride];   // next entry (at most `stride` past the list end: still inside sm.list)
-                const unsigned wr = qR[i], wl = qL[i];
-                const short *pa = qA + i, *pc = qC + i;
-                const int xa = pa[0], xb10 = qB10[i], xb18 = qB18[i], xb26 = qB26[i], xc = pc[0];
+                aLst += 16;
+                en = lds_v4(aLst);   // next entry (at most one past the list end: still inside sm.list)
+                const unsigned i2 = 2 * i, i4 = 4 * i;
+                const unsigned wr = lds_u32(aR + i4), wl = lds_u32(aL + i4);
+                const int xa = lds_s16(aA + i2), xb10 = lds_s16(aB10 + i2), xb18 = lds_s16(aB18 + i2);
+                const int xb26 = lds_s16(aB26 + i2), xc = lds_s16(aC + i2);
                 const unsigned wm = __vmins2(wr, wl);
                 const int xb = (int)(short)(wm & 0xffffu), x1 = (int)wm >> 16;
                 int g = xa + cA;
@@ -753,7 +777,7 @@ mfe3_kernel(MfeLaunch L, const MfeTables *__restrict__ T, const Tab3 *__restrict
                 v = __viaddmin_s32(a1, e1, v);
                 v = __viaddmin_s32(aB, eB, v);
                 v = __reduce_min_sync(full, v);
-                if (lane == 0) qP[i] = (short)v;   // <= INF16 + size and mismatch terms: fits
+                if (lane == 0) sts_u16(aP + i2, v);   // <= INF16 + size and mismatch terms: fits
             }
         };
 
@@ -818,7 +842,8 @@ mfe3_kernel(MfeLaunch L, const MfeTables *__restrict__ T, const Tab3 *__restrict
                 }
                 // ---- C: interior loops of size >= 2 of the pairable cells of diagonals d0+2, d0+3 (rows <= d0-1): one
                 // cell per pass, lane = loop size U with its seven taps (see the header).  The cells continue the round
-                // robin of the units above.  (Same walk as unit_C; kept inline: as a lambda it costs 2.6 % at 120 nt.)
+                // robin of the units above.  (Same walk as unit_C; kept inline: as a lambda it costs 2.6 % at 120 nt.)  One byte
+                // address per tap, the cell's scaled index added per load (+1 % at 120 nt, +2.4 % at 64 / 200 nt).
                 int c = warp - nH % NW;
                 if (c < 0) c += NW;
 #pragma unroll 1
@@ -826,22 +851,25 @@ mfe3_kernel(MfeLaunch L, const MfeTables *__restrict__ T, const Tab3 *__restrict
                     const int d = d0 + 2 + ds, n = ds ? n3 : n2;
                     if (c < n) {
                         const int slot = (d - 2 - UB) & (R32 - 1);
-                        const short *qA = smb + kA + ((d - 2 - UA) & (R32 - 1)) * PR;
-                        const short *qB10 = smb + O_M8 + 10 + ((d - 2 - UB10) & (R32 - 1)) * PR;
-                        const short *qB18 = smb + O_M8 + 18 + ((d - 2 - UB18) & (R32 - 1)) * PR;
-                        const short *qB26 = smb + O_M8 + 26 + ((d - 2 - UB26) & (R32 - 1)) * PR;
-                        const short *qC = smb + kC + ((d - 2 - UC) & (R32 - 1)) * PR;
-                        const unsigned *qR = sm.rpa + slot * PRW + 1;        // inner pair (i+1, j-1-U) and 1xn neighbour
-                        const unsigned *qL = sm.rpq + slot * PRW + d - 1;    // inner pair (i+1+U, j-1) and 1xn neighbour
-                        short *qP = sm.partc + (d & 3) * PR;
-                        const int4 *lst = reinterpret_cast<const int4 *>(sm.list) + (d & 3) * LP;
-                        int4 en = lst[c];
+                        const unsigned sb = (unsigned)__cvta_generic_to_shared(smb);
+                        const unsigned aA = sb + 2 * (kA + ((d - 2 - UA) & (R32 - 1)) * PR);
+                        const unsigned aB10 = sb + 2 * (O_M8 + 10 + ((d - 2 - UB10) & (R32 - 1)) * PR);
+                        const unsigned aB18 = sb + 2 * (O_M8 + 18 + ((d - 2 - UB18) & (R32 - 1)) * PR);
+                        const unsigned aB26 = sb + 2 * (O_M8 + 26 + ((d - 2 - UB26) & (R32 - 1)) * PR);
+                        const unsigned aC = sb + 2 * (kC + ((d - 2 - UC) & (R32 - 1)) * PR);
+                        const unsigned aR = (unsigned)__cvta_generic_to_shared(sm.rpa + slot * PRW + 1);       // inner pair (i+1, j-1-U) and 1xn neighbour
+                        const unsigned aL = (unsigned)__cvta_generic_to_shared(sm.rpq + slot * PRW + d - 1);   // inner pair (i+1+U, j-1) and 1xn neighbour
+                        const unsigned aP = (unsigned)__cvta_generic_to_shared(sm.partc + (d & 3) * PR);
+                        unsigned aLst = (unsigned)__cvta_generic_to_shared(reinterpret_cast<const int4 *>(sm.list) + (d & 3) * LP + c);
+                        int4 en = lds_v4(aLst);
                         for (; c < n; c += NW) {
                             const int i = en.x, eI = en.y, e1 = en.z, eB = en.w;
-                            en = lst[c + NW];   // next entry (at most NW past the list end: still inside sm.list)
-                            const unsigned wr = qR[i], wl = qL[i];
-                            const short *pa = qA + i, *pc = qC + i;
-                            const int xa = pa[0], xb10 = qB10[i], xb18 = qB18[i], xb26 = qB26[i], xc = pc[0];
+                            aLst += NW * 16;
+                            en = lds_v4(aLst);   // next entry (at most NW past the list end: still inside sm.list)
+                            const unsigned i2 = 2 * i, i4 = 4 * i;
+                            const unsigned wr = lds_u32(aR + i4), wl = lds_u32(aL + i4);
+                            const int xa = lds_s16(aA + i2), xb10 = lds_s16(aB10 + i2), xb18 = lds_s16(aB18 + i2);
+                            const int xb26 = lds_s16(aB26 + i2), xc = lds_s16(aC + i2);
                             const unsigned wm = __vmins2(wr, wl);
                             const int xb = (int)(short)(wm & 0xffffu), x1 = (int)wm >> 16;
                             int g = xa + cA;
@@ -854,7 +882,7 @@ mfe3_kernel(MfeLaunch L, const MfeTables *__restrict__ T, const Tab3 *__restrict
                             v = __viaddmin_s32(a1, e1, v);
                             v = __viaddmin_s32(aB, eB, v);
                             v = __reduce_min_sync(full, v);
-                            if (lane == 0) qP[i] = (short)v;   // <= INF16 + size and mismatch terms: fits
+                            if (lane == 0) sts_u16(aP + i2, v);   // <= INF16 + size and mismatch terms: fits
                         }
                     }
                     c -= n;
