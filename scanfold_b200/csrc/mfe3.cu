@@ -508,32 +508,34 @@ mfe3_kernel(MfeLaunch L, const MfeTables *__restrict__ T, const Tab3 *__restrict
         const int x = sg * SEG - 7 + lane;
         const bool valid = x >= 0 && x < ncells;
         const int i = valid ? x : 0, j = i + d;
-        const int t = valid ? tb.ptype[sm.sx5[i + 1] * 6 + sm.sx3[j + 1]] : 0;
-        int e = INF16;
-        if (t) {
-            e = min((int)sm.partc[(d & 3) * PR + i], (int)sm.parts[(d & 3) * PR + i]);
-            if (d - 2 > TURN) {   // stack: inner pair (i+1, j-1)
-                const int o = ((d - 2) & (R16 - 1)) * PR + i + 1;
-                int es = sm.rc[o] + tb.stack[t * 8 + sm.ctx[o]];
-                if (L.sc) es += sm.scp[i] + sm.scp[j - 1];   // Deigan pseudo-energy of the stack (kernel-uniform branch)
-                e = min(e, es);
-            }
-            if (d - 3 > TURN) {   // bulge of one: inner pairs (i+1, j-2) and (i+2, j-1)
-                const int o = ((d - 3) & (R16 - 1)) * PR + i + 1;
-                const int b0 = sm.rc[o] + tb.stack[t * 8 + sm.ctx[o]], b1 = sm.rc[o + 1] + tb.stack[t * 8 + sm.ctx[o + 1]];
-                e = min(e, min(b0, b1) + tb.bulge1);
-            }
-            const int dm = decof(d - 2, i + 1);   // multiloop closed by (i,j)
-            e = min(e, dm + tb.mlclose[(tb.rtype[t] * 5 + sx[j]) * 5 + sx[i + 2]]);
-            if (e >= FIN16) e = INF16;
-        }
-        int vg = INF16, v1 = INF16, vb = INF16;
+        // every load whose address does not depend on the pair type is issued before the type is known, the table lookups
+        // that do in one second round: three dependent shared-memory round trips instead of five (a lane that is no pair or
+        // sits outside the row reads valid but meaningless entries and is masked)
+        const int c5 = sm.sx5[i + 1], c3 = sm.sx3[j + 1];
+        const int pc = sm.partc[(d & 3) * PR + i], ps = sm.parts[(d & 3) * PR + i];
+        const int o2 = ((d - 2) & (R16 - 1)) * PR + i + 1, o3 = ((d - 3) & (R16 - 1)) * PR + i + 1;
+        const int rc2 = sm.rc[o2], cx2 = sm.ctx[o2];
+        const int rc3a = sm.rc[o3], cx3a = sm.ctx[o3], rc3b = sm.rc[o3 + 1], cx3b = sm.ctx[o3 + 1];
+        const int dm = decof(d - 2, i + 1);   // multiloop closed by (i,j)
+        const int si0 = sx[i], si2 = sx[i + 2], sj0 = sx[j], sj2 = sx[j + 2];
+        int scs = 0;
+        if (L.sc) scs = sm.scp[i] + sm.scp[j - 1];   // Deigan pseudo-energy of the stack (kernel-uniform branch)
+        const int t = valid ? tb.ptype[c5 * 6 + c3] : 0;
         const int t2 = tb.rtype[t];
+        const int st2 = tb.stack[t * 8 + cx2], st3a = tb.stack[t * 8 + cx3a], st3b = tb.stack[t * 8 + cx3b];
+        const int mlc = tb.mlclose[(t2 * 5 + sj0) * 5 + si2];
+        const int m2 = (t2 * 5 + sj2) * 5 + si0;
+        const int xI = tb.mmI[m2], x1n = tb.mm1n[m2], xAU = tb.tAU[t2];
+        int e = min(pc, ps);
+        if (d - 2 > TURN) e = min(e, rc2 + st2 + scs);                            // stack: inner pair (i+1, j-1)
+        if (d - 3 > TURN) e = min(e, min(rc3a + st3a, rc3b + st3b) + tb.bulge1);   // bulge of one: (i+1, j-2) and (i+2, j-1)
+        e = min(e, dm + mlc);
+        if (!t || e >= FIN16) e = INF16;
+        int vg = INF16, v1 = INF16, vb = INF16;
         if (t && i > 0 && j < W - 1 && e < FIN16) {
-            const int m2 = (t2 * 5 + sx[j + 2]) * 5 + sx[i];
-            vg = e + tb.mmI[m2];
-            v1 = e + tb.mm1n[m2];
-            vb = e + tb.tAU[t2];
+            vg = e + xI;
+            v1 = e + x1n;
+            vb = e + xAU;
         }
         const int g1 = __shfl_up_sync(full, vg, 1), g2 = __shfl_up_sync(full, vg, 2);
         const int g3 = __shfl_up_sync(full, vg, 3), g4 = __shfl_up_sync(full, vg, 4);
