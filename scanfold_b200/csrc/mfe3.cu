@@ -428,18 +428,28 @@ mfe3_kernel(MfeLaunch L, const MfeTables *__restrict__ T, const Tab3 *__restrict
 
     // compacted list of the pairable cells of diagonal d with the closing-pair terms (one warp) -> slot d & 3
     auto build_list = [&](int d) {
-        int nl = 0;
         const int ncells = W - d, slot = d & 3;
-        for (int i0 = 0; i0 < ncells; i0 += 32) {
-            const int i = i0 + lane;
-            const int t = i < ncells ? tb.ptype[sm.sx5[i + 1] * 6 + sm.sx3[i + d + 1]] : 0;
-            const unsigned m = __ballot_sync(full, t != 0);
-            if (t) {
-                const int mi = (t * 5 + sx[i + 2]) * 5 + sx[i + d];
-                const int4 en = make_int4(i, tb.mmI[mi], tb.mm1n[mi], tb.tAU[t]);
-                reinterpret_cast<int4 *>(sm.list)[slot * LP + nl + __popc(m & ((1u << lane) - 1))] = en;
+        constexpr int NCH = (P + 31) / 32;
+        // pair types of every chunk of 32 cells first (independent loads), then the compaction chunk by chunk
+        int tt[NCH];
+#pragma unroll
+        for (int k = 0; k < NCH; k++) {
+            const int i = k * 32 + lane;
+            tt[k] = i < ncells ? tb.ptype[sm.sx5[i + 1] * 6 + sm.sx3[i + d + 1]] : 0;
+        }
+        int nl = 0;
+#pragma unroll
+        for (int k = 0; k < NCH; k++) {
+            if (k * 32 < ncells) {   // warp-uniform
+                const int i = k * 32 + lane, t = tt[k];
+                const unsigned m = __ballot_sync(full, t != 0);
+                if (t) {
+                    const int mi = (t * 5 + sx[i + 2]) * 5 + sx[i + d];
+                    const int4 en = make_int4(i, tb.mmI[mi], tb.mm1n[mi], tb.tAU[t]);
+                    reinterpret_cast<int4 *>(sm.list)[slot * LP + nl + __popc(m & ((1u << lane) - 1))] = en;
+                }
+                nl += __popc(m);
             }
-            nl += __popc(m);
         }
         if (lane == 0) sm.cnt[slot] = nl;
     };
@@ -577,9 +587,14 @@ mfe3_kernel(MfeLaunch L, const MfeTables *__restrict__ T, const Tab3 *__restrict
             const int t = tb.rtype[sm.ctx[o16]];
             return e < FIN16 ? e + tb.mlstem[t * 36 + sx[xi] * 6 + sx[xi + d + 2]] : INF16;
         };
+        // the loads of both diagonals first (clamped positions, masked afterwards): the second cell only waits for the first
+        // one's value, not for its own operands
+        const int x1c = min(x, max(nc1 - 1, 0));
+        const int s0 = min(decof(dA, xx), stemof(dA, xx));
+        const int s1 = min(decof(dA + 1, x1c), stemof(dA + 1, x1c));
         int m0 = INF16;
         if (nc0 > 0) {
-            m0 = min(decof(dA, xx), stemof(dA, xx));
+            m0 = s0;
             if (dA - 1 > TURN)
                 m0 = min(m0, min((int)ldfm(fm + (xx + 1) * P + xx + dA), (int)ldfm(fm + xx * P + xx + dA - 1)) + tb.MLbase);
             if (m0 >= FIN16) m0 = INF16;
@@ -592,8 +607,7 @@ mfe3_kernel(MfeLaunch L, const MfeTables *__restrict__ T, const Tab3 *__restrict
         const int m0n = __shfl_down_sync(full, m0, 1);
         if (lane < 31 && x < nc1) {
             const int d = dA + 1;
-            int m1 = min(decof(d, x), stemof(d, x));
-            m1 = min(m1, min(m0, m0n) + tb.MLbase);
+            int m1 = min(s1, min(m0, m0n) + tb.MLbase);
             if (m1 >= FIN16) m1 = INF16;
             minv = min(minv, m1);
             fm[x * P + x + d] = (short)m1;
